@@ -1,0 +1,199 @@
+"""TEST INFRASTRUCTURE ONLY -- generate ``tests/golden/*.npz`` from the REAL reference.
+
+Run in the authoring container (needs ``/root/reference``):
+
+    python -m oracle.make_golden
+
+What runs here is the reference's own code, imported unmodified through
+``oracle/ref_shim.py``: ``Transducer.decode_greedy`` (models.py:369-455),
+``Transducer.transcribe_stream`` (models.py:457-577), ``Encoder`` /
+``Predictor`` / ``Joint`` ``forward`` (models.py:105-113, 181-187, 132-140).
+The reference's feature transforms cannot be imported (transforms.py needs
+fastai2 / fastcore / fastai2_audio), so the feature side of every fixture is
+produced with the very ``torchaudio.transforms.MelSpectrogram`` call the
+reference makes (transforms.py:290-296) followed by the literal tensor ops of
+``TransformTime`` / ``StreamPostprocess`` / ``StackDownsample`` / ``Buffer``
+(transforms.py:311-323, 335-342, 436-441, 463-471) and the serving window of
+api-server.py:26,83-115.
+
+Weights and audio are synthetic and seed-defined (``oracle/weights.py``), so the
+fixtures only store seeds plus the reference's OUTPUTS.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+import torchaudio
+
+from . import ref_shim, weights
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+WEIGHT_SEED = 1234
+CHUNK = 1280  # 80 ms @ 16 kHz (api-client.py:14)
+
+
+def build_reference(cfg):
+    M = ref_shim.import_reference_models()
+    sd = weights.make_state_dict(cfg, WEIGHT_SEED)
+    ref = M.Transducer.from_config(ref_shim.reference_conf(cfg), ref_shim.FakeLang())
+    ref.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=True)
+    ref.eval()
+    return ref
+
+
+def ref_logmel(audio, cfg):
+    """transforms.py:290-296 + 311-323 with deltas=0."""
+    op = torchaudio.transforms.MelSpectrogram(
+        sample_rate=cfg.sample_rate, win_length=cfg.win_length, hop_length=cfg.hop_length,
+        n_fft=cfg.n_fft, n_mels=cfg.n_mels,
+    )
+    with torch.no_grad():
+        res = torch.log(op(audio) + 1e-6)
+    return res.permute(0, 2, 1)
+
+
+def ref_stack(t, cfg):
+    """transforms.py:436-441."""
+    uf = t.unfold(-2, cfg.n_stack, cfg.downsample).contiguous()
+    return uf.view(uf.size(0), uf.size(1), -1).contiguous()
+
+
+def ref_features_offline(audio, cfg):
+    return ref_stack(ref_logmel(audio, cfg), cfg).unsqueeze(-1)  # FixDimensions, transforms.py:450-452
+
+
+def ref_stream_chunks(audio_1d, cfg):
+    """api-server.py:83-115 windowing + stream transform pipeline incl. Buffer(n_buffer=2):
+    yields [2, X, 1] tensors or None, one per 80 ms chunk."""
+    frames, saved = [], []
+    n_chunks = audio_1d.shape[0] // CHUNK
+    for j in range(n_chunks):
+        frames.append(audio_1d[None, j * CHUNK:(j + 1) * CHUNK])
+        if len(frames) < 3:
+            yield None  # server: `continue` (nothing reaches the model)
+            continue
+        aud = torch.cat(frames, dim=1)
+        frames.pop(0)
+        sp = ref_logmel(aud, cfg)
+        a = sp.shape[1] // 3 + 1  # StreamPostprocess, transforms.py:335-342
+        sp = sp[:, a:, :][:, : cfg.n_stack, :]
+        saved.append(ref_stack(sp, cfg).unsqueeze(-1))
+        if len(saved) == 2:  # Buffer, transforms.py:463-471
+            catted = torch.cat(saved, dim=1)
+            saved.clear()
+            yield catted[0]
+        else:
+            yield None
+
+
+def offline_fixture(name, n_utt, n_samples, audio_seed, full=False, enc_stride=8, n_logp=8):
+    cfg = weights.CONFIGS[name]
+    ref = build_reference(cfg)
+    audio = weights.make_audio(n_utt, n_samples, audio_seed)
+    out = {
+        "config": name, "weight_seed": WEIGHT_SEED, "audio_seed": audio_seed,
+        "n_utt": n_utt, "n_samples": n_samples, "max_iters": 3,
+    }
+    for b in range(n_utt):
+        feats = ref_features_offline(torch.from_numpy(audio[b:b + 1]), cfg)[0]  # [T, X, 1]
+        with torch.no_grad():
+            toks, nlp, metrics, extra = ref.decode_greedy(feats, max_iters=3)
+            enc = ref.encoder(feats[None])[0]
+        logp = torch.stack([o.reshape(-1) for o in extra["outs"]])
+        top2 = torch.topk(logp, 2, dim=-1).values
+        out[f"tokens_{b}"] = np.asarray(toks, dtype=np.int32)
+        out[f"neg_log_p_{b}"] = np.float64(nlp)
+        out[f"iters_{b}"] = np.asarray(extra["iters"], dtype=np.int32)
+        out[f"alignment_score_{b}"] = np.float64(metrics["alignment_score"])
+        out[f"margins_{b}"] = (top2[:, 0] - top2[:, 1]).numpy().astype(np.float32)
+        out[f"argmax_{b}"] = logp.argmax(-1).numpy().astype(np.int32)
+        out[f"maxlogp_{b}"] = logp.max(-1).values.numpy().astype(np.float32)
+        if full:
+            out[f"feats_{b}"] = feats[..., 0].numpy()
+            out[f"enc_{b}"] = enc.numpy()
+            out[f"logp_{b}"] = logp.numpy()
+        else:
+            out[f"feats_sub_{b}"] = feats[::enc_stride, ::7, 0].numpy()
+            out[f"enc_sub_{b}"] = enc[::enc_stride, ::16].numpy()
+            out[f"logp_first_{b}"] = logp[:n_logp].numpy()
+        print(f"[{name}] utt {b}: T={feats.shape[0]} evals={logp.shape[0]} tokens={len(toks)} "
+              f"min margin={float(out[f'margins_{b}'].min()):.2e}")
+    out["enc_stride"], out["n_logp"] = enc_stride, n_logp
+    return out
+
+
+def stream_fixture(name, n_chunks, audio_seed, lead_zero_chunks=1):
+    """api-client.py:32-47 sends one leading zero chunk, then the audio in 80 ms chunks."""
+    cfg = weights.CONFIGS[name]
+    ref = build_reference(cfg)
+    audio = weights.make_audio(1, n_chunks * CHUNK, audio_seed)[0]
+    audio[: lead_zero_chunks * CHUNK] = 0.0
+    a = torch.from_numpy(audio)
+    rows = [c for c in ref_stream_chunks(a, cfg)]
+    feats = [c[..., 0].numpy() for c in rows if c is not None]
+    with torch.no_grad():
+        yields = [(list(y), list(ys)) for (y, ys, _reset) in ref.transcribe_stream(iter(rows), lambda t: list(t), max_iters=10)]
+    out = {
+        "config": name, "weight_seed": WEIGHT_SEED, "audio_seed": audio_seed, "n_chunks": n_chunks,
+        "lead_zero_chunks": lead_zero_chunks, "max_iters": 10,
+        "n_yields": len(yields),
+        "tokens_all": np.asarray(yields[-1][0] if yields else [], dtype=np.int32),
+        "chunk_counts": np.asarray([len(ys) for _, ys in yields], dtype=np.int32),
+        "feats": np.stack(feats) if name == "tiny" else np.stack(feats)[:, :, ::7],
+    }
+    print(f"[{name} stream] chunks={n_chunks} yields={len(yields)} tokens={len(out['tokens_all'])}")
+    return out
+
+
+def modules_fixture(name="tiny", T=12, N=3):
+    """Direct ``Encoder`` / ``Predictor`` / ``Joint`` calls with explicit state (section 8b)."""
+    cfg = weights.CONFIGS[name]
+    ref = build_reference(cfg)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, 2 * T, cfg.feature_sz, 1, generator=g)
+    toks = torch.randint(1, cfg.vocab_sz, (N, 4), generator=g)
+    with torch.no_grad():
+        e1, s1 = ref.encoder(x[:, :T], return_state=True)
+        e2, s2 = ref.encoder(x[:, T:], state=s1, return_state=True)
+        efull = ref.encoder(x)
+        p_out, p_state, outs = None, None, []
+        for j in range(toks.shape[1]):
+            p_out, p_state = ref.predictor(toks[:, j:j + 1], state=p_state)
+            outs.append(p_out[:, 0])
+        jl = ref.joint(outs[-1], e2[:, -1])
+    return {
+        "config": name, "weight_seed": WEIGHT_SEED, "x": x[..., 0].numpy(), "tokens": toks.numpy().astype(np.int32),
+        "enc_first": e1.numpy(), "enc_second": e2.numpy(), "enc_full": efull.numpy(),
+        "enc_h": np.stack([s[0][0].numpy() for s in s2]), "enc_c": np.stack([s[1][0].numpy() for s in s2]),
+        "pred_outs": torch.stack(outs, 1).numpy(), "pred_h": np.stack([s[0].numpy() for s in p_state]),
+        "joint_logits": jl.numpy(),
+    }
+
+
+def main():
+    if not ref_shim.reference_available():
+        sys.exit("reference tree missing; fixtures can only be generated in the authoring container")
+    warnings.filterwarnings("ignore")
+    torch.manual_seed(0)
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    jobs = {
+        "tiny_offline": lambda: offline_fixture("tiny", n_utt=3, n_samples=40000, audio_seed=21, full=True),
+        "tiny_stream": lambda: stream_fixture("tiny", n_chunks=40, audio_seed=22),
+        "tiny_modules": lambda: modules_fixture("tiny"),
+        "cfg2_offline": lambda: offline_fixture("cfg2", n_utt=2, n_samples=80000, audio_seed=23),
+        "cfg2_stream": lambda: stream_fixture("cfg2", n_chunks=50, audio_seed=24),
+        "ref_offline": lambda: offline_fixture("ref", n_utt=1, n_samples=48000, audio_seed=25),
+        "cfg4_offline": lambda: offline_fixture("cfg4", n_utt=1, n_samples=32000, audio_seed=26),
+    }
+    only = sys.argv[1:]
+    for k, fn in jobs.items():
+        if only and k not in only:
+            continue
+        np.savez_compressed(os.path.join(GOLDEN_DIR, k + ".npz"), **fn())
+        print("wrote", k, os.path.getsize(os.path.join(GOLDEN_DIR, k + ".npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,94 @@
+"""CPU: pins the oracle (oracle/rnnt_oracle.py) against fixtures produced by the imported,
+unmodified reference (oracle/make_golden.py).  No GPU, no product code."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rnnt_oracle as O
+from oracle import weights
+from conftest import load_golden
+
+CHUNK = 1280
+
+
+def _model(g):
+    cfg = weights.CONFIGS[str(g["config"])]
+    return cfg, O.OracleTransducer(cfg, weights.make_state_dict(cfg, int(g["weight_seed"])))
+
+
+@pytest.mark.parametrize("name", ["tiny_offline", "cfg2_offline", "ref_offline", "cfg4_offline"])
+@pytest.mark.parametrize("impl", ["explicit", "aten"])
+def test_offline_greedy_matches_reference(name, impl):
+    g = load_golden(name)
+    cfg, orc = _model(g)
+    audio = weights.make_audio(int(g["n_utt"]), int(g["n_samples"]), int(g["audio_seed"]))
+    for b in range(int(g["n_utt"])):
+        feats = O.features_offline(torch.from_numpy(audio[b:b + 1]), cfg)[0]
+        r = orc.decode_greedy(feats, max_iters=int(g["max_iters"]), impl=impl, keep_logits=True)
+        assert r["tokens"] == g[f"tokens_{b}"].tolist()
+        assert r["iters"] == g[f"iters_{b}"].tolist()
+        assert abs(r["neg_log_p"] - float(g[f"neg_log_p_{b}"])) < 1e-3
+        assert abs(r["alignment_score"] - float(g[f"alignment_score_{b}"])) < 1e-9
+        np.testing.assert_allclose(r["logp"].max(-1).values.numpy(), g[f"maxlogp_{b}"], atol=2e-4)
+        if f"feats_{b}" in g:
+            np.testing.assert_allclose(feats.numpy(), g[f"feats_{b}"], atol=2e-5)
+            np.testing.assert_allclose(r["enc"].numpy(), g[f"enc_{b}"], atol=2e-5)
+            np.testing.assert_allclose(r["logp"].numpy(), g[f"logp_{b}"], atol=2e-4)
+        else:
+            s, n = int(g["enc_stride"]), int(g["n_logp"])
+            np.testing.assert_allclose(feats[::s, ::7].numpy(), g[f"feats_sub_{b}"], atol=2e-5)
+            np.testing.assert_allclose(r["enc"][::s, ::16].numpy(), g[f"enc_sub_{b}"], atol=5e-5)
+            np.testing.assert_allclose(r["logp"][:n].numpy(), g[f"logp_first_{b}"], atol=5e-4)
+
+
+@pytest.mark.parametrize("name", ["tiny_stream", "cfg2_stream"])
+def test_stream_matches_reference(name):
+    g = load_golden(name)
+    cfg, orc = _model(g)
+    n_chunks = int(g["n_chunks"])
+    audio = weights.make_audio(1, n_chunks * CHUNK, int(g["audio_seed"]))[0]
+    audio[: int(g["lead_zero_chunks"]) * CHUNK] = 0.0
+    fe = O.StreamFrontend(cfg)
+    rows = [fe.push(torch.from_numpy(audio[None, j * CHUNK:(j + 1) * CHUNK])) for j in range(n_chunks)]
+    feats = np.stack([r.numpy() for r in rows if r is not None])
+    ref_feats = g["feats"]
+    np.testing.assert_allclose(feats if name.startswith("tiny") else feats[:, :, ::7], ref_feats, atol=2e-5)
+    yields = list(orc.transcribe_stream(iter(rows), max_iters=int(g["max_iters"])))
+    assert len(yields) == int(g["n_yields"])
+    assert [len(ys) for _, ys in yields] == g["chunk_counts"].tolist()
+    assert yields[-1][0] == g["tokens_all"].tolist()
+
+
+def test_modules_match_reference():
+    g = load_golden("tiny_modules")
+    cfg, orc = _model(g)
+    x = torch.from_numpy(g["x"])
+    T = x.shape[1] // 2
+    with torch.no_grad():
+        e1, s1 = orc.encoder(x[:, :T])
+        e2, s2 = orc.encoder(x[:, T:], s1)
+        ef, _ = orc.encoder(x)
+        np.testing.assert_allclose(e1.numpy(), g["enc_first"], atol=2e-5)
+        np.testing.assert_allclose(e2.numpy(), g["enc_second"], atol=2e-5)
+        np.testing.assert_allclose(ef.numpy(), g["enc_full"], atol=2e-5)
+        np.testing.assert_allclose(torch.cat([e1, e2], 1).numpy(), g["enc_full"], atol=2e-5)
+        np.testing.assert_allclose(np.stack([s[0][0].numpy() for s in s2]), g["enc_h"], atol=2e-5)
+        np.testing.assert_allclose(np.stack([s[1][0].numpy() for s in s2]), g["enc_c"], atol=2e-5)
+        toks = torch.from_numpy(g["tokens"]).long()
+        st, outs = None, []
+        for j in range(toks.shape[1]):
+            o, st = orc.predictor(toks[:, j], st)
+            outs.append(o)
+        np.testing.assert_allclose(torch.stack(outs, 1).numpy(), g["pred_outs"], atol=2e-5)
+        np.testing.assert_allclose(np.stack([s[0].numpy() for s in st]), g["pred_h"], atol=2e-5)
+        jl = orc.joint(outs[-1], e2[:, -1])
+        np.testing.assert_allclose(jl.numpy(), g["joint_logits"], atol=1e-4)
+
+
+def test_mel_filterbank_properties():
+    fb = O.mel_fbanks_htk(513, 80, 16000)
+    assert fb.shape == (513, 80) and float(fb.min()) >= 0.0
+    nz = (fb > 0).sum(0)
+    assert int(nz.min()) >= 1  # every filter has taps at n_fft=1024
+    # triangular: each bin contributes to at most two adjacent filters
+    assert int((fb > 0).sum(1).max()) <= 2
