@@ -1,0 +1,225 @@
+/*
+ * rnnt_b200.h -- C ABI of the B200-native streaming RNN-Transducer inference path.
+ *
+ * This is the drop-in boundary for the ONE hot path of iceychris/LibreASR
+ * (audio -> log-mel/stack -> stacked-LSTM encoder -> GRU predictor -> joint ->
+ * greedy RNN-T decode).  The reference has no FFI layer of its own: its
+ * "operator API" for this path is the Python module surface of
+ * libreasr/lib/models.py and the YAML-named transforms of libreasr/lib/transforms.py
+ * (SURVEY.md section 8b).  Each entry point below therefore names the reference
+ * function(s) it replaces (paths relative to the reference root); the Python package
+ * `libreasr_b200` binds these symbols with ctypes and re-exposes the reference's
+ * module surface on top of them (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "dev" is a CUDA device pointer owned
+ *     by the caller, "host" is host memory; no allocation happens inside hot calls
+ *     once rnnt_b200_reserve() covered the shapes (workspaces grow on demand otherwise)
+ *   - all kernels are enqueued on `stream` (a cudaStream_t passed as void*); calls are
+ *     asynchronous unless stated otherwise
+ *   - every function returns 0 on success, a negative rnnt_b200_status otherwise, and
+ *     never throws; rnnt_b200_last_error() gives the message
+ *   - tensors are dense row-major fp32 unless stated; B = utterances/streams,
+ *     n = samples, T = encoder steps, X = n_mels*n_stack, H = hidden, J = joint, V = vocab
+ *   - a handle may be used from several host threads as long as concurrent calls use
+ *     distinct CUDA streams AND distinct caller-owned buffers; workspace-using calls
+ *     (transcribe*, encode, decode) on one handle must be serialised by the caller
+ */
+#ifndef RNNT_B200_H_
+#define RNNT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RNNT_B200_ABI_VERSION 1
+
+typedef struct rnnt_b200_handle_s* rnnt_b200_handle;
+
+typedef enum {
+  RNNT_B200_OK = 0,
+  RNNT_B200_ERR_INVALID = -1,   /* bad argument / shape (reference: ValueError, base_rnn.py:81-117) */
+  RNNT_B200_ERR_STATE = -2,     /* call order (weights missing, not finalized) */
+  RNNT_B200_ERR_CUDA = -3,      /* CUDA runtime error; message holds cudaGetErrorString */
+  RNNT_B200_ERR_NOMEM = -4,
+  RNNT_B200_ERR_UNSUPPORTED = -5
+} rnnt_b200_status;
+
+/* Arithmetic used for the dense contractions (LSTM gate GEMMs, joint projections). */
+typedef enum {
+  RNNT_B200_GEMM_FP32_SIMT = 0,   /* fp32 FMA on CUDA cores (bit-level closest to the reference) */
+  RNNT_B200_GEMM_TC_FP16X3 = 1,   /* tcgen05, operands split hi+lo fp16, 3 MMAs, fp32 accumulate (~fp32 accuracy) */
+  RNNT_B200_GEMM_TC_BF16 = 2      /* tcgen05, single bf16 pass (throughput mode, not token-exact) */
+} rnnt_b200_gemm_mode;
+
+/* Shape/config of the path.  Field names follow config/testing.yaml:120-229. */
+typedef struct rnnt_b200_config {
+  int32_t sample_rate;   /* sr: 16000 */
+  int32_t n_fft;         /* melkwargs.n_fft: 1024 (only 1024 is implemented) */
+  int32_t win_length;    /* int(win_length * sr) = 400, transforms.py:288 */
+  int32_t hop_length;    /* int(hop_length * sr) = 160, transforms.py:289 */
+  int32_t n_mels;        /* melkwargs.n_mels */
+  int32_t n_stack;       /* StackDownsample.n_stack = 10 */
+  int32_t downsample;    /* StackDownsample.downsample = 8 */
+  int32_t enc_layers;    /* model.encoder.num_layers (LSTM) */
+  int32_t pred_layers;   /* model.predictor.num_layers (NBRC == GRU) */
+  int32_t hidden_sz;     /* model.hidden_sz == model.out_sz */
+  int32_t embed_sz;      /* model.embed_sz */
+  int32_t joint_sz;      /* model.joint_sz */
+  int32_t vocab_sz;      /* model.vocab_sz */
+  int32_t blank;         /* models.py:203,225 -> 0 */
+  int32_t bos;           /* models.py:226-227 -> 2 */
+  int32_t device;        /* CUDA device ordinal */
+  int32_t gemm_mode;     /* rnnt_b200_gemm_mode */
+  float log_offset;      /* transforms.py:312 -> 1e-6 */
+  float ln_eps;          /* nn.LayerNorm default 1e-5 (models.py:84) */
+  float bn_eps;          /* nn.BatchNorm1d default 1e-5 (custom_rnn.py:124) */
+} rnnt_b200_config;
+
+/* ---- lifecycle ---------------------------------------------------------------- */
+
+int32_t rnnt_b200_abi_version(void);
+
+/* Fills *cfg with the reference's shipped defaults (config/testing.yaml). */
+int32_t rnnt_b200_default_config(rnnt_b200_config* cfg);
+
+/* Replaces Transducer.__init__/from_config (models.py:190-259) as far as device
+ * resources go.  Fails (ERR_CUDA) when no sm_100 device is present: there is no CPU
+ * fallback. */
+int32_t rnnt_b200_create(const rnnt_b200_config* cfg, rnnt_b200_handle* out);
+int32_t rnnt_b200_destroy(rnnt_b200_handle h);
+
+/* Message of the last failing call on this handle (never NULL).  h may be NULL for
+ * create() failures. */
+const char* rnnt_b200_last_error(rnnt_b200_handle h);
+
+/* Replaces load_asr_model / nn.Module.load_state_dict (model_utils.py:61-95): one call
+ * per tensor, `name` is the reference state_dict key verbatim (SURVEY.md section 8b:
+ * "encoder.rnn_stack.rnns.0.weight_ih_l0", "predictor.rnn_stack.rnns.1.recurrent_kernel",
+ * "joint.joint.2.bias", ...) plus two front-end tensors that the reference builds inside
+ * torchaudio (transforms.py:290-296): "frontend.window" [win_length] and
+ * "frontend.mel_fb" [n_fft/2+1, n_mels].  `data` is HOST fp32, copied before return.
+ * Unknown names and wrong element counts return ERR_INVALID. */
+int32_t rnnt_b200_set_weight(rnnt_b200_handle h, const char* name, const float* data_host, int64_t numel);
+
+/* Repacks the weights into kernel layouts (gate interleave, transposes, BatchNorm
+ * folded to scale/shift, embedding*ffn*kernel_0 table).  Synchronises `stream`.
+ * ERR_STATE lists the first missing tensor. */
+int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream);
+
+/* Pre-allocates workspaces for up to max_batch utterances of max_samples samples. */
+int32_t rnnt_b200_reserve(rnnt_b200_handle h, int32_t max_batch, int64_t max_samples);
+
+/* ---- shape helpers -------------------------------------------------------------- */
+
+/* F = n/hop + 1 (torch.stft center=True), T = (F - n_stack)/downsample + 1 (unfold), 0 if F < n_stack. */
+int64_t rnnt_b200_num_frames(rnnt_b200_handle h, int64_t n_samples);
+int64_t rnnt_b200_num_steps(rnnt_b200_handle h, int64_t n_samples);
+
+/* ---- features: a3 + a5 (+ a4 for streams) ---------------------------------------- */
+
+/* Replaces TransformTime.encodes -> StackDownsample.encodes (transforms.py:301-323,
+ * 436-441) for 16 kHz mono input.  audio_dev [B, n]; lens_dev [B] int32 valid samples
+ * per utterance or NULL (= n); feats_dev [B, T, X] with T = num_steps(n); rows
+ * t >= num_steps(lens[b]) are zero-filled. */
+int32_t rnnt_b200_features(rnnt_b200_handle h, const float* audio_dev, const int32_t* lens_dev,
+                           int32_t B, int64_t n, float* feats_dev, void* stream);
+
+/* Replaces TransformTime.encodes alone (transforms.py:301-323): un-stacked log-mel frames
+ * logmel_dev [B, F, n_mels], F = num_frames(n).  For callers that keep the reference's
+ * transform-by-transform pipeline; the fused rnnt_b200_features() is the hot path. */
+int32_t rnnt_b200_logmel(rnnt_b200_handle h, const float* audio_dev, const int32_t* lens_dev,
+                         int32_t B, int64_t n, float* logmel_dev, void* stream);
+
+/* Replaces the `stream` transform pipeline up to Buffer (config/testing.yaml:356-374;
+ * transforms.py:301-342, 436-441): window_dev [B, W] is the serving loop's 3-chunk
+ * window (api-server.py:26,95-102); feats_dev [B, X] is the single stacked row made of
+ * frames F/3+1 .. F/3+n_stack of that window. */
+int32_t rnnt_b200_features_stream(rnnt_b200_handle h, const float* window_dev, int32_t B, int64_t W,
+                                  float* feats_dev, void* stream);
+
+/* ---- encoder: a7 + a8 + a9 -------------------------------------------------------- */
+
+/* Replaces Encoder.forward(x, state, lengths, return_state) (models.py:105-113) and
+ * CustomRNN.forward (custom_rnn.py:177-232) in eval mode.  feats_dev [B, T, X];
+ * lens_T_dev [B] int32 or NULL; state_h_dev / state_c_dev [L, B, H] or NULL.  When
+ * use_state_in == 0 the learnable initial state `hs[i]` is used (custom_rnn.py:152-156);
+ * when the state pointers are non-NULL the final (h, c) per layer is written back
+ * (state at lens_T[b] for ragged batches, as pack_padded_sequence gives,
+ * custom_rnn.py:164-170).  enc_out_dev [B, T, H]. */
+int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats_dev, const int32_t* lens_T_dev,
+                         int32_t B, int32_t T, float* state_h_dev, float* state_c_dev,
+                         int32_t use_state_in, float* enc_out_dev, void* stream);
+
+/* ---- predictor: a10 + a11 ---------------------------------------------------------- */
+
+/* Replaces Predictor.forward(x, state) for one step (models.py:181-187; cell
+ * haste/nbrc.py:46-56).  tokens_dev [B] int32; state_h_dev [Lp, B, H] in/out (required);
+ * use_state_in == 0 starts from `hs[i]`; out_dev [B, H]. */
+int32_t rnnt_b200_predict(rnnt_b200_handle h, const int32_t* tokens_dev, int32_t B,
+                          float* state_h_dev, int32_t use_state_in, float* out_dev, void* stream);
+
+/* ---- joint: a12 --------------------------------------------------------------------- */
+
+/* Replaces Joint.forward(h_pred, h_enc), concat method (models.py:132-140): raw logits,
+ * no softmax.  h_pred_dev, h_enc_dev [B, H]; logits_dev [B, V]. */
+int32_t rnnt_b200_joint(rnnt_b200_handle h, const float* h_pred_dev, const float* h_enc_dev,
+                        int32_t B, float* logits_dev, void* stream);
+
+/* ---- greedy decode: a13 / a14 inner loop ---------------------------------------------- */
+
+/* Replaces the loops of Transducer.decode_greedy (models.py:403-443) and
+ * Transducer.transcribe_stream (models.py:528-571) for B independent utterances/streams,
+ * entirely on the device (no host round trip per symbol).
+ *   enc_dev [B, T, H], lens_T_dev [B] int32 or NULL
+ *   max_iters: 3 offline (models.py:369), 10 streaming (models.py:458)
+ *   pred_state_h_dev [Lp, B, H], pred_out_dev [B, H]: predictor state and last predictor
+ *     output (`h_t_pred`); in/out.  use_state_in == 0 -> initialised by feeding BOS from the
+ *     learnable state (models.py:397-398, 484-489)
+ *   tokens_out_dev [B, U_cap] int32, ntok_out_dev [B] int32 (U_cap >= max_iters*T)
+ *   neg_logp_out_dev [B] double or NULL: -sum of the chosen log-probs incl. blanks (models.py:422,455)
+ *   iters_out_dev [B, T] uint8 or NULL: joint evaluations per frame (models.py:443)
+ *   trace_logp_dev [B, trace_cap, V] or NULL: log_softmax rows of the first trace_cap
+ *     evaluations of every utterance (parity testing; `extra["outs"]`, models.py:419) */
+int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc_dev, const int32_t* lens_T_dev,
+                                int32_t B, int32_t T, int32_t max_iters,
+                                float* pred_state_h_dev, float* pred_out_dev, int32_t use_state_in,
+                                int32_t* tokens_out_dev, int32_t U_cap, int32_t* ntok_out_dev,
+                                double* neg_logp_out_dev, uint8_t* iters_out_dev,
+                                float* trace_logp_dev, int32_t trace_cap, void* stream);
+
+/* ---- whole path ------------------------------------------------------------------------- */
+
+/* Replaces ASRServicer.Transcribe's compute (api-server.py:68-78: x_tfm -> model.transcribe)
+ * for a batch: features -> encoder -> greedy decode with device-resident audio. */
+int32_t rnnt_b200_transcribe(rnnt_b200_handle h, const float* audio_dev, const int32_t* lens_dev,
+                             int32_t B, int64_t n, int32_t max_iters,
+                             int32_t* tokens_out_dev, int32_t U_cap, int32_t* ntok_out_dev,
+                             double* neg_logp_out_dev, uint8_t* iters_out_dev, void* stream);
+
+/* Same with HOST buffers (pinned for full speed): copies audio host->device, runs the
+ * path, copies tokens / counts / scores back and synchronises `stream` before
+ * returning.  lens_host may be NULL.  This is the end-to-end call bench.py times. */
+int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, const int32_t* lens_host,
+                                  int32_t B, int64_t n, int32_t max_iters,
+                                  int32_t* tokens_out_host, int32_t U_cap, int32_t* ntok_out_host,
+                                  double* neg_logp_out_host, void* stream);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t rnnt_b200_kernel_launches(rnnt_b200_handle h);
+
+/* Device time (ms) the most recent transcribe*() spent per stage, measured with CUDA
+ * events on `stream`: out[0]=features, [1]=encoder (LayerNorm + hoisted input GEMMs +
+ * recurrent steps), [2]=reserved (0), [3]=joint enc projection GEMM, [4]=decode loop.
+ * Synchronises.  Profiling must have been enabled with rnnt_b200_set_profiling(h, 1). */
+int32_t rnnt_b200_set_profiling(rnnt_b200_handle h, int32_t enable);
+int32_t rnnt_b200_stage_times_ms(rnnt_b200_handle h, float* out5_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNNT_B200_H_ */

@@ -1,0 +1,802 @@
+// C-ABI layer: handle, weight ingestion / repack, workspaces, and the entry points declared
+// in include/rnnt_b200.h.  Host orchestration only -- all arithmetic is in the kernels.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rnnt_b200.h"
+#include "kernels.h"
+
+using namespace rnnt;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    size_t sz = need + need / 8;
+    cudaError_t e = cudaMalloc(&p, sz);
+    if (e != cudaSuccess) return e;
+    bytes = sz;
+    return cudaMemset(p, 0, sz);
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+struct EncLayer {
+  int in = 0;
+  float *Wih_r = nullptr, *bias_r = nullptr, *Whh_t = nullptr, *h0 = nullptr, *c0 = nullptr, *bn_scale = nullptr,
+        *bn_shift = nullptr;
+};
+
+}  // namespace
+
+struct rnnt_b200_handle_s {
+  rnnt_b200_config cfg;
+  std::string err;
+  std::map<std::string, std::vector<float>> raw;
+  bool finalized = false;
+  int sm_count = 0, coop_blocks = 0;
+  int64_t launches = 0;
+  std::vector<void*> weight_allocs;
+  // frontend
+  float* window = nullptr;
+  float2* tw = nullptr;
+  int *mel_start = nullptr, *mel_count = nullptr, *mel_off = nullptr;
+  float* mel_w = nullptr;
+  // encoder
+  float *ln_g = nullptr, *ln_b = nullptr;
+  std::vector<EncLayer> enc;
+  // predictor + joint
+  DecodeWeights dw;
+  float* W1 = nullptr;  // [J][2H] as loaded; enc half = W1 + H with ld 2H
+  // workspaces
+  DevBuf feats, lnx, xp, ya, yb, ep, ehT[2], ecT, dhT, dxT, dgT, deT, dppT, dzT, dpart, dlse;
+  DevBuf t_audio, t_lens, t_tokens, t_ntok, t_nlp, t_iters, t_enc;
+  // profiling
+  bool profiling = false;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+thread_local std::string g_create_err;
+
+int fail(rnnt_b200_handle h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+int fail_cuda(rnnt_b200_handle h, cudaError_t e, const char* what) {
+  return fail(h, RNNT_B200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CK(expr)                                                   \
+  do {                                                             \
+    cudaError_t e_ = (expr);                                       \
+    if (e_ != cudaSuccess) return fail_cuda(h, e_, #expr);         \
+  } while (0)
+// kernel launch through a launcher returning cudaError_t; counts launches
+#define LAUNCH(n, expr)                                            \
+  do {                                                             \
+    cudaError_t e_ = (expr);                                       \
+    if (e_ != cudaSuccess) return fail_cuda(h, e_, #expr);         \
+    h->launches += (n);                                            \
+  } while (0)
+
+int64_t num_frames(const rnnt_b200_config& c, int64_t n) { return n / c.hop_length + 1; }
+int64_t num_steps(const rnnt_b200_config& c, int64_t n) {
+  const int64_t F = num_frames(c, n);
+  return F >= c.n_stack ? (F - c.n_stack) / c.downsample + 1 : 0;
+}
+
+template <class T>
+cudaError_t upload(rnnt_b200_handle h, const std::vector<T>& v, T** out) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  h->weight_allocs.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+cudaError_t dalloc(rnnt_b200_handle h, size_t n_floats, float** out) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, std::max<size_t>(n_floats, 1) * sizeof(float));
+  if (e != cudaSuccess) return e;
+  h->weight_allocs.push_back(p);
+  *out = reinterpret_cast<float*>(p);
+  return cudaSuccess;
+}
+
+int64_t expected_numel(const rnnt_b200_config& c, const std::string& name, bool* known) {
+  const int64_t H = c.hidden_sz, X = (int64_t)c.n_mels * c.n_stack, E = c.embed_sz, J = c.joint_sz, V = c.vocab_sz;
+  *known = true;
+  if (name == "frontend.window") return c.win_length;
+  if (name == "frontend.mel_fb") return (int64_t)(c.n_fft / 2 + 1) * c.n_mels;
+  if (name == "encoder.input_norm.weight" || name == "encoder.input_norm.bias") return X;
+  if (name == "predictor.embed.weight") return V * E;
+  if (name == "predictor.ffn.weight") return H * E;
+  if (name == "predictor.ffn.bias") return H;
+  if (name == "joint.joint.0.weight") return J * 2 * H;
+  if (name == "joint.joint.0.bias") return J;
+  if (name == "joint.joint.2.weight") return V * J;
+  if (name == "joint.joint.2.bias") return V;
+  for (int side = 0; side < 2; ++side) {
+    const std::string pre = side == 0 ? "encoder.rnn_stack." : "predictor.rnn_stack.";
+    if (name.compare(0, pre.size(), pre) != 0) continue;
+    const std::string rest = name.substr(pre.size());
+    const int L = side == 0 ? c.enc_layers : c.pred_layers;
+    int idx = -1, used = 0;
+    if (sscanf(rest.c_str(), "hs.%d%n", &idx, &used) == 1 && (size_t)used == rest.size() && idx >= 0 && idx < L)
+      return side == 0 ? 2 * H : H;
+    char field[64];
+    if (sscanf(rest.c_str(), "bns.%d.%63s", &idx, field) == 2 && idx >= 0 && idx < L) {
+      const std::string f(field);
+      if (f == "weight" || f == "bias" || f == "running_mean" || f == "running_var") return H;
+    }
+    if (sscanf(rest.c_str(), "rnns.%d.%63s", &idx, field) == 2 && idx >= 0 && idx < L) {
+      const std::string f(field);
+      if (side == 0) {
+        const int64_t in = idx == 0 ? X : H;
+        if (f == "weight_ih_l0") return 4 * H * in;
+        if (f == "weight_hh_l0") return 4 * H * H;
+        if (f == "bias_ih_l0" || f == "bias_hh_l0") return 4 * H;
+      } else {
+        if (f == "kernel" || f == "recurrent_kernel") return H * 3 * H;
+        if (f == "bias" || f == "recurrent_bias") return 3 * H;
+      }
+    }
+  }
+  *known = false;
+  return 0;
+}
+
+int validate_config(const rnnt_b200_config& c, std::string* why) {
+  auto bad = [&](const char* m) { *why = m; return 1; };
+  if (c.n_fft != 1024) return bad("only n_fft == 1024 is implemented (melkwargs.n_fft, config/testing.yaml:133)");
+  if (c.win_length < 2 || c.win_length > 1024 || (c.win_length & 1)) return bad("win_length must be even and <= n_fft");
+  if (c.hop_length < 1) return bad("hop_length must be >= 1");
+  if (c.n_mels < 1 || c.n_mels > 256) return bad("n_mels must be in [1, 256]");
+  if (c.n_stack < 1 || c.n_stack > kFrontendMaxWarps) return bad("n_stack must be in [1, 16]");
+  if (c.downsample < 1) return bad("downsample must be >= 1");
+  if (c.hidden_sz < 64 || c.hidden_sz % 64) return bad("hidden_sz must be a positive multiple of 64");
+  if (c.joint_sz < 64 || c.joint_sz % 64) return bad("joint_sz must be a positive multiple of 64");
+  if (c.vocab_sz < 32 || c.vocab_sz % 32) return bad("vocab_sz must be a positive multiple of 32");
+  if ((c.n_mels * c.n_stack) % 4) return bad("n_mels*n_stack must be a multiple of 4");
+  if (c.embed_sz < 4 || c.embed_sz % 4) return bad("embed_sz must be a positive multiple of 4");
+  if (c.enc_layers < 1 || c.enc_layers > 16) return bad("enc_layers must be in [1, 16]");
+  if (c.pred_layers < 1 || c.pred_layers > kMaxPredLayers) return bad("pred_layers must be in [1, 4]");
+  if (c.blank < 0 || c.blank >= c.vocab_sz || c.bos < 0 || c.bos >= c.vocab_sz) return bad("blank/bos out of range");
+  if (c.gemm_mode != RNNT_B200_GEMM_FP32_SIMT) return bad("gemm_mode not available in this build");
+  return 0;
+}
+
+int bp_of(int B) { return (int)round_up(B, kBatchTile); }
+
+}  // namespace
+
+extern "C" {
+
+int32_t rnnt_b200_abi_version(void) { return RNNT_B200_ABI_VERSION; }
+
+int32_t rnnt_b200_default_config(rnnt_b200_config* c) {
+  if (!c) return RNNT_B200_ERR_INVALID;
+  memset(c, 0, sizeof(*c));
+  c->sample_rate = 16000; c->n_fft = 1024; c->win_length = 400; c->hop_length = 160;
+  c->n_mels = 128; c->n_stack = 10; c->downsample = 8;
+  c->enc_layers = 6; c->pred_layers = 2; c->hidden_sz = 1024; c->embed_sz = 512; c->joint_sz = 1024; c->vocab_sz = 2048;
+  c->blank = 0; c->bos = 2; c->device = 0; c->gemm_mode = RNNT_B200_GEMM_FP32_SIMT;
+  c->log_offset = 1e-6f; c->ln_eps = 1e-5f; c->bn_eps = 1e-5f;
+  return RNNT_B200_OK;
+}
+
+const char* rnnt_b200_last_error(rnnt_b200_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int32_t rnnt_b200_create(const rnnt_b200_config* cfg, rnnt_b200_handle* out) {
+  rnnt_b200_handle h = nullptr;
+  if (!cfg || !out) return fail(nullptr, RNNT_B200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  std::string why;
+  if (validate_config(*cfg, &why)) return fail(nullptr, RNNT_B200_ERR_INVALID, why);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, RNNT_B200_ERR_CUDA,
+                std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, RNNT_B200_ERR_INVALID, "device ordinal out of range");
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail_cuda(nullptr, e, "cudaSetDevice");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return fail_cuda(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(nullptr, RNNT_B200_ERR_UNSUPPORTED, "kernels are built for sm_100a (B200) only; found sm_" +
+                                                        std::to_string(prop.major) + std::to_string(prop.minor));
+  h = new rnnt_b200_handle_s();
+  h->cfg = *cfg;
+  h->sm_count = prop.multiProcessorCount;
+  if ((e = configure_lstm()) != cudaSuccess || (e = configure_decode(cfg->device, &h->coop_blocks)) != cudaSuccess) {
+    delete h;
+    return fail_cuda(nullptr, e, "kernel configuration");
+  }
+  for (auto& ev : h->ev) cudaEventCreate(&ev);
+  *out = h;
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_destroy(rnnt_b200_handle h) {
+  if (!h) return RNNT_B200_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (void* p : h->weight_allocs) cudaFree(p);
+  DevBuf* bufs[] = {&h->feats, &h->lnx, &h->xp, &h->ya, &h->yb, &h->ep, &h->ehT[0], &h->ehT[1], &h->ecT, &h->dhT, &h->dxT,
+                    &h->dgT, &h->deT, &h->dppT, &h->dzT, &h->dpart, &h->dlse, &h->t_audio, &h->t_lens, &h->t_tokens,
+                    &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& ev : h->ev)
+    if (ev) cudaEventDestroy(ev);
+  delete h;
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_set_weight(rnnt_b200_handle h, const char* name, const float* data, int64_t numel) {
+  if (!h || !name || !data) return fail(h, RNNT_B200_ERR_INVALID, "null argument");
+  if (h->finalized) return fail(h, RNNT_B200_ERR_STATE, "weights are frozen after finalize()");
+  const std::string nm(name);
+  if (nm.size() > 19 && nm.compare(nm.size() - 19, 19, "num_batches_tracked") == 0) return RNNT_B200_OK;
+  bool known = false;
+  const int64_t want = expected_numel(h->cfg, nm, &known);
+  if (!known) return fail(h, RNNT_B200_ERR_INVALID, "unknown weight name: " + nm);
+  if (want != numel)
+    return fail(h, RNNT_B200_ERR_INVALID,
+                "size mismatch for " + nm + ": expected " + std::to_string(want) + " elements, got " + std::to_string(numel));
+  h->raw[nm].assign(data, data + numel);
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
+  if (!h) return RNNT_B200_ERR_INVALID;
+  if (h->finalized) return RNNT_B200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const rnnt_b200_config& c = h->cfg;
+  const int H = c.hidden_sz, X = c.n_mels * c.n_stack, E = c.embed_sz, J = c.joint_sz, V = c.vocab_sz;
+  CK(cudaSetDevice(c.device));
+  auto need = [&](const std::string& n) -> const std::vector<float>* {
+    auto it = h->raw.find(n);
+    return it == h->raw.end() ? nullptr : &it->second;
+  };
+#define NEED(var, name)                                                                    \
+  const std::vector<float>* var = need(name);                                              \
+  if (!var) return fail(h, RNNT_B200_ERR_STATE, std::string("missing weight: ") + (name));
+
+  // ---- frontend constants ----
+  NEED(win, "frontend.window");
+  NEED(fb, "frontend.mel_fb");
+  CK(upload(h, *win, &h->window));
+  {
+    std::vector<float2> tw(512);
+    for (int j = 0; j < 512; ++j) {
+      const double a = -2.0 * M_PI * (double)j / 1024.0;
+      tw[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    CK(upload(h, tw, &h->tw));
+    const int nf = c.n_fft / 2 + 1;
+    std::vector<int> ms(c.n_mels), mc(c.n_mels), mo(c.n_mels);
+    std::vector<float> mw;
+    for (int m = 0; m < c.n_mels; ++m) {
+      int lo = -1, hi = -1;
+      for (int k = 0; k < nf; ++k)
+        if ((*fb)[(size_t)k * c.n_mels + m] != 0.f) {
+          if (lo < 0) lo = k;
+          hi = k;
+        }
+      ms[m] = lo < 0 ? 0 : lo;
+      mc[m] = lo < 0 ? 0 : hi - lo + 1;
+      mo[m] = (int)mw.size();
+      for (int k = 0; k < mc[m]; ++k) mw.push_back((*fb)[(size_t)(ms[m] + k) * c.n_mels + m]);
+    }
+    CK(upload(h, ms, &h->mel_start));
+    CK(upload(h, mc, &h->mel_count));
+    CK(upload(h, mo, &h->mel_off));
+    CK(upload(h, mw, &h->mel_w));
+  }
+
+  auto bn_fold = [&](const std::string& pre, float** scale, float** shift) -> int {
+    NEED(g, pre + ".weight");
+    NEED(b, pre + ".bias");
+    NEED(mu, pre + ".running_mean");
+    NEED(var, pre + ".running_var");
+    std::vector<float> sc(H), sh(H);
+    for (int i = 0; i < H; ++i) {
+      sc[i] = (*g)[i] / sqrtf((*var)[i] + c.bn_eps);
+      sh[i] = (*b)[i] - (*mu)[i] * sc[i];
+    }
+    CK(upload(h, sc, scale));
+    CK(upload(h, sh, shift));
+    return 0;
+  };
+
+  // scratch for device-side repacks (freed at the end)
+  std::vector<void*> tmp;
+  auto tmp_upload = [&](const std::vector<float>& v, float** out) -> cudaError_t {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, v.size() * sizeof(float));
+    if (e != cudaSuccess) return e;
+    tmp.push_back(p);
+    *out = (float*)p;
+    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, st);
+  };
+  auto tmp_alloc = [&](size_t n, float** out) -> cudaError_t {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(float));
+    if (e != cudaSuccess) return e;
+    tmp.push_back(p);
+    *out = (float*)p;
+    return cudaSuccess;
+  };
+  int* perm4 = nullptr;  // interleaved row (unit*4+gate) <- native row (gate*H+unit)
+  int* perm3 = nullptr;
+  {
+    std::vector<int> p4(4 * H), p3(3 * H);
+    for (int u = 0; u < H; ++u) {
+      for (int g = 0; g < 4; ++g) p4[u * 4 + g] = g * H + u;
+      for (int g = 0; g < 3; ++g) p3[u * 3 + g] = g * H + u;
+    }
+    CK(upload(h, p4, &perm4));
+    CK(upload(h, p3, &perm3));
+  }
+  auto interleave = [&](const std::vector<float>& v, int G) {
+    std::vector<float> o(v.size());
+    for (int u = 0; u < H; ++u)
+      for (int g = 0; g < G; ++g) o[u * G + g] = v[g * H + u];
+    return o;
+  };
+
+  // ---- encoder (models.py:68-100; custom_rnn.py:113-126,259-269) ----
+  {
+    NEED(lg, "encoder.input_norm.weight");
+    NEED(lb, "encoder.input_norm.bias");
+    CK(upload(h, *lg, &h->ln_g));
+    CK(upload(h, *lb, &h->ln_b));
+  }
+  h->enc.resize(c.enc_layers);
+  for (int l = 0; l < c.enc_layers; ++l) {
+    EncLayer& L = h->enc[l];
+    L.in = l == 0 ? X : H;
+    const std::string p = "encoder.rnn_stack.rnns." + std::to_string(l) + ".";
+    NEED(wih, p + "weight_ih_l0");
+    NEED(whh, p + "weight_hh_l0");
+    NEED(bih, p + "bias_ih_l0");
+    NEED(bhh, p + "bias_hh_l0");
+    NEED(hs, "encoder.rnn_stack.hs." + std::to_string(l));
+    std::vector<float> bsum(4 * H);
+    for (int i = 0; i < 4 * H; ++i) bsum[i] = (*bih)[i] + (*bhh)[i];
+    CK(upload(h, interleave(bsum, 4), &L.bias_r));
+    CK(upload(h, std::vector<float>(hs->begin(), hs->begin() + H), &L.h0));
+    CK(upload(h, std::vector<float>(hs->begin() + H, hs->end()), &L.c0));
+    if (bn_fold("encoder.rnn_stack.bns." + std::to_string(l), &L.bn_scale, &L.bn_shift)) return RNNT_B200_ERR_STATE;
+    float *d_wih, *d_whh, *d_whh_r;
+    CK(tmp_upload(*wih, &d_wih));
+    CK(tmp_upload(*whh, &d_whh));
+    CK(tmp_alloc((size_t)4 * H * H, &d_whh_r));
+    CK(dalloc(h, (size_t)4 * H * L.in, &L.Wih_r));
+    CK(dalloc(h, (size_t)4 * H * H, &L.Whh_t));
+    LAUNCH(1, launch_gather_rows(d_wih, L.Wih_r, perm4, 4 * H, L.in, st));
+    LAUNCH(1, launch_gather_rows(d_whh, d_whh_r, perm4, 4 * H, H, st));
+    LAUNCH(1, launch_transpose(d_whh_r, H, L.Whh_t, 4 * H, H, st));  // -> [H][4H]
+  }
+
+  // ---- predictor (models.py:143-187; haste/nbrc.py:134-138) ----
+  DecodeWeights& dw = h->dw;
+  memset(&dw, 0, sizeof(dw));
+  dw.H = H; dw.J = J; dw.V = V; dw.Lp = c.pred_layers; dw.blank = c.blank; dw.bos = c.bos;
+  for (int l = 0; l < c.pred_layers; ++l) {
+    const std::string p = "predictor.rnn_stack.rnns." + std::to_string(l) + ".";
+    NEED(kern, p + "kernel");
+    NEED(rk, p + "recurrent_kernel");
+    NEED(kb, p + "bias");
+    NEED(rb, p + "recurrent_bias");
+    NEED(hs, "predictor.rnn_stack.hs." + std::to_string(l));
+    float *t_h0, *t_rb, *bs, *bh;
+    CK(upload(h, *hs, &t_h0));
+    CK(upload(h, interleave(*rb, 3), &t_rb));
+    if (bn_fold("predictor.rnn_stack.bns." + std::to_string(l), &bs, &bh)) return RNNT_B200_ERR_STATE;
+    dw.h0[l] = t_h0; dw.rbias[l] = t_rb; dw.bn_scale[l] = bs; dw.bn_shift[l] = bh;
+    // recurrent_kernel [H(k)][3H gate-major] -> [H(k)][unit*3+gate]
+    float *d_rk, *d_t1, *d_t2, *Rt;
+    CK(tmp_upload(*rk, &d_rk));
+    CK(tmp_alloc((size_t)3 * H * H, &d_t1));
+    CK(tmp_alloc((size_t)3 * H * H, &d_t2));
+    CK(dalloc(h, (size_t)3 * H * H, &Rt));
+    LAUNCH(1, launch_transpose(d_rk, 3 * H, d_t1, H, 3 * H, st));   // [3H][H]
+    LAUNCH(1, launch_gather_rows(d_t1, d_t2, perm3, 3 * H, H, st));  // rows interleaved
+    LAUNCH(1, launch_transpose(d_t2, H, Rt, 3 * H, H, st));          // [H][3H interleaved]
+    dw.Rt[l] = Rt;
+    float* d_k;
+    CK(tmp_upload(*kern, &d_k));
+    if (l == 0) {
+      // table0 = (embed * ffn^T + ffn.b) * kernel_0 + bias_0  -> [V][3H] gate-major
+      NEED(emb, "predictor.embed.weight");
+      float *d_emb, *d_e1 = nullptr, *d_k0t, *d_kb, *table;
+      CK(tmp_upload(*emb, &d_emb));
+      const std::vector<float>* fw = need("predictor.ffn.weight");
+      const std::vector<float>* fbias = need("predictor.ffn.bias");
+      if (fw) {
+        if (!fbias) return fail(h, RNNT_B200_ERR_STATE, "missing weight: predictor.ffn.bias");
+        float *d_fw, *d_fb;
+        CK(tmp_upload(*fw, &d_fw));
+        CK(tmp_upload(*fbias, &d_fb));
+        CK(tmp_alloc((size_t)V * H, &d_e1));
+        LAUNCH(1, launch_gemm_nt_f32(d_emb, E, d_fw, E, d_fb, d_e1, H, V, H, E, st));
+      } else {
+        if (E != H) return fail(h, RNNT_B200_ERR_STATE, "missing weight: predictor.ffn.weight (required when embed_sz != hidden_sz, models.py:160-163)");
+        d_e1 = d_emb;
+      }
+      CK(tmp_alloc((size_t)3 * H * H, &d_k0t));
+      CK(tmp_upload(*kb, &d_kb));
+      CK(dalloc(h, (size_t)V * 3 * H, &table));
+      LAUNCH(1, launch_transpose(d_k, 3 * H, d_k0t, H, 3 * H, st));  // [3H][H]
+      LAUNCH(1, launch_gemm_nt_f32(d_e1, H, d_k0t, H, d_kb, table, 3 * H, V, 3 * H, H, st));
+      dw.table0 = table;
+    } else {
+      float *d_a, *d_b, *Kt, *t_kb;
+      CK(tmp_alloc((size_t)3 * H * H, &d_a));
+      CK(tmp_alloc((size_t)3 * H * H, &d_b));
+      CK(dalloc(h, (size_t)3 * H * H, &Kt));
+      LAUNCH(1, launch_transpose(d_k, 3 * H, d_a, H, 3 * H, st));
+      LAUNCH(1, launch_gather_rows(d_a, d_b, perm3, 3 * H, H, st));
+      LAUNCH(1, launch_transpose(d_b, H, Kt, 3 * H, H, st));
+      CK(upload(h, interleave(*kb, 3), &t_kb));
+      dw.Kt[l] = Kt; dw.kbias[l] = t_kb;
+    }
+  }
+
+  // ---- joint (models.py:116-140, concat) ----
+  {
+    NEED(w1, "joint.joint.0.weight");
+    NEED(b1, "joint.joint.0.bias");
+    NEED(w2, "joint.joint.2.weight");
+    NEED(b2, "joint.joint.2.bias");
+    float *t_b1, *t_b2, *d_w2, *W1p_t, *W1e_t, *W2_t;
+    CK(upload(h, *w1, &h->W1));
+    CK(upload(h, *b1, &t_b1));
+    CK(upload(h, *b2, &t_b2));
+    CK(tmp_upload(*w2, &d_w2));
+    CK(dalloc(h, (size_t)H * J, &W1p_t));
+    CK(dalloc(h, (size_t)H * J, &W1e_t));
+    CK(dalloc(h, (size_t)J * V, &W2_t));
+    LAUNCH(1, launch_transpose(h->W1, 2 * H, W1p_t, J, H, st));      // pred half: cat((h_pred, h_enc)) -> first H columns
+    LAUNCH(1, launch_transpose(h->W1 + H, 2 * H, W1e_t, J, H, st));  // enc half
+    LAUNCH(1, launch_transpose(d_w2, J, W2_t, V, J, st));
+    dw.W1p_t = W1p_t; dw.W1e_t = W1e_t; dw.b1 = t_b1; dw.W2_t = W2_t; dw.b2 = t_b2;
+  }
+#undef NEED
+  CK(cudaStreamSynchronize(st));
+  for (void* p : tmp) cudaFree(p);
+  h->raw.clear();
+  h->finalized = true;
+  return RNNT_B200_OK;
+}
+
+int64_t rnnt_b200_num_frames(rnnt_b200_handle h, int64_t n) { return h ? num_frames(h->cfg, n) : -1; }
+int64_t rnnt_b200_num_steps(rnnt_b200_handle h, int64_t n) { return h ? num_steps(h->cfg, n) : -1; }
+
+static int ensure_encode_ws(rnnt_b200_handle h, int B, int T) {
+  const rnnt_b200_config& c = h->cfg;
+  const size_t M = (size_t)B * T, H = c.hidden_sz, X = (size_t)c.n_mels * c.n_stack, Bp = bp_of(B);
+  CK(h->lnx.ensure(M * X * 4));
+  CK(h->xp.ensure(M * 4 * H * 4));
+  CK(h->ya.ensure(M * H * 4));
+  CK(h->yb.ensure(M * H * 4));
+  CK(h->ehT[0].ensure(H * Bp * 4));
+  CK(h->ehT[1].ensure(H * Bp * 4));
+  CK(h->ecT.ensure(H * Bp * 4));
+  return 0;
+}
+static int ensure_decode_ws(rnnt_b200_handle h, int B, int T, int trace_cap) {
+  const rnnt_b200_config& c = h->cfg;
+  const size_t M = (size_t)B * T, H = c.hidden_sz, J = c.joint_sz, V = c.vocab_sz, Bp = bp_of(B);
+  CK(h->ep.ensure(M * J * 4));
+  CK(h->dhT.ensure((size_t)c.pred_layers * 2 * H * Bp * 4));
+  CK(h->dxT.ensure(2 * H * Bp * 4));
+  CK(h->dgT.ensure(H * Bp * 4));
+  CK(h->deT.ensure(H * Bp * 4));
+  CK(h->dppT.ensure(J * Bp * 4));
+  CK(h->dzT.ensure(J * Bp * 4));
+  CK(h->dpart.ensure((V / 32) * Bp * 4 * 4));
+  CK(h->dlse.ensure(std::max<size_t>((size_t)B * trace_cap, 1) * 4));
+  return 0;
+}
+
+int32_t rnnt_b200_reserve(rnnt_b200_handle h, int32_t max_batch, int64_t max_samples) {
+  if (!h || max_batch < 1 || max_samples < 1) return fail(h, RNNT_B200_ERR_INVALID, "bad reserve() arguments");
+  CK(cudaSetDevice(h->cfg.device));
+  const rnnt_b200_config& c = h->cfg;
+  const int64_t T = std::max<int64_t>(num_steps(c, max_samples), 1);
+  const size_t X = (size_t)c.n_mels * c.n_stack;
+  CK(h->feats.ensure((size_t)max_batch * T * X * 4));
+  if (int r = ensure_encode_ws(h, max_batch, (int)T)) return r;
+  if (int r = ensure_decode_ws(h, max_batch, (int)T, 0)) return r;
+  CK(h->t_enc.ensure((size_t)max_batch * T * c.hidden_sz * 4));
+  CK(h->t_audio.ensure((size_t)max_batch * max_samples * 4));
+  CK(h->t_lens.ensure((size_t)max_batch * 4 * 2));
+  return RNNT_B200_OK;
+}
+
+static int check_ready(rnnt_b200_handle h) {
+  if (!h) return RNNT_B200_ERR_INVALID;
+  if (!h->finalized) return fail(h, RNNT_B200_ERR_STATE, "finalize() has not been called");
+  cudaError_t e = cudaSetDevice(h->cfg.device);
+  if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
+  return 0;
+}
+
+int32_t rnnt_b200_features(rnnt_b200_handle h, const float* audio, const int32_t* lens, int32_t B, int64_t n, float* feats,
+                           void* stream) {
+  if (int r = check_ready(h)) return r;
+  const rnnt_b200_config& c = h->cfg;
+  if (!audio || !feats || B < 1 || B > 65535) return fail(h, RNNT_B200_ERR_INVALID, "features: bad arguments");
+  if (n <= c.n_fft / 2) return fail(h, RNNT_B200_ERR_INVALID, "features: need more than n_fft/2 samples (reflect padding, torch.stft)");
+  const int64_t T = num_steps(c, n);
+  if (T < 1) return fail(h, RNNT_B200_ERR_INVALID, "features: input shorter than one stacked row");
+  FrontendArgs a;
+  a.audio = audio; a.n = n; a.lens = lens; a.out = feats; a.T_out = (int)T; a.frame0 = 0; a.is_stream = 0;
+  a.n_mels = c.n_mels; a.n_stack = c.n_stack; a.D = c.downsample; a.hop = c.hop_length; a.win = c.win_length;
+  a.window = h->window; a.tw = h->tw; a.mel_start = h->mel_start; a.mel_count = h->mel_count; a.mel_off = h->mel_off;
+  a.mel_w = h->mel_w; a.log_offset = c.log_offset;
+  LAUNCH(1, launch_mel_stack(a, B, (cudaStream_t)stream));
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_logmel(rnnt_b200_handle h, const float* audio, const int32_t* lens, int32_t B, int64_t n, float* out,
+                         void* stream) {
+  if (int r = check_ready(h)) return r;
+  const rnnt_b200_config& c = h->cfg;
+  if (!audio || !out || B < 1 || B > 65535) return fail(h, RNNT_B200_ERR_INVALID, "logmel: bad arguments");
+  if (n <= c.n_fft / 2) return fail(h, RNNT_B200_ERR_INVALID, "logmel: need more than n_fft/2 samples (reflect padding, torch.stft)");
+  FrontendArgs a;
+  a.audio = audio; a.n = n; a.lens = lens; a.out = out; a.T_out = (int)num_frames(c, n); a.frame0 = 0; a.is_stream = 0;
+  a.n_mels = c.n_mels; a.n_stack = 1; a.D = 1; a.hop = c.hop_length; a.win = c.win_length;
+  a.window = h->window; a.tw = h->tw; a.mel_start = h->mel_start; a.mel_count = h->mel_count; a.mel_off = h->mel_off;
+  a.mel_w = h->mel_w; a.log_offset = c.log_offset;
+  LAUNCH(1, launch_mel_stack(a, B, (cudaStream_t)stream));
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_features_stream(rnnt_b200_handle h, const float* window, int32_t B, int64_t W, float* feats, void* stream) {
+  if (int r = check_ready(h)) return r;
+  const rnnt_b200_config& c = h->cfg;
+  if (!window || !feats || B < 1 || B > 65535) return fail(h, RNNT_B200_ERR_INVALID, "features_stream: bad arguments");
+  const int64_t F = num_frames(c, W);
+  const int64_t a0 = F / 3 + 1;  // StreamPostprocess, transforms.py:338-341
+  if (W <= c.n_fft / 2 || a0 + c.n_stack > F)
+    return fail(h, RNNT_B200_ERR_INVALID, "features_stream: window too short for n_stack frames after the middle-third crop");
+  FrontendArgs a;
+  a.audio = window; a.n = W; a.lens = nullptr; a.out = feats; a.T_out = 1; a.frame0 = (int)a0; a.is_stream = 1;
+  a.n_mels = c.n_mels; a.n_stack = c.n_stack; a.D = c.downsample; a.hop = c.hop_length; a.win = c.win_length;
+  a.window = h->window; a.tw = h->tw; a.mel_start = h->mel_start; a.mel_count = h->mel_count; a.mel_off = h->mel_off;
+  a.mel_w = h->mel_w; a.log_offset = c.log_offset;
+  LAUNCH(1, launch_mel_stack(a, B, (cudaStream_t)stream));
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* lens_T, int32_t B, int32_t T, float* state_h,
+                         float* state_c, int32_t use_state_in, float* enc_out, void* stream) {
+  if (int r = check_ready(h)) return r;
+  const rnnt_b200_config& c = h->cfg;
+  if (!feats || !enc_out || B < 1 || T < 1) return fail(h, RNNT_B200_ERR_INVALID, "encode: bad arguments");
+  if (use_state_in && (!state_h || !state_c)) return fail(h, RNNT_B200_ERR_INVALID, "encode: use_state_in needs state_h and state_c");
+  if ((state_h == nullptr) != (state_c == nullptr)) return fail(h, RNNT_B200_ERR_INVALID, "encode: state_h and state_c must both be given");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = c.hidden_sz, X = c.n_mels * c.n_stack, Bp = bp_of(B);
+  const int64_t M = (int64_t)B * T;
+  if (int r = ensure_encode_ws(h, B, T)) return r;
+  if (h->profiling) cudaEventRecord(h->ev[0], st);
+  LAUNCH(1, launch_layernorm(feats, h->lnx.as<float>(), h->ln_g, h->ln_b, M, X, c.ln_eps, st));
+  for (int l = 0; l < c.enc_layers; ++l) {
+    const EncLayer& L = h->enc[l];
+    const float* A = l == 0 ? h->lnx.as<float>() : ((l - 1) & 1 ? h->yb.as<float>() : h->ya.as<float>());
+    float* y = (l == c.enc_layers - 1) ? enc_out : (l & 1 ? h->yb.as<float>() : h->ya.as<float>());
+    LAUNCH(1, launch_gemm_nt_f32(A, L.in, L.Wih_r, L.in, L.bias_r, h->xp.as<float>(), 4 * H, M, 4 * H, L.in, st));
+    if (use_state_in) {
+      LAUNCH(1, launch_state_to_T(state_h + (size_t)l * B * H, h->ehT[0].as<float>(), B, Bp, H, st));
+      LAUNCH(1, launch_state_to_T(state_c + (size_t)l * B * H, h->ecT.as<float>(), B, Bp, H, st));
+    } else {
+      LAUNCH(1, launch_state_broadcast_T(L.h0, h->ehT[0].as<float>(), B, Bp, H, st));
+      LAUNCH(1, launch_state_broadcast_T(L.c0, h->ecT.as<float>(), B, Bp, H, st));
+    }
+    LstmStepArgs a;
+    a.Whh_t = L.Whh_t; a.cT = h->ecT.as<float>(); a.xp = h->xp.as<float>(); a.bn_scale = L.bn_scale; a.bn_shift = L.bn_shift;
+    a.y = y; a.lens_T = lens_T; a.T = T; a.B = B; a.Bp = Bp; a.H = H;
+    for (int t = 0; t < T; ++t) {
+      a.t = t;
+      a.hT_in = h->ehT[t & 1].as<float>();
+      a.hT_out = h->ehT[(t + 1) & 1].as<float>();
+      LAUNCH(1, launch_lstm_step(a, st));
+    }
+    if (state_h) {
+      LAUNCH(1, launch_state_from_T(h->ehT[T & 1].as<float>(), state_h + (size_t)l * B * H, B, Bp, H, st));
+      LAUNCH(1, launch_state_from_T(h->ecT.as<float>(), state_c + (size_t)l * B * H, B, Bp, H, st));
+    }
+  }
+  if (h->profiling) cudaEventRecord(h->ev[1], st);
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_predict(rnnt_b200_handle h, const int32_t* tokens, int32_t B, float* state_h, int32_t use_state_in,
+                          float* out, void* stream) {
+  if (int r = check_ready(h)) return r;
+  const rnnt_b200_config& c = h->cfg;
+  if (!tokens || !state_h || !out || B < 1 || B > kDecodeMaxBatch)
+    return fail(h, RNNT_B200_ERR_INVALID, "predict: bad arguments (1 <= B <= 256, state_h and out required)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = c.hidden_sz, Bp = bp_of(B);
+  if (int r = ensure_decode_ws(h, B, 1, 0)) return r;
+  const size_t hb = (size_t)H * Bp;
+  float* dh = h->dhT.as<float>();
+  for (int l = 0; l < c.pred_layers; ++l) {
+    float* in = dh + (size_t)(2 * l) * hb;
+    float* outb = dh + (size_t)(2 * l + 1) * hb;
+    if (use_state_in) LAUNCH(1, launch_state_to_T(state_h + (size_t)l * B * H, in, B, Bp, H, st));
+    else LAUNCH(1, launch_state_broadcast_T(h->dw.h0[l], in, B, Bp, H, st));
+    PredictArgs a;
+    a.w = h->dw; a.tokens = tokens; a.B = B; a.Bp = Bp; a.layer = l; a.hT_in = in; a.hT_out = outb;
+    a.xT_in = l == 0 ? nullptr : h->dxT.as<float>() + (size_t)((l - 1) & 1) * hb;
+    a.xT_out = (l == c.pred_layers - 1) ? h->dgT.as<float>() : h->dxT.as<float>() + (size_t)(l & 1) * hb;
+    LAUNCH(1, launch_gru_layer(a, st));
+    LAUNCH(1, launch_state_from_T(outb, state_h + (size_t)l * B * H, B, Bp, H, st));
+  }
+  LAUNCH(1, launch_state_from_T(h->dgT.as<float>(), out, B, Bp, H, st));
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_joint(rnnt_b200_handle h, const float* h_pred, const float* h_enc, int32_t B, float* logits, void* stream) {
+  if (int r = check_ready(h)) return r;
+  const rnnt_b200_config& c = h->cfg;
+  if (!h_pred || !h_enc || !logits || B < 1) return fail(h, RNNT_B200_ERR_INVALID, "joint: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = c.hidden_sz, Bp = bp_of(B);
+  if (int r = ensure_decode_ws(h, B, 1, 0)) return r;
+  LAUNCH(1, launch_state_to_T(h_pred, h->dgT.as<float>(), B, Bp, H, st));
+  LAUNCH(1, launch_state_to_T(h_enc, h->deT.as<float>(), B, Bp, H, st));
+  JointArgs a;
+  a.w = h->dw; a.B = B; a.Bp = Bp; a.gT = h->dgT.as<float>(); a.eT = h->deT.as<float>(); a.zT = h->dzT.as<float>();
+  a.logits = logits;
+  LAUNCH(2, launch_joint(a, st));
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int32_t* lens_T, int32_t B, int32_t T,
+                                int32_t max_iters, float* pred_state_h, float* pred_out, int32_t use_state_in,
+                                int32_t* tokens_out, int32_t U_cap, int32_t* ntok_out, double* neg_logp_out,
+                                uint8_t* iters_out, float* trace_logp, int32_t trace_cap, void* stream) {
+  if (int r = check_ready(h)) return r;
+  const rnnt_b200_config& c = h->cfg;
+  if (!enc || !tokens_out || !ntok_out || B < 1 || T < 1 || max_iters < 1 || max_iters > 255)
+    return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: bad arguments");
+  if (B > kDecodeMaxBatch) return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: B > 256 (split the batch)");
+  if ((int64_t)U_cap < (int64_t)max_iters * T) return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: U_cap < max_iters*T");
+  if (use_state_in && (!pred_state_h || !pred_out)) return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: use_state_in needs pred_state_h and pred_out");
+  if (trace_logp && trace_cap < 1) return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: trace_cap < 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = c.hidden_sz, J = c.joint_sz, Bp = bp_of(B);
+  const int64_t M = (int64_t)B * T;
+  if (int r = ensure_decode_ws(h, B, T, trace_logp ? trace_cap : 0)) return r;
+  if (h->profiling) cudaEventRecord(h->ev[2], st);
+  // hoisted encoder half of the joint's first Linear (incl. its bias): ep = enc * W1[:, H:]^T + b1
+  LAUNCH(1, launch_gemm_nt_f32(enc, H, h->W1 + H, 2 * H, h->dw.b1, h->ep.as<float>(), J, M, J, H, st));
+  if (h->profiling) cudaEventRecord(h->ev[3], st);
+  const size_t hb = (size_t)H * Bp;
+  float* dh = h->dhT.as<float>();
+  DecodeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.w = h->dw;
+  for (int l = 0; l < c.pred_layers; ++l) {
+    a.hT[l][0] = dh + (size_t)(2 * l) * hb;
+    a.hT[l][1] = dh + (size_t)(2 * l + 1) * hb;
+    if (use_state_in) LAUNCH(1, launch_state_to_T(pred_state_h + (size_t)l * B * H, a.hT[l][0], B, Bp, H, st));
+    else LAUNCH(1, launch_state_broadcast_T(h->dw.h0[l], a.hT[l][0], B, Bp, H, st));
+  }
+  if (use_state_in) LAUNCH(1, launch_state_to_T(pred_out, h->dgT.as<float>(), B, Bp, H, st));
+  if (iters_out) CK(cudaMemsetAsync(iters_out, 0, (size_t)B * T, st));
+  a.ep = h->ep.as<float>(); a.lens_T = lens_T; a.B = B; a.Bp = Bp; a.T = T; a.max_iters = max_iters; a.use_state_in = use_state_in;
+  a.xT = h->dxT.as<float>(); a.gT = h->dgT.as<float>(); a.ppT = h->dppT.as<float>(); a.zT = h->dzT.as<float>();
+  a.part = h->dpart.as<float>(); a.trace_lse = h->dlse.as<float>();
+  a.tokens = tokens_out; a.U_cap = U_cap; a.ntok = ntok_out; a.neg_logp = neg_logp_out; a.iters = iters_out;
+  a.trace = trace_logp; a.trace_cap = trace_logp ? trace_cap : 0;
+  LAUNCH(1, launch_decode(a, h->coop_blocks, st));
+  if (pred_state_h)
+    for (int l = 0; l < c.pred_layers; ++l)
+      LAUNCH(1, launch_state_from_T(a.hT[l][0], pred_state_h + (size_t)l * B * H, B, Bp, H, st));
+  if (pred_out) LAUNCH(1, launch_state_from_T(h->dgT.as<float>(), pred_out, B, Bp, H, st));
+  if (h->profiling) cudaEventRecord(h->ev[4], st);
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_transcribe(rnnt_b200_handle h, const float* audio, const int32_t* lens, int32_t B, int64_t n, int32_t max_iters,
+                             int32_t* tokens_out, int32_t U_cap, int32_t* ntok_out, double* neg_logp_out, uint8_t* iters_out,
+                             void* stream) {
+  if (int r = check_ready(h)) return r;
+  const rnnt_b200_config& c = h->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t T = num_steps(c, n);
+  if (T < 1) return fail(h, RNNT_B200_ERR_INVALID, "transcribe: input shorter than one stacked row");
+  const size_t X = (size_t)c.n_mels * c.n_stack;
+  CK(h->feats.ensure((size_t)B * T * X * 4));
+  CK(h->t_enc.ensure((size_t)B * T * c.hidden_sz * 4));
+  const int32_t* lens_T = nullptr;
+  if (lens) {
+    // lens_T[b] = num_steps(lens[b]); computed on the host would need a sync, so the feature
+    // kernel's own rule is replayed by a tiny device pass stored behind t_lens
+    CK(h->t_lens.ensure((size_t)B * 4 * 2));
+  }
+  if (h->profiling) cudaEventRecord(h->ev[5], st);
+  if (int r = rnnt_b200_features(h, audio, lens, B, n, h->feats.as<float>(), stream)) return r;
+  if (lens) {
+    int32_t* lt = h->t_lens.as<int32_t>() + B;
+    LAUNCH(1, launch_lens_to_steps(lens, lt, B, c.hop_length, c.n_stack, c.downsample, (int)T, st));
+    lens_T = lt;
+  }
+  if (int r = rnnt_b200_encode(h, h->feats.as<float>(), lens_T, B, (int)T, nullptr, nullptr, 0, h->t_enc.as<float>(), stream)) return r;
+  return rnnt_b200_decode_greedy(h, h->t_enc.as<float>(), lens_T, B, (int)T, max_iters, nullptr, nullptr, 0, tokens_out, U_cap,
+                                 ntok_out, neg_logp_out, iters_out, nullptr, 0, stream);
+}
+
+int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, const int32_t* lens_host, int32_t B, int64_t n,
+                                  int32_t max_iters, int32_t* tokens_host, int32_t U_cap, int32_t* ntok_host,
+                                  double* neg_logp_host, void* stream) {
+  if (int r = check_ready(h)) return r;
+  if (!audio_host || !tokens_host || !ntok_host || B < 1 || n < 1) return fail(h, RNNT_B200_ERR_INVALID, "transcribe_host: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(h->t_audio.ensure((size_t)B * n * 4));
+  CK(h->t_lens.ensure((size_t)B * 4 * 2));
+  CK(h->t_tokens.ensure((size_t)B * U_cap * 4));
+  CK(h->t_ntok.ensure((size_t)B * 4));
+  CK(h->t_nlp.ensure((size_t)B * 8));
+  CK(cudaMemcpyAsync(h->t_audio.p, audio_host, (size_t)B * n * 4, cudaMemcpyHostToDevice, st));
+  if (lens_host) CK(cudaMemcpyAsync(h->t_lens.p, lens_host, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  if (int r = rnnt_b200_transcribe(h, h->t_audio.as<float>(), lens_host ? h->t_lens.as<int32_t>() : nullptr, B, n, max_iters,
+                                   h->t_tokens.as<int32_t>(), U_cap, h->t_ntok.as<int32_t>(), h->t_nlp.as<double>(), nullptr, stream))
+    return r;
+  CK(cudaMemcpyAsync(tokens_host, h->t_tokens.p, (size_t)B * U_cap * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ntok_host, h->t_ntok.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (neg_logp_host) CK(cudaMemcpyAsync(neg_logp_host, h->t_nlp.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return RNNT_B200_OK;
+}
+
+int64_t rnnt_b200_kernel_launches(rnnt_b200_handle h) { return h ? h->launches : -1; }
+
+int32_t rnnt_b200_set_profiling(rnnt_b200_handle h, int32_t enable) {
+  if (!h) return RNNT_B200_ERR_INVALID;
+  h->profiling = enable != 0;
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_stage_times_ms(rnnt_b200_handle h, float* out) {
+  if (!h || !out) return RNNT_B200_ERR_INVALID;
+  if (!h->profiling) return fail(h, RNNT_B200_ERR_STATE, "profiling is not enabled");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventSynchronize(h->ev[4]));
+  // ev5 -> ev0: features ; ev0 -> ev1: layernorm + input GEMMs + recurrent steps ; ev2 -> ev3: ep GEMM ; ev3 -> ev4: decode
+  float f = 0, e = 0, j = 0, d = 0;
+  CK(cudaEventElapsedTime(&f, h->ev[5], h->ev[0]));
+  CK(cudaEventElapsedTime(&e, h->ev[0], h->ev[1]));
+  CK(cudaEventElapsedTime(&j, h->ev[2], h->ev[3]));
+  CK(cudaEventElapsedTime(&d, h->ev[3], h->ev[4]));
+  out[0] = f; out[1] = e; out[2] = 0.f; out[3] = j; out[4] = d;
+  return RNNT_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+// Internal launcher interface between the C-ABI layer (capi.cu) and the kernels.
+#pragma once
+#include "common.cuh"
+
+namespace rnnt {
+
+// ---------------- frontend.cu ----------------
+constexpr int kFrontendMaxWarps = 16;
+
+struct FrontendArgs {
+  const float* audio;      // [B, n]
+  int64_t n;               // row stride (samples)
+  const int32_t* lens;     // [B] valid samples or nullptr
+  float* out;              // [B, T_out, n_mels*n_stack]
+  int T_out;               // rows per utterance
+  int frame0;              // first frame of row t is t*D + frame0
+  int is_stream;           // 1: every row valid (serving window), 0: rows >= T_b are zero-filled
+  int n_mels, n_stack, D, hop, win;
+  const float* window;     // [win]
+  const float2* tw;        // [512] exp(-2 pi i j / 1024)
+  const int* mel_start;    // [n_mels] first non-zero FFT bin
+  const int* mel_count;    // [n_mels] number of taps
+  const int* mel_off;      // [n_mels] offset into mel_w
+  const float* mel_w;      // taps
+  float log_offset;
+};
+size_t frontend_smem_bytes(int n_stack, int n_mels);
+cudaError_t launch_mel_stack(const FrontendArgs& a, int B, cudaStream_t st);
+cudaError_t launch_layernorm(const float* in, float* out, const float* gamma, const float* beta, int64_t rows, int X,
+                             float eps, cudaStream_t st);
+
+// ---------------- gemm_simt.cu ----------------
+// C[M,N] = A[M,K] * W[N,K]^T + bias[N]   (fp32 FMA; lda/ldw/ldc in elements, K % 4 == 0)
+cudaError_t launch_gemm_nt_f32(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                               int64_t M, int N, int K, cudaStream_t st);
+// out[c][r] = in[r*ld_in + c]   (out is dense [cols][rows])
+cudaError_t launch_transpose(const float* in, int ld_in, float* out, int rows, int cols, cudaStream_t st);
+// out[r][perm(c)] row/column permutations used by the weight repack (see capi.cu)
+cudaError_t launch_gather_rows(const float* in, float* out, const int* src_row, int rows_out, int cols, cudaStream_t st);
+
+// ---------------- lstm.cu ----------------
+struct LstmStepArgs {
+  const float* Whh_t;   // [H][4H] k-major, columns interleaved unit*4 + gate(i,f,g,o)
+  const float* hT_in;   // [H][Bp]
+  float* hT_out;        // [H][Bp]
+  float* cT;            // [H][Bp] in/out
+  const float* xp;      // [B*T][4H] hoisted input projection incl. both biases, interleaved columns
+  const float* bn_scale;  // [H]
+  const float* bn_shift;  // [H]
+  float* y;             // [B*T][H] BatchNorm(h_t)
+  const int32_t* lens_T;  // [B] or nullptr
+  int t, T, B, Bp, H;
+};
+cudaError_t configure_lstm();
+cudaError_t launch_lstm_step(const LstmStepArgs& a, cudaStream_t st);
+// state layout helpers: [B,H] row-major <-> [H][Bp] feature-major
+cudaError_t launch_state_to_T(const float* in_BH, float* out_HB, int B, int Bp, int H, cudaStream_t st);
+cudaError_t launch_state_from_T(const float* in_HB, float* out_BH, int B, int Bp, int H, cudaStream_t st);
+cudaError_t launch_state_broadcast_T(const float* vec_H, float* out_HB, int B, int Bp, int H, cudaStream_t st);
+// steps[b] = min(T_max, encoder steps of an utterance with lens[b] samples)
+cudaError_t launch_lens_to_steps(const int32_t* lens, int32_t* steps, int B, int hop, int n_stack, int D, int T_max,
+                                 cudaStream_t st);
+
+// ---------------- decode.cu ----------------
+constexpr int kMaxPredLayers = 4;
+constexpr int kDecodeMaxBatch = 256;
+
+struct DecodeWeights {
+  int H, J, V, Lp, blank, bos;
+  const float* table0;          // [V][3H] gate-major (z|r|g): (embed*ffn)*kernel_0 + bias_0
+  const float* Rt[kMaxPredLayers];     // [H][3H] k-major, columns unit*3 + gate
+  const float* rbias[kMaxPredLayers];  // [3H] interleaved
+  const float* Kt[kMaxPredLayers];     // layers >= 1: [H][3H] k-major interleaved
+  const float* kbias[kMaxPredLayers];  // layers >= 1: [3H] interleaved
+  const float* h0[kMaxPredLayers];     // [H] learnable initial state
+  const float* bn_scale[kMaxPredLayers];
+  const float* bn_shift[kMaxPredLayers];
+  const float* W1p_t;           // [H][J]  pred half of joint.0, k-major
+  const float* W1e_t;           // [H][J]  enc half of joint.0, k-major (standalone joint only)
+  const float* b1;              // [J]
+  const float* W2_t;            // [J][V]  k-major
+  const float* b2;              // [V]
+};
+
+struct DecodeArgs {
+  DecodeWeights w;
+  const float* ep;        // [B][T][J] enc half projection incl. b1
+  const int32_t* lens_T;  // [B] or nullptr
+  int B, Bp, T, max_iters, use_state_in;
+  // feature-major state, ping-pong where a phase reads and writes the same vector
+  float* hT[kMaxPredLayers][2];  // [H][Bp]
+  float* xT;      // [2][H][Bp] BatchNorm output of the layer below (input of layers >= 1), ping-pong by layer parity
+  float* gT;      // [H][Bp] predictor output (h_t_pred)
+  float* ppT;     // [J][Bp] W1p * g
+  float* zT;      // [J][Bp] tanh(pp + ep[t_b])
+  float* part;    // [V/32][Bp][4] per-tile (max, argmax, sumexp, -) partials
+  float* trace_lse;  // [B][trace_cap] log-sum-exp of every traced evaluation (workspace)
+  // outputs
+  int32_t* tokens; int U_cap; int32_t* ntok; double* neg_logp; uint8_t* iters; float* trace; int trace_cap;
+};
+size_t decode_smem_bytes();
+cudaError_t configure_decode(int device, int* max_coop_blocks);
+cudaError_t launch_decode(const DecodeArgs& a, int grid_blocks, cudaStream_t st);
+
+// standalone predictor step / joint (same phase code, one launch per phase)
+struct PredictArgs {
+  DecodeWeights w;
+  const int32_t* tokens;  // [B]
+  int B, Bp, layer;
+  const float* hT_in; float* hT_out;   // [H][Bp]
+  const float* xT_in;     // layers >= 1
+  float* xT_out;          // BN(h_new)
+};
+cudaError_t launch_gru_layer(const PredictArgs& a, cudaStream_t st);
+struct JointArgs {
+  DecodeWeights w;
+  int B, Bp;
+  const float* gT; const float* eT;   // [H][Bp]
+  float* zT;                           // [J][Bp]
+  float* logits;                       // [B][V]
+};
+cudaError_t launch_joint(const JointArgs& a, cudaStream_t st);
+
+}  // namespace rnnt

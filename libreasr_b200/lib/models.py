@@ -1,0 +1,284 @@
+"""Drop-in module surface of the reference's ``libreasr/lib/models.py`` for the inference
+path: ``Transducer`` / ``Encoder`` / ``Predictor`` / ``Joint`` with the same constructor
+arguments, ``state_dict`` key set and method signatures, executing
+on the sm_100a CUDA library through the C ABI (``libreasr_b200.engine``).
+
+The ``nn.Module`` objects here are parameter CONTAINERS (so ``load_state_dict`` /
+``state_dict`` / ``.to()`` keep working with reference checkpoints); they never run a
+PyTorch forward.  Anything that needs a CPU or a non-CUDA device raises: there is no
+fallback path.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from ..engine import Engine, EngineConfig, tokens_to_lists
+
+__all__ = ["Transducer", "Encoder", "Predictor", "Joint", "NBRC", "CustomRNNParams"]
+
+
+class NBRC(nn.Module):
+    """Parameter container for the Haste-style GRU ("NBRC") cell
+    (reference libreasr/lib/layers/haste/nbrc.py:134-138): gate layout z,r,g."""
+
+    def __init__(self, input_size, hidden_size, batch_first=True):
+        super().__init__()
+        self.input_size, self.hidden_size, self.batch_first = input_size, hidden_size, batch_first
+        self.kernel = nn.Parameter(torch.empty(input_size, hidden_size * 3))
+        self.recurrent_kernel = nn.Parameter(torch.empty(hidden_size, hidden_size * 3))
+        self.bias = nn.Parameter(torch.zeros(hidden_size * 3))
+        self.recurrent_bias = nn.Parameter(torch.zeros(hidden_size * 3))
+        for i in range(3):  # nbrc.py:201-212
+            nn.init.xavier_uniform_(self.kernel.data[:, i * hidden_size:(i + 1) * hidden_size])
+            nn.init.orthogonal_(self.recurrent_kernel.data[:, i * hidden_size:(i + 1) * hidden_size])
+
+
+class CustomRNNParams(nn.Module):
+    """Parameter container mirroring ``CustomCPURNN`` (custom_rnn.py:85-132, 259-269):
+    ``hs`` learnable initial states, ``bns`` BatchNorm1d per layer, ``rnns`` single-layer
+    ``nn.LSTM`` (weight_ih_l0 ...) or ``NBRC``."""
+
+    def __init__(self, input_size, hidden_size, num_layers=1, rnn_type="LSTM", **_):
+        super().__init__()
+        assert rnn_type in ("LSTM", "NBRC"), "the path implements LSTM encoders and NBRC (GRU) predictors"
+        self.rnn_type, self.hidden_size, self.num_layers = rnn_type, hidden_size, num_layers
+        ins = [input_size] + [hidden_size] * (num_layers - 1)
+        self.hs = nn.ParameterList(
+            [nn.Parameter(torch.zeros(2 if rnn_type == "LSTM" else 1, 1, 1, hidden_size)) for _ in ins])
+        self.bns = nn.ModuleList([nn.BatchNorm1d(hidden_size) for _ in ins])
+        if rnn_type == "LSTM":
+            self.rnns = nn.ModuleList([nn.LSTM(i, hidden_size, batch_first=True) for i in ins])
+        else:
+            self.rnns = nn.ModuleList([NBRC(i, hidden_size, batch_first=True) for i in ins])
+
+
+def _owner(mod):
+    o = getattr(mod, "_owner", None)
+    if o is None:
+        raise RuntimeError(
+            f"{type(mod).__name__} must belong to a Transducer (its CUDA engine holds the repacked weights)")
+    return o()
+
+
+class Encoder(nn.Module):
+    """``Encoder`` (models.py:68-113)."""
+
+    def __init__(self, feature_sz, hidden_sz, out_sz, dropout=0.01, num_layers=2, trace=True, device="cuda:0",
+                 layer_norm=False, rnn_type="LSTM", use_tmp_state_pcent=0.9, **kwargs):
+        super().__init__()
+        if hidden_sz != out_sz:
+            raise NotImplementedError("hidden_sz != out_sz (extra Linear, models.py:97-98) is outside the built path")
+        self.num_layers = num_layers
+        self.input_norm = nn.LayerNorm(feature_sz)
+        self.rnn_stack = CustomRNNParams(feature_sz, hidden_sz, num_layers, rnn_type=rnn_type)
+
+    def param_groups(self):
+        return [p for p in self.parameters() if p.requires_grad]
+
+    def forward(self, x, state=None, lengths=None, return_state=False):
+        """x [N,T,X(,1)]; state list of (h,c) each [1,N,H] (models.py:105-113)."""
+        eng = _owner(self).engine()
+        x = x.reshape((x.size(0), x.size(1), -1)).to(eng.device, torch.float32)
+        st = None
+        if state is not None:
+            st = (torch.cat([s[0] for s in state], 0).to(eng.device), torch.cat([s[1] for s in state], 0).to(eng.device))
+        out, ns = eng.encode(x, lens_T=lengths, state=st, want_state=return_state)
+        if return_state:
+            return out, [(ns[0][i:i + 1], ns[1][i:i + 1]) for i in range(self.num_layers)]
+        return out
+
+
+class Predictor(nn.Module):
+    """``Predictor`` (models.py:143-187)."""
+
+    def __init__(self, vocab_sz, embed_sz, hidden_sz, out_sz, dropout=0.01, num_layers=2, blank=0, layer_norm=False,
+                 rnn_type="NBRC", use_tmp_state_pcent=0.9):
+        super().__init__()
+        if hidden_sz != out_sz:
+            raise NotImplementedError("hidden_sz != out_sz (extra Linear, models.py:173-174) is outside the built path")
+        self.vocab_sz, self.num_layers = vocab_sz, num_layers
+        self.embed = nn.Embedding(vocab_sz, embed_sz, padding_idx=blank)
+        self.ffn = nn.Linear(embed_sz, hidden_sz) if embed_sz != hidden_sz else nn.Sequential()
+        self.rnn_stack = CustomRNNParams(hidden_sz, hidden_sz, num_layers, rnn_type=rnn_type)
+
+    def param_groups(self):
+        return [p for p in self.parameters() if p.requires_grad]
+
+    def forward(self, x, state=None, lengths=None):
+        """x [N,1] tokens; state list of [1,N,H] -> (out [N,1,H], new state) (models.py:181-187)."""
+        eng = _owner(self).engine()
+        if x.dim() != 2 or x.size(1) != 1:
+            raise ValueError("Predictor.forward takes one token per sequence: x of shape [N, 1]")
+        st = None if state is None else torch.cat(list(state), 0).to(eng.device)
+        out, ns = eng.predict(x[:, 0], st)
+        return out[:, None, :], [ns[i:i + 1] for i in range(self.num_layers)]
+
+
+class Joint(nn.Module):
+    """``Joint`` (models.py:116-140)."""
+
+    def __init__(self, out_sz, joint_sz, vocab_sz, joint_method):
+        super().__init__()
+        self.joint_method = joint_method
+        if joint_method == "concat":
+            input_sz = 2 * out_sz
+        elif joint_method == "add":
+            raise NotImplementedError('joint_method "add" is outside the built path (config uses "concat", testing.yaml:225)')
+        else:
+            raise Exception("No such joint_method")  # models.py:124
+        self.joint = nn.Sequential(nn.Linear(input_sz, joint_sz), nn.Tanh(), nn.Linear(joint_sz, vocab_sz))
+
+    def param_groups(self):
+        return [p for p in self.parameters() if p.requires_grad]
+
+    def forward(self, h_pred, h_enc):
+        """Broadcasting ``cat`` + MLP (models.py:132-140): [...,H] x [...,H] -> logits [...,V]."""
+        eng = _owner(self).engine()
+        hp, he = torch.broadcast_tensors(h_pred.to(eng.device), h_enc.to(eng.device))
+        lead = hp.shape[:-1]
+        H = hp.shape[-1]
+        out = eng.joint(hp.reshape(-1, H).float(), he.reshape(-1, H).float())
+        return out.reshape(*lead, -1)
+
+
+class Transducer(nn.Module):
+    """``Transducer`` (models.py:190-577), inference methods."""
+
+    def __init__(self, feature_sz, embed_sz, vocab_sz, hidden_sz, out_sz, joint_sz, lang, l_e=6, l_p=2, p_j=0.0,
+                 blank=0, joint_method="concat", perf=False, act=None, use_tmp_bos=True, use_tmp_bos_pcent=0.99,
+                 encoder_kwargs={}, predictor_kwargs={}, n_stack=10, downsample=8, gemm_mode=0, **kwargs):
+        super().__init__()
+        import weakref
+
+        self.encoder = Encoder(feature_sz, hidden_sz=hidden_sz, out_sz=out_sz, **encoder_kwargs)
+        self.predictor = Predictor(vocab_sz, embed_sz=embed_sz, hidden_sz=hidden_sz, out_sz=out_sz, **predictor_kwargs)
+        self.joint = Joint(out_sz, joint_sz, vocab_sz, joint_method)
+        for m in (self.encoder, self.predictor, self.joint):
+            object.__setattr__(m, "_owner", weakref.ref(self))
+        self.lang = lang
+        self.blank = blank
+        self.bos = 2  # models.py:226-227
+        self.perf = perf
+        self.mp = False
+        self.vocab_sz = vocab_sz
+        self.lm = None
+        if feature_sz % n_stack:
+            raise ValueError("feature_sz must be n_mels * n_stack")
+        self._ecfg = EngineConfig(
+            n_mels=feature_sz // n_stack, n_stack=n_stack, downsample=downsample,
+            enc_layers=self.encoder.num_layers, pred_layers=self.predictor.num_layers, hidden_sz=hidden_sz,
+            embed_sz=embed_sz, joint_sz=joint_sz, vocab_sz=vocab_sz, blank=blank, bos=self.bos, gemm_mode=gemm_mode)
+        self._engine = None
+
+    # ---- construction ---------------------------------------------------------------
+    @staticmethod
+    def from_config(conf, lang, lm=None):
+        """models.py:236-259; ``conf["cuda"]["device"]`` must be a CUDA device."""
+        ecfg = EngineConfig.from_conf(conf)
+        m = Transducer(
+            conf["model"]["feature_sz"], conf["model"]["embed_sz"], conf["model"]["vocab_sz"],
+            conf["model"]["hidden_sz"], conf["model"]["out_sz"], conf["model"]["joint_sz"], lang,
+            p_j=conf["model"]["joint"].get("dropout", 0.0), joint_method=conf["model"]["joint"]["method"],
+            encoder_kwargs=conf["model"]["encoder"], predictor_kwargs=conf["model"]["predictor"],
+            n_stack=ecfg.n_stack, downsample=ecfg.downsample, gemm_mode=conf.get("gemm_mode", 0),
+        ).to(conf["cuda"]["device"])
+        m.mp = conf.get("mp", False)
+        return m
+
+    def param_groups(self):
+        return [self.encoder.param_groups(), self.predictor.param_groups(), self.joint.param_groups()]
+
+    def convert_to_cpu(self):
+        raise RuntimeError("libreasr_b200 is CUDA (sm_100a) only: there is no CPU inference path")
+
+    def convert_to_gpu(self):
+        self.engine()
+        return self
+
+    def load_state_dict(self, state_dict, strict=True):
+        r = super().load_state_dict(state_dict, strict=strict)
+        self._drop_engine()
+        return r
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._drop_engine()
+        return r
+
+    def _drop_engine(self):
+        if getattr(self, "_engine", None) is not None:
+            self._engine.close()
+        self._engine = None
+
+    def engine(self) -> Engine:
+        """The CUDA engine holding the repacked weights (built lazily from the parameters)."""
+        if self._engine is None:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("Transducer parameters are on %s; move the model to a CUDA device "
+                                   "(libreasr_b200 has no CPU path)" % dev)
+            eng = Engine(self._ecfg, device=dev)
+            eng.load_state_dict({k: v for k, v in self.state_dict().items()})
+            self._engine = eng
+        return self._engine
+
+    def forward(self, tpl):
+        raise NotImplementedError("training forward (models.py:308-359) is outside the built inference path")
+
+    # ---- inference (models.py:361-455) ---------------------------------------------------
+    def decode(self, *args, **kwargs):
+        res, log_p, _ = self.decode_greedy(*args, **kwargs)[:3]
+        return res, log_p
+
+    def transcribe(self, *args, **kwargs):
+        res, _, metrics, _ = self.decode_greedy(*args, **kwargs)
+        return res, metrics
+
+    def decode_greedy(self, x, max_iters=3, alpha=0.005, theta=1.0, return_logp=False):
+        """x [T,X,1] (what the inference transform pipeline yields, api-server.py:75-78) or
+        [T,X]: features of one utterance (models.py:369-455)."""
+        if self.lm is not None:
+            raise NotImplementedError("LM shallow fusion (lm.py:43-83) is a 'next' row, not part of this path")
+        eng = self.engine()
+        x = x.to(eng.device, torch.float32)
+        if x.dim() == 2:
+            x = x[:, :, None]
+        x = x[None]  # models.py:391
+        x = x.reshape(x.size(0), x.size(1), -1)  # Encoder.forward, models.py:106
+        enc, _ = eng.encode(x)
+        T = enc.shape[1]
+        r = eng.decode_greedy(enc, max_iters=max_iters, trace_cap=(max_iters * T if return_logp else 0))
+        y_seq = tokens_to_lists(r["tokens"], r["ntok"])[0]
+        iters = r["iters"][0].cpu().numpy().astype(np.int64)
+        _sum = iters.sum()
+        _ones = int((iters == 1).sum())
+        metrics = {"alignment_score": (_sum - _ones) / (_sum + 1e-4)}  # models.py:445-453
+        extra = {"iters": iters.tolist(), "outs": []}
+        if return_logp:
+            n_eval = int(_sum)
+            extra["outs"] = [o[None, None, None] for o in r["trace"][0, :n_eval]]
+        return self.lang.denumericalize(y_seq), float(r["neg_logp"][0]), metrics, extra
+
+    def transcribe_stream(self, stream, denumericalizer, max_iters=10, alpha=0.3, theta=1.0):
+        """Generator over chunks of shape [T_c, X(,1)] or None (models.py:457-577): yields
+        (all tokens so far, denumericalizer(tokens of this chunk), reset_fn)."""
+        if self.lm is not None:
+            raise NotImplementedError("LM shallow fusion (lm.py:43-83) is a 'next' row, not part of this path")
+        eng = self.engine()
+        st = {"enc": None, "pred": None}
+
+        def reset():  # models.py:480-500
+            st["enc"], st["pred"] = None, None
+
+        y = []
+        for chunk in stream:
+            if chunk is None:  # models.py:509
+                continue
+            x = chunk.to(eng.device, torch.float32)
+            x = x.reshape(1, x.size(0), -1)
+            enc, st["enc"] = eng.encode(x, state=st["enc"], want_state=True)
+            r = eng.decode_greedy(enc, max_iters=max_iters, state=st["pred"], want_state=True)
+            st["pred"] = r["state"]
+            y_seq = tokens_to_lists(r["tokens"], r["ntok"])[0]
+            y = y + y_seq
+            yield y, denumericalizer(y_seq), reset
