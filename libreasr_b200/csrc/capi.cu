@@ -69,7 +69,9 @@ struct rnnt_b200_handle_s {
   DevBuf t_audio, t_lens, t_tokens, t_ntok, t_nlp, t_iters, t_enc;
   // profiling
   bool profiling = false;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t*> evsets;  // one set of 6 events per profiled transcribe() call
+  int ev_used = 0;                   // sets holding a complete recording
+  cudaEvent_t* ev = nullptr;         // set being recorded
 };
 
 namespace {
@@ -230,7 +232,6 @@ int32_t rnnt_b200_create(const rnnt_b200_config* cfg, rnnt_b200_handle* out) {
     delete h;
     return fail_cuda(nullptr, e, "kernel configuration");
   }
-  for (auto& ev : h->ev) cudaEventCreate(&ev);
   *out = h;
   return RNNT_B200_OK;
 }
@@ -244,8 +245,10 @@ int32_t rnnt_b200_destroy(rnnt_b200_handle h) {
                     &h->dgT, &h->deT, &h->dppT, &h->dzT, &h->dpart, &h->dlse, &h->t_audio, &h->t_lens, &h->t_tokens,
                     &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc};
   for (DevBuf* b : bufs) b->release();
-  for (auto& ev : h->ev)
-    if (ev) cudaEventDestroy(ev);
+  for (cudaEvent_t* set : h->evsets) {
+    for (int i = 0; i < 6; ++i) cudaEventDestroy(set[i]);
+    delete[] set;
+  }
   delete h;
   return RNNT_B200_OK;
 }
@@ -602,7 +605,7 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
   const int H = c.hidden_sz, X = c.n_mels * c.n_stack, Bp = bp_of(B);
   const int64_t M = (int64_t)B * T;
   if (int r = ensure_encode_ws(h, B, T)) return r;
-  if (h->profiling) cudaEventRecord(h->ev[0], st);
+  if (h->ev) cudaEventRecord(h->ev[0], st);
   LAUNCH(1, launch_layernorm(feats, h->lnx.as<float>(), h->ln_g, h->ln_b, M, X, c.ln_eps, st));
   for (int l = 0; l < c.enc_layers; ++l) {
     const EncLayer& L = h->enc[l];
@@ -630,7 +633,7 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
       LAUNCH(1, launch_state_from_T(h->ecT.as<float>(), state_c + (size_t)l * B * H, B, Bp, H, st));
     }
   }
-  if (h->profiling) cudaEventRecord(h->ev[1], st);
+  if (h->ev) cudaEventRecord(h->ev[1], st);
   return RNNT_B200_OK;
 }
 
@@ -693,10 +696,10 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
   const int H = c.hidden_sz, J = c.joint_sz, Bp = bp_of(B);
   const int64_t M = (int64_t)B * T;
   if (int r = ensure_decode_ws(h, B, T, trace_logp ? trace_cap : 0)) return r;
-  if (h->profiling) cudaEventRecord(h->ev[2], st);
+  if (h->ev) cudaEventRecord(h->ev[2], st);
   // hoisted encoder half of the joint's first Linear (incl. its bias): ep = enc * W1[:, H:]^T + b1
   LAUNCH(1, launch_gemm_nt_f32(enc, H, h->W1 + H, 2 * H, h->dw.b1, h->ep.as<float>(), J, M, J, H, st));
-  if (h->profiling) cudaEventRecord(h->ev[3], st);
+  if (h->ev) cudaEventRecord(h->ev[3], st);
   const size_t hb = (size_t)H * Bp;
   float* dh = h->dhT.as<float>();
   DecodeArgs a;
@@ -720,7 +723,7 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     for (int l = 0; l < c.pred_layers; ++l)
       LAUNCH(1, launch_state_from_T(a.hT[l][0], pred_state_h + (size_t)l * B * H, B, Bp, H, st));
   if (pred_out) LAUNCH(1, launch_state_from_T(h->dgT.as<float>(), pred_out, B, Bp, H, st));
-  if (h->profiling) cudaEventRecord(h->ev[4], st);
+  if (h->ev) cudaEventRecord(h->ev[4], st);
   return RNNT_B200_OK;
 }
 
@@ -741,7 +744,17 @@ int32_t rnnt_b200_transcribe(rnnt_b200_handle h, const float* audio, const int32
     // kernel's own rule is replayed by a tiny device pass stored behind t_lens
     CK(h->t_lens.ensure((size_t)B * 4 * 2));
   }
-  if (h->profiling) cudaEventRecord(h->ev[5], st);
+  if (h->profiling) {
+    if (h->ev_used >= (int)h->evsets.size()) {
+      cudaEvent_t* set = new cudaEvent_t[6];
+      for (int i = 0; i < 6; ++i) cudaEventCreate(&set[i]);
+      h->evsets.push_back(set);
+    }
+    h->ev = h->evsets[h->ev_used++];
+    cudaEventRecord(h->ev[5], st);
+  } else {
+    h->ev = nullptr;
+  }
   if (int r = rnnt_b200_features(h, audio, lens, B, n, h->feats.as<float>(), stream)) return r;
   if (lens) {
     int32_t* lt = h->t_lens.as<int32_t>() + B;
@@ -781,21 +794,30 @@ int64_t rnnt_b200_kernel_launches(rnnt_b200_handle h) { return h ? h->launches :
 int32_t rnnt_b200_set_profiling(rnnt_b200_handle h, int32_t enable) {
   if (!h) return RNNT_B200_ERR_INVALID;
   h->profiling = enable != 0;
+  h->ev_used = 0;
+  h->ev = nullptr;
   return RNNT_B200_OK;
 }
 
 int32_t rnnt_b200_stage_times_ms(rnnt_b200_handle h, float* out) {
   if (!h || !out) return RNNT_B200_ERR_INVALID;
-  if (!h->profiling) return fail(h, RNNT_B200_ERR_STATE, "profiling is not enabled");
+  if (!h->profiling || h->ev_used < 1) return fail(h, RNNT_B200_ERR_STATE, "no profiled transcribe() call recorded");
   CK(cudaSetDevice(h->cfg.device));
-  CK(cudaEventSynchronize(h->ev[4]));
-  // ev5 -> ev0: features ; ev0 -> ev1: layernorm + input GEMMs + recurrent steps ; ev2 -> ev3: ep GEMM ; ev3 -> ev4: decode
-  float f = 0, e = 0, j = 0, d = 0;
-  CK(cudaEventElapsedTime(&f, h->ev[5], h->ev[0]));
-  CK(cudaEventElapsedTime(&e, h->ev[0], h->ev[1]));
-  CK(cudaEventElapsedTime(&j, h->ev[2], h->ev[3]));
-  CK(cudaEventElapsedTime(&d, h->ev[3], h->ev[4]));
-  out[0] = f; out[1] = e; out[2] = 0.f; out[3] = j; out[4] = d;
+  // ev5 -> ev0: features ; ev0 -> ev1: encoder ; ev2 -> ev3: ep GEMM ; ev3 -> ev4: decode
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int s = 0; s < h->ev_used; ++s) {
+    cudaEvent_t* ev = h->evsets[s];
+    CK(cudaEventSynchronize(ev[4]));
+    float f = 0, e = 0, j = 0, d = 0;
+    CK(cudaEventElapsedTime(&f, ev[5], ev[0]));
+    CK(cudaEventElapsedTime(&e, ev[0], ev[1]));
+    CK(cudaEventElapsedTime(&j, ev[2], ev[3]));
+    CK(cudaEventElapsedTime(&d, ev[3], ev[4]));
+    acc[0] += f; acc[1] += e; acc[3] += j; acc[4] += d;
+  }
+  for (int i = 0; i < 5; ++i) out[i] = (float)(acc[i] / h->ev_used);
+  h->ev_used = 0;
+  h->ev = nullptr;
   return RNNT_B200_OK;
 }
 

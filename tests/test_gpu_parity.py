@@ -1,0 +1,254 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every call goes through the C ABI
+(include/rnnt_b200.h) via the reference-named Python surface; the checker is the CPU oracle
+(pinned to the reference by tests/test_oracle_golden.py) and the golden fixtures produced
+by the imported reference itself.
+
+Tolerances (fp32 path, gemm_mode 0): features 5e-5 abs in the log domain, encoder 5e-5,
+joint logits / log-softmax rows 2e-4 abs; token sequences, per-frame iteration counts:
+exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import rnnt_oracle as O
+from oracle import weights
+
+pytestmark = pytest.mark.gpu
+CHUNK = 1280
+
+
+class Lang:
+    def denumericalize(self, ids):
+        return list(ids)
+
+
+_models = {}
+
+
+def model_for(name):
+    """Reference-surface Transducer on cuda:0 with the synthetic state_dict loaded."""
+    from libreasr_b200.lib.models import Transducer
+
+    if name not in _models:
+        cfg = weights.CONFIGS[name]
+        sd = weights.make_state_dict(cfg, 1234)
+        m = Transducer(cfg.feature_sz, cfg.embed_sz, cfg.vocab_sz, cfg.hidden_sz, cfg.out_sz, cfg.joint_sz, Lang(),
+                       encoder_kwargs={"num_layers": cfg.enc_layers}, predictor_kwargs={"num_layers": cfg.pred_layers})
+        m.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()}, strict=True)
+        m = m.to("cuda:0")
+        _models[name] = (cfg, sd, m, O.OracleTransducer(cfg, sd))
+    return _models[name]
+
+
+def cpu(t):
+    return t.detach().float().cpu().numpy()
+
+
+# ---------------- golden fixtures from the imported reference ----------------
+@pytest.mark.parametrize("name", ["tiny_offline", "cfg2_offline", "ref_offline", "cfg4_offline"])
+def test_offline_greedy_matches_reference_fixture(name):
+    g = load_golden(name)
+    cfg, sd, m, _ = model_for(str(g["config"]))
+    eng = m.engine()
+    audio = weights.make_audio(int(g["n_utt"]), int(g["n_samples"]), int(g["audio_seed"]))
+    for b in range(int(g["n_utt"])):
+        feats = eng.features(torch.from_numpy(audio[b:b + 1]).cuda())[0]  # [T, X]
+        toks, nlp, metrics, extra = m.decode_greedy(feats.unsqueeze(-1), max_iters=int(g["max_iters"]), return_logp=True)
+        assert toks == g[f"tokens_{b}"].tolist()
+        assert extra["iters"] == g[f"iters_{b}"].tolist()
+        assert abs(nlp - float(g[f"neg_log_p_{b}"])) < 2e-3
+        assert abs(metrics["alignment_score"] - float(g[f"alignment_score_{b}"])) < 1e-9
+        logp = torch.stack([o.reshape(-1) for o in extra["outs"]])
+        np.testing.assert_allclose(cpu(logp.max(-1).values), g[f"maxlogp_{b}"], atol=2e-4)
+        assert cpu(logp.argmax(-1)).tolist() == g[f"argmax_{b}"].tolist()
+        enc = m.encoder(feats[None, :, :, None])[0]
+        if f"feats_{b}" in g:
+            np.testing.assert_allclose(cpu(feats), g[f"feats_{b}"], atol=5e-5)
+            np.testing.assert_allclose(cpu(enc), g[f"enc_{b}"], atol=5e-5)
+            np.testing.assert_allclose(cpu(logp), g[f"logp_{b}"], atol=2e-4)
+        else:
+            s, n = int(g["enc_stride"]), int(g["n_logp"])
+            np.testing.assert_allclose(cpu(feats[::s, ::7]), g[f"feats_sub_{b}"], atol=5e-5)
+            np.testing.assert_allclose(cpu(enc[::s, ::16]), g[f"enc_sub_{b}"], atol=1e-4)
+            np.testing.assert_allclose(cpu(logp[:n]), g[f"logp_first_{b}"], atol=5e-4)
+
+
+@pytest.mark.parametrize("name", ["tiny_stream", "cfg2_stream"])
+def test_transcribe_stream_matches_reference_fixture(name):
+    """Transducer.transcribe_stream fed by the reference-named stream transforms."""
+    from libreasr_b200.lib.transforms import FusedStreamFeatures
+
+    g = load_golden(name)
+    cfg, sd, m, _ = model_for(str(g["config"]))
+    n_chunks = int(g["n_chunks"])
+    audio = weights.make_audio(1, n_chunks * CHUNK, int(g["audio_seed"]))[0]
+    audio[: int(g["lead_zero_chunks"]) * CHUNK] = 0.0
+    tfm = FusedStreamFeatures(m.engine(), n_buffer=2)
+    frames, rows = [], []
+    for j in range(n_chunks):  # api-server.py:83-115
+        frames.append(torch.from_numpy(audio[None, j * CHUNK:(j + 1) * CHUNK]))
+        if len(frames) < 3:
+            rows.append(None)
+            continue
+        rows.append(tfm(torch.cat(frames, dim=1)))
+        frames.pop(0)
+    feats = np.stack([cpu(r[..., 0]) for r in rows if r is not None])
+    np.testing.assert_allclose(feats if name.startswith("tiny") else feats[:, :, ::7], g["feats"], atol=5e-5)
+    yields = [(list(y), list(ys)) for y, ys, _ in m.transcribe_stream(iter(rows), lambda t: list(t), max_iters=int(g["max_iters"]))]
+    assert len(yields) == int(g["n_yields"])
+    assert [len(ys) for _, ys in yields] == g["chunk_counts"].tolist()
+    assert yields[-1][0] == g["tokens_all"].tolist()
+
+
+def test_modules_match_reference_fixture():
+    """Encoder / Predictor / Joint forward with explicit state."""
+    g = load_golden("tiny_modules")
+    cfg, sd, m, _ = model_for("tiny")
+    x = torch.from_numpy(g["x"])[..., None]
+    T = x.shape[1] // 2
+    e1, s1 = m.encoder(x[:, :T], return_state=True)
+    e2, s2 = m.encoder(x[:, T:], state=s1, return_state=True)
+    ef = m.encoder(x)
+    np.testing.assert_allclose(cpu(e1), g["enc_first"], atol=5e-5)
+    np.testing.assert_allclose(cpu(e2), g["enc_second"], atol=5e-5)
+    np.testing.assert_allclose(cpu(ef), g["enc_full"], atol=5e-5)
+    assert s2[0][0].shape == (1, x.shape[0], cfg.hidden_sz)
+    np.testing.assert_allclose(np.stack([cpu(s[0][0]) for s in s2]), g["enc_h"], atol=5e-5)
+    np.testing.assert_allclose(np.stack([cpu(s[1][0]) for s in s2]), g["enc_c"], atol=5e-5)
+    toks = torch.from_numpy(g["tokens"]).long()
+    st, outs = None, []
+    for j in range(toks.shape[1]):
+        o, st = m.predictor(toks[:, j:j + 1], state=st)
+        assert o.shape == (toks.shape[0], 1, cfg.hidden_sz)
+        outs.append(o[:, 0])
+    np.testing.assert_allclose(cpu(torch.stack(outs, 1)), g["pred_outs"], atol=5e-5)
+    np.testing.assert_allclose(np.stack([cpu(s[0]) for s in st]), g["pred_h"], atol=5e-5)
+    jl = m.joint(outs[-1], e2[:, -1])
+    np.testing.assert_allclose(cpu(jl), g["joint_logits"], atol=2e-4)
+    # broadcasting form used inside the reference decode loop (models.py:413-415)
+    jb = m.joint(outs[-1][:1][None], e2[0, -1][None, None, None])
+    assert jb.shape == (1, 1, 1, cfg.vocab_sz)
+    np.testing.assert_allclose(cpu(jb[0, 0, 0]), g["joint_logits"][0], atol=2e-4)
+
+
+# ---------------- oracle comparisons on fresh seeded inputs ----------------
+@pytest.mark.parametrize("name,n_utt,seconds", [("tiny", 5, 4.0), ("cfg2", 4, 6.0)])
+def test_batched_transcribe_matches_oracle(name, n_utt, seconds):
+    """Batched path (one call for all utterances) == the reference's utterance-by-utterance path."""
+    cfg, sd, m, orc = model_for(name)
+    eng = m.engine()
+    n = int(seconds * 16000)
+    audio = weights.make_audio(n_utt, n, seed=77)
+    r = eng.transcribe(torch.from_numpy(audio).cuda(), max_iters=3)
+    from libreasr_b200.engine import tokens_to_lists
+
+    got = tokens_to_lists(r["tokens"], r["ntok"])
+    for b in range(n_utt):
+        feats = O.features_offline(torch.from_numpy(audio[b:b + 1]), cfg)[0]
+        ro = orc.decode_greedy(feats, max_iters=3, impl="aten")
+        assert got[b] == ro["tokens"], f"utt {b}: min oracle margin {min(ro['margins']):.2e}"
+        assert r["iters"][b].cpu().tolist() == ro["iters"]
+        assert abs(float(r["neg_logp"][b]) - ro["neg_log_p"]) < 2e-3
+
+
+def test_ragged_batch_matches_per_utterance():
+    """lens[b] < n: each utterance reflect-pads at its own end and stops at its own T_b."""
+    cfg, sd, m, orc = model_for("tiny")
+    eng = m.engine()
+    from libreasr_b200.engine import tokens_to_lists
+
+    n = 48000
+    audio = weights.make_audio(4, n, seed=5)
+    lens = torch.tensor([48000, 40001, 16000, 1700], dtype=torch.int32)
+    r = eng.transcribe(torch.from_numpy(audio).cuda(), lens.cuda(), max_iters=3)
+    got = tokens_to_lists(r["tokens"], r["ntok"])
+    for b in range(4):
+        want = O.transcribe_batch(orc, audio[b:b + 1, : int(lens[b])], max_iters=3, impl="explicit")[0]
+        assert got[b] == want, b
+
+
+def test_host_api_equals_device_api():
+    cfg, sd, m, _ = model_for("tiny")
+    eng = m.engine()
+    from libreasr_b200.engine import tokens_to_lists
+
+    audio = torch.from_numpy(weights.make_audio(3, 32000, seed=9))
+    a = eng.transcribe(audio.cuda(), max_iters=3)
+    b = eng.transcribe_host(audio.pin_memory(), max_iters=3)
+    assert tokens_to_lists(a["tokens"], a["ntok"]) == tokens_to_lists(b["tokens"], b["ntok"])
+    np.testing.assert_allclose(cpu(a["neg_logp"]), b["neg_logp"].numpy(), rtol=0, atol=0)
+
+
+def test_libreasr_facade_transcribe_and_stream():
+    from libreasr_b200 import LibreASR
+
+    cfg, sd, m, orc = model_for("tiny")
+    asr = LibreASR(m)
+    audio = weights.make_audio(1, 40 * CHUNK, seed=13)[0]
+    want = O.transcribe_batch(orc, audio[None], max_iters=3, impl="explicit")[0]
+    assert asr.transcribe(audio) == want
+    assert asr.transcribe(audio.tobytes()) == want  # raw little-endian f32 PCM, utils.py:149-153
+    fe = O.StreamFrontend(cfg)
+    rows = [fe.push(torch.from_numpy(audio[None, j * CHUNK:(j + 1) * CHUNK])) for j in range(40)]
+    ys = list(orc.transcribe_stream(iter(rows), max_iters=10))
+    out = list(asr.stream(audio[j * CHUNK:(j + 1) * CHUNK] for j in range(40)))
+    assert len(out) == len(ys)
+    assert out[-1][0] == ys[-1][0]
+
+
+# ---------------- size-independent properties at BASELINE sizes ----------------
+def test_streaming_state_carry_equals_full_sequence_cfg2():
+    """Chunked encoder with carried (h, c) == one pass over the full sequence (config 2 size)."""
+    cfg, sd, m, _ = model_for("cfg2")
+    eng = m.engine()
+    g = torch.Generator().manual_seed(0)
+    feats = torch.randn(8, 124, cfg.feature_sz, generator=g).cuda()
+    full, _ = eng.encode(feats)
+    st, outs = None, []
+    for t0 in range(0, 124, 31):
+        o, st = eng.encode(feats[:, t0:t0 + 31].contiguous(), state=st, want_state=True)
+        outs.append(o)
+    assert float((torch.cat(outs, 1) - full).abs().max()) == 0.0  # same kernels, same order -> bit equal
+
+
+def test_batch_invariance_full_size_cfg2():
+    """32 x 10 s (BASELINE config 2): every utterance decodes to the same tokens alone and in the batch;
+    a permuted batch gives permuted results."""
+    from libreasr_b200.engine import tokens_to_lists
+
+    cfg, sd, m, _ = model_for("cfg2")
+    eng = m.engine()
+    audio = torch.from_numpy(weights.make_audio(32, 160000, seed=0)).cuda()
+    r = eng.transcribe(audio, max_iters=3)
+    toks = tokens_to_lists(r["tokens"], r["ntok"])
+    assert sum(map(len, toks)) > 0
+    perm = torch.randperm(32, generator=torch.Generator().manual_seed(1))
+    rp = eng.transcribe(audio[perm.cuda()].contiguous(), max_iters=3)
+    tp = tokens_to_lists(rp["tokens"], rp["ntok"])
+    assert [tp[i] for i in range(32)] == [toks[int(perm[i])] for i in range(32)]
+    for b in (0, 13, 31):
+        r1 = eng.transcribe(audio[b:b + 1].contiguous(), max_iters=3)
+        assert tokens_to_lists(r1["tokens"], r1["ntok"])[0] == toks[b]
+    it = r["iters"].cpu().numpy().astype(np.int64)
+    assert it.min() >= 1 and it.max() <= 3
+    # every evaluation but the last of a frame emitted a token; the last one emitted iff it was not blank,
+    # which can only happen on the max_iters-th evaluation (models.py:408-437)
+    ntok = r["ntok"].cpu().numpy().astype(np.int64)
+    lo = (it - 1).sum(1)
+    hi = lo + (it == 3).sum(1)
+    assert (lo <= ntok).all() and (ntok <= hi).all()
+
+
+def test_error_behaviour():
+    """Shape validation mirrors the reference's ValueErrors (haste/base_rnn.py:81-117)."""
+    cfg, sd, m, _ = model_for("tiny")
+    eng = m.engine()
+    with pytest.raises(ValueError):
+        eng.encode(torch.zeros(1, 4, cfg.feature_sz + 4, device="cuda"))
+    with pytest.raises(ValueError):
+        eng.encode(torch.zeros(2, 4, cfg.feature_sz, device="cuda"), state=(torch.zeros(1, 2, 64, device="cuda"),) * 2)
+    with pytest.raises(ValueError):
+        eng.features(torch.zeros(1, 300, device="cuda"))  # shorter than the reflect padding
+    with pytest.raises(NotImplementedError):
+        m(None)
