@@ -51,7 +51,7 @@ typedef enum {
 typedef enum {
   RNNT_B200_GEMM_FP32_SIMT = 0,   /* fp32 FMA on CUDA cores (bit-level closest to the reference) */
   RNNT_B200_GEMM_TC_FP16X3 = 1,   /* tcgen05, operands split hi+lo fp16, 3 MMAs, fp32 accumulate (~fp32 accuracy) */
-  RNNT_B200_GEMM_TC_BF16 = 2      /* tcgen05, single bf16 pass (throughput mode, not token-exact) */
+  RNNT_B200_GEMM_TC_FP16 = 2      /* tcgen05, single fp16 pass (throughput mode, not token-exact; reserved) */
 } rnnt_b200_gemm_mode;
 
 /* Shape/config of the path.  Field names follow config/testing.yaml:120-229. */
@@ -206,6 +206,15 @@ int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, c
                                   int32_t B, int64_t n, int32_t max_iters,
                                   int32_t* tokens_out_host, int32_t U_cap, int32_t* ntok_out_host,
                                   double* neg_logp_out_host, void* stream);
+
+/* ---- self test -------------------------------------------------------------------------------- */
+
+/* Runs the library's own GEMM (the contraction behind the LSTM gate and joint projections)
+ * on caller data: C[M,N] = A[M,K] * W[N,K]^T + bias[N] with the arithmetic of `gemm_mode`.
+ * Test hook (no reference counterpart): lets the parity tests measure each arithmetic mode
+ * against an fp64 product.  K and N must be multiples of 4.  Synchronises in the TC modes. */
+int32_t rnnt_b200_selftest_gemm(rnnt_b200_handle h, const float* A_dev, const float* W_dev, const float* bias_dev,
+                                float* C_dev, int64_t M, int32_t N, int32_t K, int32_t gemm_mode, void* stream);
 
 /* ---- introspection ------------------------------------------------------------------------ */
 

@@ -26,7 +26,7 @@ class Config(C.Structure):
     ]
 
 
-GEMM_FP32_SIMT, GEMM_TC_FP16X3, GEMM_TC_BF16 = 0, 1, 2
+GEMM_FP32_SIMT, GEMM_TC_FP16X3, GEMM_TC_FP16 = 0, 1, 2
 
 _vp, _i32, _i64, _cp = C.c_void_p, C.c_int32, C.c_int64, C.c_char_p
 
@@ -51,6 +51,7 @@ SIGNATURES = {
     "rnnt_b200_decode_greedy": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "rnnt_b200_transcribe": (_i32, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "rnnt_b200_transcribe_host": (_i32, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "rnnt_b200_selftest_gemm": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "rnnt_b200_kernel_launches": (_i64, [_vp]),
     "rnnt_b200_set_profiling": (_i32, [_vp, _i32]),
     "rnnt_b200_stage_times_ms": (_i32, [_vp, _vp]),

@@ -64,6 +64,9 @@ struct rnnt_b200_handle_s {
   // predictor + joint
   DecodeWeights dw;
   float* W1 = nullptr;  // [J][2H] as loaded; enc half = W1 + H with ld 2H
+  uint8_t* W1e_img = nullptr;          // TC modes: operand image of the enc half
+  std::vector<uint8_t*> Wih_img;       // TC modes: operand images of the interleaved W_ih
+  DevBuf a_img;                        // TC modes: activation operand image (workspace)
   // workspaces
   DevBuf feats, lnx, xp, ya, yb, ep, ehT[2], ecT, dhT, dxT, dgT, deT, dppT, dzT, dpart, dlse;
   DevBuf t_audio, t_lens, t_tokens, t_ntok, t_nlp, t_iters, t_enc;
@@ -182,7 +185,8 @@ int validate_config(const rnnt_b200_config& c, std::string* why) {
   if (c.enc_layers < 1 || c.enc_layers > 16) return bad("enc_layers must be in [1, 16]");
   if (c.pred_layers < 1 || c.pred_layers > kMaxPredLayers) return bad("pred_layers must be in [1, 4]");
   if (c.blank < 0 || c.blank >= c.vocab_sz || c.bos < 0 || c.bos >= c.vocab_sz) return bad("blank/bos out of range");
-  if (c.gemm_mode != RNNT_B200_GEMM_FP32_SIMT) return bad("gemm_mode not available in this build");
+  if (c.gemm_mode != RNNT_B200_GEMM_FP32_SIMT && c.gemm_mode != RNNT_B200_GEMM_TC_FP16X3)
+    return bad("gemm_mode not available in this build (0 = fp32 CUDA cores, 1 = tcgen05 3xFP16)");
   return 0;
 }
 
@@ -228,7 +232,8 @@ int32_t rnnt_b200_create(const rnnt_b200_config* cfg, rnnt_b200_handle* out) {
   h = new rnnt_b200_handle_s();
   h->cfg = *cfg;
   h->sm_count = prop.multiProcessorCount;
-  if ((e = configure_lstm()) != cudaSuccess || (e = configure_decode(cfg->device, &h->coop_blocks)) != cudaSuccess) {
+  if ((e = configure_lstm()) != cudaSuccess || (e = configure_gemm_tc()) != cudaSuccess ||
+      (e = configure_decode(cfg->device, &h->coop_blocks)) != cudaSuccess) {
     delete h;
     return fail_cuda(nullptr, e, "kernel configuration");
   }
@@ -243,7 +248,7 @@ int32_t rnnt_b200_destroy(rnnt_b200_handle h) {
   for (void* p : h->weight_allocs) cudaFree(p);
   DevBuf* bufs[] = {&h->feats, &h->lnx, &h->xp, &h->ya, &h->yb, &h->ep, &h->ehT[0], &h->ehT[1], &h->ecT, &h->dhT, &h->dxT,
                     &h->dgT, &h->deT, &h->dppT, &h->dzT, &h->dpart, &h->dlse, &h->t_audio, &h->t_lens, &h->t_tokens,
-                    &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc};
+                    &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc, &h->a_img};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t* set : h->evsets) {
     for (int i = 0; i < 6; ++i) cudaEventDestroy(set[i]);
@@ -398,6 +403,13 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
     LAUNCH(1, launch_gather_rows(d_wih, L.Wih_r, perm4, 4 * H, L.in, st));
     LAUNCH(1, launch_gather_rows(d_whh, d_whh_r, perm4, 4 * H, H, st));
     LAUNCH(1, launch_transpose(d_whh_r, H, L.Whh_t, 4 * H, H, st));  // -> [H][4H]
+    if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3) {
+      void* img = nullptr;
+      CK(cudaMalloc(&img, gemm_tc_w_image_bytes(4 * H, L.in)));
+      h->weight_allocs.push_back(img);
+      h->Wih_img.push_back((uint8_t*)img);
+      LAUNCH(1, launch_to_image(L.Wih_r, L.in, 4 * H, L.in, 256, (uint8_t*)img, st));
+    }
   }
 
   // ---- predictor (models.py:143-187; haste/nbrc.py:134-138) ----
@@ -483,6 +495,13 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
     LAUNCH(1, launch_transpose(h->W1 + H, 2 * H, W1e_t, J, H, st));  // enc half
     LAUNCH(1, launch_transpose(d_w2, J, W2_t, V, J, st));
     dw.W1p_t = W1p_t; dw.W1e_t = W1e_t; dw.b1 = t_b1; dw.W2_t = W2_t; dw.b2 = t_b2;
+    if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3) {
+      void* img = nullptr;
+      CK(cudaMalloc(&img, gemm_tc_w_image_bytes(J, H)));
+      h->weight_allocs.push_back(img);
+      h->W1e_img = (uint8_t*)img;
+      LAUNCH(1, launch_to_image(h->W1 + H, 2 * H, J, H, 256, h->W1e_img, st));
+    }
   }
 #undef NEED
   CK(cudaStreamSynchronize(st));
@@ -611,7 +630,13 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
     const EncLayer& L = h->enc[l];
     const float* A = l == 0 ? h->lnx.as<float>() : ((l - 1) & 1 ? h->yb.as<float>() : h->ya.as<float>());
     float* y = (l == c.enc_layers - 1) ? enc_out : (l & 1 ? h->yb.as<float>() : h->ya.as<float>());
-    LAUNCH(1, launch_gemm_nt_f32(A, L.in, L.Wih_r, L.in, L.bias_r, h->xp.as<float>(), 4 * H, M, 4 * H, L.in, st));
+    if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3) {
+      CK(h->a_img.ensure(gemm_tc_a_image_bytes(M, L.in)));
+      LAUNCH(1, launch_to_image(A, L.in, M, L.in, 128, h->a_img.as<uint8_t>(), st));
+      LAUNCH(1, launch_gemm_tc(h->a_img.as<uint8_t>(), h->Wih_img[l], L.bias_r, h->xp.as<float>(), 4 * H, M, 4 * H, L.in, st));
+    } else {
+      LAUNCH(1, launch_gemm_nt_f32(A, L.in, L.Wih_r, L.in, L.bias_r, h->xp.as<float>(), 4 * H, M, 4 * H, L.in, st));
+    }
     if (use_state_in) {
       LAUNCH(1, launch_state_to_T(state_h + (size_t)l * B * H, h->ehT[0].as<float>(), B, Bp, H, st));
       LAUNCH(1, launch_state_to_T(state_c + (size_t)l * B * H, h->ecT.as<float>(), B, Bp, H, st));
@@ -698,7 +723,13 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
   if (int r = ensure_decode_ws(h, B, T, trace_logp ? trace_cap : 0)) return r;
   if (h->ev) cudaEventRecord(h->ev[2], st);
   // hoisted encoder half of the joint's first Linear (incl. its bias): ep = enc * W1[:, H:]^T + b1
-  LAUNCH(1, launch_gemm_nt_f32(enc, H, h->W1 + H, 2 * H, h->dw.b1, h->ep.as<float>(), J, M, J, H, st));
+  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3) {
+    CK(h->a_img.ensure(gemm_tc_a_image_bytes(M, H)));
+    LAUNCH(1, launch_to_image(enc, H, M, H, 128, h->a_img.as<uint8_t>(), st));
+    LAUNCH(1, launch_gemm_tc(h->a_img.as<uint8_t>(), h->W1e_img, h->dw.b1, h->ep.as<float>(), J, M, J, H, st));
+  } else {
+    LAUNCH(1, launch_gemm_nt_f32(enc, H, h->W1 + H, 2 * H, h->dw.b1, h->ep.as<float>(), J, M, J, H, st));
+  }
   if (h->ev) cudaEventRecord(h->ev[3], st);
   const size_t hb = (size_t)H * Bp;
   float* dh = h->dhT.as<float>();
@@ -786,6 +817,30 @@ int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, c
   CK(cudaMemcpyAsync(ntok_host, h->t_ntok.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   if (neg_logp_host) CK(cudaMemcpyAsync(neg_logp_host, h->t_nlp.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_selftest_gemm(rnnt_b200_handle h, const float* A, const float* W, const float* bias, float* C, int64_t M,
+                                int32_t N, int32_t K, int32_t gemm_mode, void* stream) {
+  if (!h || !A || !W || !C || M < 1 || N < 1 || K < 1 || (K & 3) || (N & 3)) return fail(h, RNNT_B200_ERR_INVALID, "selftest_gemm: bad arguments");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gemm_mode == RNNT_B200_GEMM_FP32_SIMT) {
+    LAUNCH(1, launch_gemm_nt_f32(A, K, W, K, bias, C, N, M, N, K, st));
+    return RNNT_B200_OK;
+  }
+  if (gemm_mode != RNNT_B200_GEMM_TC_FP16X3) return fail(h, RNNT_B200_ERR_INVALID, "selftest_gemm: unknown gemm_mode");
+  void *ai = nullptr, *wi = nullptr;
+  CK(cudaMalloc(&ai, gemm_tc_a_image_bytes(M, K)));
+  CK(cudaMalloc(&wi, gemm_tc_w_image_bytes(N, K)));
+  cudaError_t e = launch_to_image(A, K, M, K, 128, (uint8_t*)ai, st);
+  if (e == cudaSuccess) e = launch_to_image(W, K, N, K, 256, (uint8_t*)wi, st);
+  if (e == cudaSuccess) e = launch_gemm_tc((uint8_t*)ai, (uint8_t*)wi, bias, C, N, M, N, K, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(ai);
+  cudaFree(wi);
+  if (e != cudaSuccess) return fail_cuda(h, e, "selftest_gemm");
+  h->launches += 3;
   return RNNT_B200_OK;
 }
 

@@ -38,6 +38,16 @@ cudaError_t launch_transpose(const float* in, int ld_in, float* out, int rows, i
 // out[r][perm(c)] row/column permutations used by the weight repack (see capi.cu)
 cudaError_t launch_gather_rows(const float* in, float* out, const int* src_row, int rows_out, int cols, cudaStream_t st);
 
+// ---------------- gemm_tc.cu (tcgen05, 3xFP16 split) ----------------
+cudaError_t configure_gemm_tc();
+size_t gemm_tc_a_image_bytes(int64_t M, int K);   // activation operand image, 128-row tiles
+size_t gemm_tc_w_image_bytes(int N, int K);       // weight operand image, 256-row tiles
+// fp32 row-major [R][ld] -> hi/lo fp16 operand image with TR-row tiles (tc_common.cuh)
+cudaError_t launch_to_image(const float* src, int ld, int64_t R, int K, int TR, uint8_t* img, cudaStream_t st);
+// C[M,N] = A * W^T + bias from operand images (A: TR=128, W: TR=256)
+cudaError_t launch_gemm_tc(const uint8_t* a_img, const uint8_t* w_img, const float* bias, float* C, int ldc, int64_t M, int N,
+                           int K, cudaStream_t st);
+
 // ---------------- lstm.cu ----------------
 struct LstmStepArgs {
   const float* Whh_t;   // [H][4H] k-major, columns interleaved unit*4 + gate(i,f,g,o)

@@ -305,6 +305,16 @@ class Engine:
         mk = (lambda *s, dtype: torch.zeros(*s, dtype=dtype).pin_memory()) if pin else (lambda *s, dtype: torch.zeros(*s, dtype=dtype))
         return {"tokens": mk(B, U, dtype=torch.int32), "ntok": mk(B, dtype=torch.int32), "neg_logp": mk(B, dtype=torch.float64)}
 
+    def selftest_gemm(self, A, W, bias=None, gemm_mode=None):
+        """C = A @ W.T + bias with the library's GEMM in the given arithmetic mode (test hook)."""
+        A, W = self._f32(A), self._f32(W)
+        M, K = A.shape
+        N = W.shape[0]
+        out = torch.empty(M, N, device=self.device)
+        mode = self.cfg.gemm_mode if gemm_mode is None else gemm_mode
+        self._ck(self.lib.rnnt_b200_selftest_gemm(self._h, _ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, mode, self._stream()))
+        return out
+
     # ---- introspection ---------------------------------------------------------------------------------
     def kernel_launches(self):
         return int(self.lib.rnnt_b200_kernel_launches(self._h))
