@@ -9,6 +9,7 @@
 
 #include "../../include/rnnt_b200.h"
 #include "kernels.h"
+#include "tc_common.cuh"
 
 using namespace rnnt;
 
@@ -66,6 +67,9 @@ struct rnnt_b200_handle_s {
   float* W1 = nullptr;  // [J][2H] as loaded; enc half = W1 + H with ld 2H
   uint8_t* W1e_img = nullptr;          // TC modes: operand image of the enc half
   std::vector<uint8_t*> Wih_img;       // TC modes: operand images of the interleaved W_ih
+  std::vector<uint8_t*> Whh_img;       // TC modes: operand images (TR = NC) of the interleaved W_hh
+  bool lstm_tc_ok = false;             // persistent tcgen05 LSTM layer usable for this H / SM count
+  DevBuf x_img[2], gbar;               // TC modes: h operand images (ping-pong), grid step counter
   DevBuf a_img;                        // TC modes: activation operand image (workspace)
   // workspaces
   DevBuf feats, lnx, xp, ya, yb, ep, ehT[2], ecT, dhT, dxT, dgT, deT, dppT, dzT, dpart, dlse;
@@ -233,7 +237,7 @@ int32_t rnnt_b200_create(const rnnt_b200_config* cfg, rnnt_b200_handle* out) {
   h->cfg = *cfg;
   h->sm_count = prop.multiProcessorCount;
   if ((e = configure_lstm()) != cudaSuccess || (e = configure_gemm_tc()) != cudaSuccess ||
-      (e = configure_decode(cfg->device, &h->coop_blocks)) != cudaSuccess) {
+      (e = configure_lstm_tc()) != cudaSuccess || (e = configure_decode(cfg->device, &h->coop_blocks)) != cudaSuccess) {
     delete h;
     return fail_cuda(nullptr, e, "kernel configuration");
   }
@@ -248,7 +252,7 @@ int32_t rnnt_b200_destroy(rnnt_b200_handle h) {
   for (void* p : h->weight_allocs) cudaFree(p);
   DevBuf* bufs[] = {&h->feats, &h->lnx, &h->xp, &h->ya, &h->yb, &h->ep, &h->ehT[0], &h->ehT[1], &h->ecT, &h->dhT, &h->dxT,
                     &h->dgT, &h->deT, &h->dppT, &h->dzT, &h->dpart, &h->dlse, &h->t_audio, &h->t_lens, &h->t_tokens,
-                    &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc, &h->a_img};
+                    &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc, &h->a_img, &h->x_img[0], &h->x_img[1], &h->gbar};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t* set : h->evsets) {
     for (int i = 0; i < 6; ++i) cudaEventDestroy(set[i]);
@@ -409,6 +413,15 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
       h->weight_allocs.push_back(img);
       h->Wih_img.push_back((uint8_t*)img);
       LAUNCH(1, launch_to_image(L.Wih_r, L.in, 4 * H, L.in, 256, (uint8_t*)img, st));
+      LstmTcPlan pl;
+      h->lstm_tc_ok = lstm_tc_plan(H, 1, h->sm_count, &pl);
+      if (h->lstm_tc_ok) {
+        void* wimg = nullptr;
+        CK(cudaMalloc(&wimg, img_bytes(4 * H, H, pl.NC)));
+        h->weight_allocs.push_back(wimg);
+        h->Whh_img.push_back((uint8_t*)wimg);
+        LAUNCH(1, launch_to_image(d_whh_r, H, 4 * H, H, pl.NC, (uint8_t*)wimg, st));
+      }
     }
   }
 
@@ -630,12 +643,39 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
     const EncLayer& L = h->enc[l];
     const float* A = l == 0 ? h->lnx.as<float>() : ((l - 1) & 1 ? h->yb.as<float>() : h->ya.as<float>());
     float* y = (l == c.enc_layers - 1) ? enc_out : (l & 1 ? h->yb.as<float>() : h->ya.as<float>());
-    if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3) {
-      CK(h->a_img.ensure(gemm_tc_a_image_bytes(M, L.in)));
-      LAUNCH(1, launch_to_image(A, L.in, M, L.in, 128, h->a_img.as<uint8_t>(), st));
+    const bool tc = c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3;
+    LstmTcPlan pl;
+    const bool tc_rec = tc && h->lstm_tc_ok && B <= 128 && lstm_tc_plan(H, B, h->sm_count, &pl);
+    if (tc) {
+      CK(h->a_img.ensure(gemm_tc_a_image_bytes(M, std::max(L.in, H))));
+      // layer 0 reads the LayerNorm output; deeper layers find their operand image already written
+      // by the previous layer's recurrent kernel (when that ran on the tensor-core path)
+      if (l == 0 || !tc_rec) LAUNCH(1, launch_to_image(A, L.in, M, L.in, 128, h->a_img.as<uint8_t>(), st));
       LAUNCH(1, launch_gemm_tc(h->a_img.as<uint8_t>(), h->Wih_img[l], L.bias_r, h->xp.as<float>(), 4 * H, M, 4 * H, L.in, st));
     } else {
       LAUNCH(1, launch_gemm_nt_f32(A, L.in, L.Wih_r, L.in, L.bias_r, h->xp.as<float>(), 4 * H, M, 4 * H, L.in, st));
+    }
+    if (tc_rec) {
+      const size_t ximg = img_bytes(128, H, 128);
+      CK(h->x_img[0].ensure(ximg));
+      CK(h->x_img[1].ensure(ximg));
+      CK(h->gbar.ensure(64));
+      CK(cudaMemsetAsync(h->gbar.p, 0, 4, st));
+      LstmTcArgs a;
+      memset(&a, 0, sizeof(a));
+      a.w_img = h->Whh_img[l];
+      a.x_img[0] = h->x_img[0].as<uint8_t>(); a.x_img[1] = h->x_img[1].as<uint8_t>();
+      a.xp = h->xp.as<float>(); a.bn_scale = L.bn_scale; a.bn_shift = L.bn_shift;
+      a.y = y; a.y_img = (l == c.enc_layers - 1) ? nullptr : h->a_img.as<uint8_t>();
+      a.lens_T = lens_T; a.h_init_vec = L.h0; a.c_init_vec = L.c0;
+      a.state_h_in = use_state_in ? state_h + (size_t)l * B * H : nullptr;
+      a.state_c_in = use_state_in ? state_c + (size_t)l * B * H : nullptr;
+      a.state_h_out = state_h ? state_h + (size_t)l * B * H : nullptr;
+      a.state_c_out = state_c ? state_c + (size_t)l * B * H : nullptr;
+      a.barrier = h->gbar.as<unsigned int>();
+      a.T = T; a.B = B; a.H = H;
+      LAUNCH(1, launch_lstm_layer_tc(a, pl, st));
+      continue;
     }
     if (use_state_in) {
       LAUNCH(1, launch_state_to_T(state_h + (size_t)l * B * H, h->ehT[0].as<float>(), B, Bp, H, st));

@@ -48,6 +48,30 @@ cudaError_t launch_to_image(const float* src, int ld, int64_t R, int K, int TR, 
 cudaError_t launch_gemm_tc(const uint8_t* a_img, const uint8_t* w_img, const float* bias, float* C, int ldc, int64_t M, int N,
                            int K, cudaStream_t st);
 
+// ---------------- lstm_tc.cu (persistent tcgen05 LSTM layer) ----------------
+struct LstmTcPlan {
+  int U, NC, grid, KB, Bpad8, stages, w_resident, bar_offset, smem_bytes, tmem_cols;
+};
+struct LstmTcArgs {
+  const uint8_t* w_img;      // operand image (TR = NC) of the interleaved W_hh [4H][H]
+  uint8_t* x_img[2];         // h_{t-1} / h_t operand images (TR = 128, one row tile), ping-pong
+  const float* xp;           // [B*T][4H] hoisted input projection incl. biases
+  const float* bn_scale; const float* bn_shift;
+  float* y;                  // [B*T][H] BatchNorm(h_t) fp32, or nullptr
+  uint8_t* y_img;            // operand image (TR = 128) of the same rows, or nullptr
+  const int32_t* lens_T;
+  const float* h_init_vec; const float* c_init_vec;   // [H] learnable initial state
+  const float* state_h_in; const float* state_c_in;   // [B][H] or nullptr
+  float* state_h_out; float* state_c_out;             // [B][H] or nullptr
+  unsigned int* barrier;     // grid step counter, zero at launch
+  int T, B, H;
+  // filled from the plan by the launcher
+  int U, NC, KB, Bpad8, stages, w_resident, bar_offset, tmem_cols;
+};
+cudaError_t configure_lstm_tc();
+bool lstm_tc_plan(int H, int B, int sms, LstmTcPlan* pl);
+cudaError_t launch_lstm_layer_tc(const LstmTcArgs& a, const LstmTcPlan& pl, cudaStream_t st);
+
 // ---------------- lstm.cu ----------------
 struct LstmStepArgs {
   const float* Whh_t;   // [H][4H] k-major, columns interleaved unit*4 + gate(i,f,g,o)

@@ -6,6 +6,8 @@ by the imported reference itself.
 Tolerances (fp32 path, gemm_mode 0): features 5e-5 abs in the log domain, encoder 5e-5,
 joint logits / log-softmax rows 2e-4 abs; token sequences, per-frame iteration counts:
 exact."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -16,6 +18,7 @@ from oracle import weights
 
 pytestmark = pytest.mark.gpu
 CHUNK = 1280
+GEMM_MODE = int(os.environ.get("RNNT_GEMM_MODE", "0"))  # 0 = fp32 CUDA cores, 1 = tcgen05 3xFP16
 
 
 class Lang:
@@ -34,7 +37,8 @@ def model_for(name):
         cfg = weights.CONFIGS[name]
         sd = weights.make_state_dict(cfg, 1234)
         m = Transducer(cfg.feature_sz, cfg.embed_sz, cfg.vocab_sz, cfg.hidden_sz, cfg.out_sz, cfg.joint_sz, Lang(),
-                       encoder_kwargs={"num_layers": cfg.enc_layers}, predictor_kwargs={"num_layers": cfg.pred_layers})
+                       encoder_kwargs={"num_layers": cfg.enc_layers}, predictor_kwargs={"num_layers": cfg.pred_layers},
+                       gemm_mode=GEMM_MODE)
         m.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()}, strict=True)
         m = m.to("cuda:0")
         _models[name] = (cfg, sd, m, O.OracleTransducer(cfg, sd))
