@@ -2,6 +2,7 @@
 // in include/rnnt_b200.h.  Host orchestration only -- all arithmetic is in the kernels.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -674,7 +675,29 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
       a.state_c_out = state_c ? state_c + (size_t)l * B * H : nullptr;
       a.barrier = h->gbar.as<unsigned int>();
       a.T = T; a.B = B; a.H = H;
+      static const bool dbg_on = getenv("RNNT_LSTM_DBG") != nullptr;
+      unsigned long long* dbg = nullptr;
+      if (dbg_on && l == 0) {
+        CK(cudaMalloc((void**)&dbg, (size_t)T * 32));
+        CK(cudaMemset(dbg, 0, (size_t)T * 32));
+        a.dbg = dbg;
+      }
       LAUNCH(1, launch_lstm_layer_tc(a, pl, st));
+      if (dbg) {
+        std::vector<unsigned long long> hb((size_t)T * 4);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(hb.data(), dbg, (size_t)T * 32, cudaMemcpyDeviceToHost));
+        cudaFree(dbg);
+        double w = 0, ld = 0, mma = 0, epi = 0;
+        for (int t = 1; t < T; ++t) {
+          w += (double)(hb[t * 4 + 0] - hb[(t - 1) * 4 + 3]);   // counter visible after previous arrive
+          ld += (double)(hb[t * 4 + 1] - hb[t * 4 + 0]);        // producer issue time
+          mma += (double)(hb[t * 4 + 2] - hb[t * 4 + 0]);       // barrier passed -> accumulators ready
+          epi += (double)(hb[t * 4 + 3] - hb[t * 4 + 2]);       // epilogue incl. fences and arrive
+        }
+        fprintf(stderr, "[lstm_tc dbg] B=%d T=%d steps avg ns: wait-after-arrive %.0f | issue %.0f | barrier->tmem_full %.0f | epilogue %.0f | total/step %.0f\n",
+                B, T, w / (T - 1), ld / (T - 1), mma / (T - 1), epi / (T - 1), (double)(hb[(T - 1) * 4 + 3] - hb[3]) / (T - 1));
+      }
       continue;
     }
     if (use_state_in) {

@@ -51,10 +51,15 @@ cudaError_t launch_gemm_tc(const uint8_t* a_img, const uint8_t* w_img, const flo
 // ---------------- lstm_tc.cu (persistent tcgen05 LSTM layer) ----------------
 struct LstmTcPlan {
   int U, NC, grid, KB, Bpad8, stages, w_resident, bar_offset, smem_bytes, tmem_cols;
+  int kps;         // k-blocks (64 k) per pipeline stage / TMA bulk copy
+  int nk;          // interleaved accumulator sets (breaks the MMA accumulate dependency chain)
+  int mma_m;       // 64 (B <= 32) or 128
+  int small;       // B <= 32: epilogue redistributes the tile over all 128 threads through smem
+  int pre_offset;  // smem offset of that exchange buffer
 };
 struct LstmTcArgs {
   const uint8_t* w_img;      // operand image (TR = NC) of the interleaved W_hh [4H][H]
-  uint8_t* x_img[2];         // h_{t-1} / h_t operand images (TR = 128, one row tile), ping-pong
+  uint8_t* x_img[2];         // h_{t-1} / h_t operand images (TR = Bpad8 rows: [kb][part] contiguous), ping-pong
   const float* xp;           // [B*T][4H] hoisted input projection incl. biases
   const float* bn_scale; const float* bn_shift;
   float* y;                  // [B*T][H] BatchNorm(h_t) fp32, or nullptr
@@ -64,9 +69,10 @@ struct LstmTcArgs {
   const float* state_h_in; const float* state_c_in;   // [B][H] or nullptr
   float* state_h_out; float* state_c_out;             // [B][H] or nullptr
   unsigned int* barrier;     // grid step counter, zero at launch
+  unsigned long long* dbg;   // optional [T][4] globaltimer stamps of CTA 0 (tuning aid), or nullptr
   int T, B, H;
   // filled from the plan by the launcher
-  int U, NC, KB, Bpad8, stages, w_resident, bar_offset, tmem_cols;
+  int U, NC, KB, Bpad8, stages, w_resident, bar_offset, tmem_cols, kps, nk, mma_m, small, pre_offset;
 };
 cudaError_t configure_lstm_tc();
 bool lstm_tc_plan(int H, int B, int sms, LstmTcPlan* pl);

@@ -34,32 +34,78 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 struct Smem {
   uint8_t* ring;
   uint8_t* wres;
+  float* pre;
   uint64_t *full, *empty, *tfull, *tempty, *wfull;
   uint32_t* tptr;
 };
+
+// Sum of the interleaved partial accumulators for 16 gate columns starting at c0:
+//   pre = sum_a D0_a + 2^-11 * sum_a (D1a_a + D1b_a)      (fixed order: deterministic)
+__device__ __forceinline__ void load_pre16(uint32_t tlane, int c0, int NC, int nk, float (&pre)[16]) {
+  float s0[16], s1[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
+  for (int a = 0; a < nk; ++a) {
+    float d0[16], d1[16], d2[16];
+    const uint32_t base = tlane + a * 3 * NC + c0;
+    tmem_ld16(base, d0);
+    tmem_ld16(base + NC, d1);
+    tmem_ld16(base + 2 * NC, d2);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { s0[i] += d0[i]; s1[i] += d1[i] + d2[i]; }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) pre[i] = fmaf(s1[i], kLoInv, s0[i]);
+}
+
+// n (1, 2 or 4) consecutive k of one image row as hi / lo halves
+__device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, int r, int k, int n, const float* v) {
+  __align__(8) __half hi[4];
+  __align__(8) __half lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < n) split_f16x3(v[j], hi[j], lo[j]);
+  const uint32_t off = img_elem_offset(r, k);
+  if (n == 4) {
+    *reinterpret_cast<uint2*>(hi_tile + off) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(lo_tile + off) = *reinterpret_cast<const uint2*>(lo);
+  } else if (n == 2) {
+    *reinterpret_cast<uint32_t*>(hi_tile + off) = *reinterpret_cast<const uint32_t*>(hi);
+    *reinterpret_cast<uint32_t*>(lo_tile + off) = *reinterpret_cast<const uint32_t*>(lo);
+  } else {
+    *reinterpret_cast<__half*>(hi_tile + off) = hi[0];
+    *reinterpret_cast<__half*>(lo_tile + off) = lo[0];
+  }
+}
 
 __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x, G = gridDim.x;
-  const int NC = p.NC, U = p.U, KB = p.KB, S = p.stages;
-  const uint32_t xrows_bytes = (uint32_t)p.Bpad8 * 128;      // valid rows of one part of the h tile
-  const uint32_t wtile = (uint32_t)NC * 256;                 // hi + lo weight tile of one k-block
-  const uint32_t stage_bytes = 2 * xrows_bytes + (p.w_resident ? 0 : wtile);
+  const int NC = p.NC, U = p.U, KB = p.KB, S = p.stages, KPS = p.kps, NK = p.nk, MM = p.mma_m;
+  const uint32_t xr = (uint32_t)p.Bpad8 * 128;          // valid rows of one part of an h tile
+  const uint32_t wtile = (uint32_t)NC * 256;            // hi + lo weight tile of one k-block
+  const uint32_t xstage = (uint32_t)KPS * 2 * xr;
+  const uint32_t stage_bytes = xstage + (p.w_resident ? 0 : KPS * wtile);
+  const int n_groups = KB / KPS;                        // stage fills per time step
   Smem sm;
   sm.ring = base;
   sm.wres = base + (size_t)S * stage_bytes;
-  uint8_t* after = sm.wres + (p.w_resident ? (size_t)KB * wtile : 0);
-  // the MMA reads 128 rows per A tile; rows >= Bpad8 alias whatever follows (never used): keep >= 16 KB mapped
+  sm.pre = reinterpret_cast<float*>(base + p.pre_offset);
   uint8_t* bars = base + p.bar_offset;
-  (void)after;
   sm.full = reinterpret_cast<uint64_t*>(bars);
   sm.empty = sm.full + S;
   sm.tfull = sm.empty + S;
@@ -88,8 +134,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
     if (lane == 0) {
       if (p.w_resident) {
         mbar_arrive_expect_tx(sm.wfull, (uint32_t)KB * wtile);
-        for (int kb = 0; kb < KB; ++kb)
-          tma_bulk_g2s(sm.wres + (size_t)kb * wtile, p.w_img + img_tile_offset(cta, kb, 0, KB, NC), wtile, sm.wfull);
+        tma_bulk_g2s(sm.wres, p.w_img + img_tile_offset(cta, 0, 0, KB, NC), (uint32_t)KB * wtile, sm.wfull);
       }
       uint32_t g = 0;
       for (int t = 0; t < p.T; ++t) {
@@ -97,46 +142,50 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
         while (ld_acquire_u32(p.barrier) < target) {
         }
         fence_proxy_async_global();
+        if (p.dbg && cta == 0) p.dbg[t * 4 + 0] = gtimer();
         const uint8_t* ximg = p.x_img[t & 1];
-        for (int kb = 0; kb < KB; ++kb, ++g) {
+        for (int gi = 0; gi < n_groups; ++gi, ++g) {
           const int s = g % S;
           const uint32_t ph = (g / S) & 1;
           mbar_wait(&sm.empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&sm.full[s], stage_bytes);
           uint8_t* dst = sm.ring + (size_t)s * stage_bytes;
-          tma_bulk_g2s(dst, ximg + img_tile_offset(0, kb, 0, KB, 128), xrows_bytes, &sm.full[s]);
-          tma_bulk_g2s(dst + xrows_bytes, ximg + img_tile_offset(0, kb, 1, KB, 128), xrows_bytes, &sm.full[s]);
+          tma_bulk_g2s(dst, ximg + (size_t)gi * xstage, xstage, &sm.full[s]);
           if (!p.w_resident)
-            tma_bulk_g2s(dst + 2 * xrows_bytes, p.w_img + img_tile_offset(cta, kb, 0, KB, NC), wtile, &sm.full[s]);
+            tma_bulk_g2s(dst + xstage, p.w_img + img_tile_offset(cta, gi * KPS, 0, KB, NC), KPS * wtile, &sm.full[s]);
         }
+        if (p.dbg && cta == 0) p.dbg[t * 4 + 1] = gtimer();
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(128, NC);
+      const uint32_t idesc_cat = umma_idesc_f16(MM, 2 * NC);   // A_hi x [B_hi ; B_lo]
+      const uint32_t idesc_one = umma_idesc_f16(MM, NC);       // A_lo x B_hi
       if (p.w_resident) mbar_wait(sm.wfull, 0);
       uint32_t g = 0;
       for (int t = 0; t < p.T; ++t) {
         if (t > 0) mbar_wait(sm.tempty, (t - 1) & 1);
         tc_fence_after();
-        for (int kb = 0; kb < KB; ++kb, ++g) {
+        int k16 = 0;
+        for (int gi = 0; gi < n_groups; ++gi, ++g) {
           const int s = g % S;
           const uint32_t ph = (g / S) & 1;
           mbar_wait(&sm.full[s], ph);
           tc_fence_after();
-          const uint32_t a_hi0 = smem_u32(sm.ring + (size_t)s * stage_bytes);
-          const uint32_t a_lo0 = a_hi0 + xrows_bytes;
-          const uint32_t b_hi0 = p.w_resident ? smem_u32(sm.wres + (size_t)kb * wtile) : a_hi0 + 2 * xrows_bytes;
-          const uint32_t b_lo0 = b_hi0 + (uint32_t)NC * 128;
+          const uint32_t st0 = smem_u32(sm.ring + (size_t)s * stage_bytes);
+          for (int i = 0; i < KPS; ++i) {
+            const int kb = gi * KPS + i;
+            const uint32_t a_hi0 = st0 + (uint32_t)i * 2 * xr;
+            const uint32_t a_lo0 = a_hi0 + xr;
+            const uint32_t b0 = p.w_resident ? smem_u32(sm.wres + (size_t)kb * wtile) : st0 + xstage + (uint32_t)i * wtile;
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const uint64_t a_hi = umma_desc_sw128(a_hi0 + k4 * 32), a_lo = umma_desc_sw128(a_lo0 + k4 * 32);
-            const uint64_t b_hi = umma_desc_sw128(b_hi0 + k4 * 32), b_lo = umma_desc_sw128(b_lo0 + k4 * 32);
-            const uint32_t acc = (kb > 0 || k4 > 0) ? 1u : 0u;
-            tc_mma_f16(tmem, a_hi, b_hi, idesc, acc);
-            tc_mma_f16(tmem + NC, a_hi, b_lo, idesc, acc);
-            tc_mma_f16(tmem + NC, a_lo, b_hi, idesc, 1u);
+            for (int k4 = 0; k4 < 4; ++k4, ++k16) {
+              const uint32_t acc_col = tmem + (uint32_t)((k16 % NK) * 3 * NC);
+              const uint32_t accumulate = (k16 >= NK) ? 1u : 0u;
+              tc_mma_f16(acc_col, umma_desc_sw128(a_hi0 + k4 * 32), umma_desc_sw128(b0 + k4 * 32), idesc_cat, accumulate);
+              tc_mma_f16(acc_col + 2 * NC, umma_desc_sw128(a_lo0 + k4 * 32), umma_desc_sw128(b0 + k4 * 32), idesc_one, accumulate);
+            }
           }
           tc_commit(&sm.empty[s]);
         }
@@ -146,39 +195,53 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
   } else {
     // =========================== epilogue ===========================
     const int q = warp & 3;
-    const int b = q * 32 + lane;        // batch row == TMEM lane
-    const bool valid = b < p.B;
     const int et = (warp - 2) * 32 + lane;  // 0..127
-    const int unit0 = cta * U;
     const int H = p.H;
-    float c[LT_MAX_U], h[LT_MAX_U];
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    // ownership: small batch (B <= 32, M = 64): thread -> (b = et % 32, U/4 units); else thread -> row, all U units
+    const bool small = p.small != 0;
+    const int upt = small ? U / 4 : U;                     // units per thread
+    const int b = small ? (et & 31) : q * 32 + lane;
+    const int unit0 = cta * U + (small ? (et >> 5) * upt : 0);
+    const bool valid = b < p.B;
+    float c[LT_MAX_U], h[LT_MAX_U], bsc[LT_MAX_U], bsh[LT_MAX_U];
     const int len = valid ? (p.lens_T ? min(p.lens_T[b], p.T) : p.T) : 0;
 #pragma unroll
     for (int j = 0; j < LT_MAX_U; ++j) {
-      if (j < U && valid) {
+      if (j < upt && valid) {
         h[j] = p.state_h_in ? p.state_h_in[(size_t)b * H + unit0 + j] : p.h_init_vec[unit0 + j];
         c[j] = p.state_c_in ? p.state_c_in[(size_t)b * H + unit0 + j] : p.c_init_vec[unit0 + j];
+        bsc[j] = p.bn_scale[unit0 + j];
+        bsh[j] = p.bn_shift[unit0 + j];
       } else {
-        h[j] = 0.f; c[j] = 0.f;
+        h[j] = 0.f; c[j] = 0.f; bsc[j] = 0.f; bsh[j] = 0.f;
       }
     }
-    // writes U consecutive values (k = unit0 ..) of row `r` of a TR=128 image tile set as hi/lo halves
-    auto store_img = [&](uint8_t* img, int64_t row_tile, int r, const float* v) {
+    // h_t of this thread's units -> h operand image (TR = Bpad8 row tiles, [kb][part] contiguous)
+    auto store_h = [&](uint8_t* img, const float* v) {
+      const int n = upt < 4 ? upt : 4;
 #pragma unroll
       for (int j0 = 0; j0 < LT_MAX_U; j0 += 4) {
-        if (j0 < U) {
+        if (j0 < upt) {
           const int k = unit0 + j0;
-          __align__(8) __half hi[4];
-          __align__(8) __half lo[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) split_f16x3(v[j0 + j], hi[j], lo[j]);
-          const uint32_t off = img_elem_offset(r, k & 63);
-          *reinterpret_cast<uint2*>(img + img_tile_offset(row_tile, k >> 6, 0, KB, 128) + off) = *reinterpret_cast<const uint2*>(hi);
-          *reinterpret_cast<uint2*>(img + img_tile_offset(row_tile, k >> 6, 1, KB, 128) + off) = *reinterpret_cast<const uint2*>(lo);
+          uint8_t* hi = img + (size_t)((k >> 6) * 2) * xr;
+          store_split(hi, hi + xr, b, k & 63, n, v + j0);
         }
       }
     };
-    if (valid) store_img(p.x_img[0], 0, b, h);
+    // BatchNorm(h_t) -> operand image (TR = 128 row tiles) of the next layer's input GEMM
+    auto store_yimg = [&](int64_t row, const float* v) {
+      const int n = upt < 4 ? upt : 4;
+#pragma unroll
+      for (int j0 = 0; j0 < LT_MAX_U; j0 += 4) {
+        if (j0 < upt) {
+          const int k = unit0 + j0;
+          uint8_t* hi = p.y_img + img_tile_offset(row >> 7, k >> 6, 0, KB, 128);
+          store_split(hi, hi + 128 * 128, (int)(row & 127), k & 63, n, v + j0);
+        }
+      }
+    };
+    if (valid) store_h(p.x_img[0], h);
     fence_proxy_async_global();
     named_bar_sync(1, 128);
     if (et == 0) {
@@ -186,61 +249,102 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
       atomicAdd(p.barrier, 1u);
     }
 
-    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    const int prs = NC + 1;  // row stride of the exchange buffer
     for (int t = 0; t < p.T; ++t) {
       const int64_t row = (int64_t)b * p.T + t;
+      // hoisted input projection of this thread's units for step t: issued before the accumulators are ready
+      float4 xv[LT_MAX_U];
+#pragma unroll
+      for (int j = 0; j < LT_MAX_U; ++j)
+        if (j < upt && valid) xv[j] = *reinterpret_cast<const float4*>(p.xp + row * (size_t)(4 * H) + (size_t)(unit0 + j) * 4);
       mbar_wait(sm.tfull, t & 1);
       tc_fence_after();
+      if (p.dbg && cta == 0 && et == 0) p.dbg[t * 4 + 2] = gtimer();
       float hy[LT_MAX_U];
+      if (small) {
+        // M = 64: batch row r lives in TMEM lane (r % 16) + 32 * (r / 16): quarters 0 and 1 hold rows 0..31
+        if (q * 16 < p.Bpad8) {
+          const int r = q * 16 + lane;
+          for (int c0 = 0; c0 < NC; c0 += 16) {
+            float pre[16];
+            load_pre16(tlane, c0, NC, NK, pre);
+            if (lane < 16) {
 #pragma unroll
-      for (int j0 = 0; j0 < LT_MAX_U; j0 += 4) {  // 16 gate columns = 4 units per chunk
-        if (j0 < U) {
-          float d0[16], d1[16];
-          tmem_ld16(tlane + j0 * 4, d0);
-          tmem_ld16(tlane + NC + j0 * 4, d1);
-          tmem_ld_wait();
-          if (valid) {
-            const float4* xr = reinterpret_cast<const float4*>(p.xp + row * (size_t)(4 * H) + (size_t)(unit0 + j0) * 4);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 x = xr[j];
-              const float vi = fmaf(d1[4 * j + 0], kLoInv, d0[4 * j + 0]) + x.x;
-              const float vf = fmaf(d1[4 * j + 1], kLoInv, d0[4 * j + 1]) + x.y;
-              const float vg = fmaf(d1[4 * j + 2], kLoInv, d0[4 * j + 2]) + x.z;
-              const float vo = fmaf(d1[4 * j + 3], kLoInv, d0[4 * j + 3]) + x.w;
-              if (t < len) {
-                const float cn = sigmoidf_acc(vf) * c[j0 + j] + sigmoidf_acc(vi) * tanhf(vg);
-                c[j0 + j] = cn;
-                h[j0 + j] = sigmoidf_acc(vo) * tanhf(cn);
-              }
-              hy[j0 + j] = h[j0 + j] * p.bn_scale[unit0 + j0 + j] + p.bn_shift[unit0 + j0 + j];
+              for (int i = 0; i < 16; ++i) sm.pre[r * prs + c0 + i] = pre[i];
             }
           }
         }
-      }
-      tc_fence_before();
-      mbar_arrive(sm.tempty);
-      if (valid) {
-        store_img(p.x_img[(t + 1) & 1], 0, b, h);
-        if (p.y) {
+        tc_fence_before();
+        mbar_arrive(sm.tempty);
+        named_bar_sync(1, 128);
+        if (valid) {
+          const float* pr = sm.pre + b * prs + (unit0 - cta * U) * 4;
 #pragma unroll
-          for (int j0 = 0; j0 < LT_MAX_U; j0 += 4)
-            if (j0 < U)
-              *reinterpret_cast<float4*>(p.y + row * H + unit0 + j0) = make_float4(hy[j0], hy[j0 + 1], hy[j0 + 2], hy[j0 + 3]);
+          for (int j = 0; j < 4; ++j) {
+            if (j < upt) {
+              if (t < len) {
+                const float vi = pr[4 * j + 0] + xv[j].x, vf = pr[4 * j + 1] + xv[j].y;
+                const float vg = pr[4 * j + 2] + xv[j].z, vo = pr[4 * j + 3] + xv[j].w;
+                const float cn = sigmoidf_acc(vf) * c[j] + sigmoidf_acc(vi) * tanhf(vg);
+                c[j] = cn;
+                h[j] = sigmoidf_acc(vo) * tanhf(cn);
+              }
+              hy[j] = h[j] * bsc[j] + bsh[j];
+            }
+          }
         }
-        if (p.y_img) store_img(p.y_img, row >> 7, (int)(row & 127), hy);
+      } else {
+#pragma unroll
+        for (int j0 = 0; j0 < LT_MAX_U; j0 += 4) {  // 16 gate columns = 4 units per chunk
+          if (j0 < U) {
+            float pre[16];
+            load_pre16(tlane, j0 * 4, NC, NK, pre);
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (t < len) {
+                  const float vi = pre[4 * j + 0] + xv[j0 + j].x, vf = pre[4 * j + 1] + xv[j0 + j].y;
+                  const float vg = pre[4 * j + 2] + xv[j0 + j].z, vo = pre[4 * j + 3] + xv[j0 + j].w;
+                  const float cn = sigmoidf_acc(vf) * c[j0 + j] + sigmoidf_acc(vi) * tanhf(vg);
+                  c[j0 + j] = cn;
+                  h[j0 + j] = sigmoidf_acc(vo) * tanhf(cn);
+                }
+                hy[j0 + j] = h[j0 + j] * bsc[j0 + j] + bsh[j0 + j];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(sm.tempty);
+      }
+      if (valid) {
+        store_h(p.x_img[(t + 1) & 1], h);
+        if (p.y) {
+          float* yo = p.y + row * H + unit0;
+          if (upt >= 4) {
+#pragma unroll
+            for (int j0 = 0; j0 < LT_MAX_U; j0 += 4)
+              if (j0 < upt) *reinterpret_cast<float4*>(yo + j0) = make_float4(hy[j0], hy[j0 + 1], hy[j0 + 2], hy[j0 + 3]);
+          } else if (upt == 2) {
+            *reinterpret_cast<float2*>(yo) = make_float2(hy[0], hy[1]);
+          } else {
+            yo[0] = hy[0];
+          }
+        }
+        if (p.y_img) store_yimg(row, hy);
       }
       fence_proxy_async_global();
       named_bar_sync(1, 128);
       if (et == 0) {
         __threadfence();
         atomicAdd(p.barrier, 1u);
+        if (p.dbg && cta == 0) p.dbg[t * 4 + 3] = gtimer();
       }
     }
     if (valid) {
 #pragma unroll
       for (int j = 0; j < LT_MAX_U; ++j) {
-        if (j < U) {
+        if (j < upt) {
           if (p.state_h_out) p.state_h_out[(size_t)b * H + unit0 + j] = h[j];
           if (p.state_c_out) p.state_c_out[(size_t)b * H + unit0 + j] = c[j];
         }
@@ -258,7 +362,7 @@ cudaError_t configure_lstm_tc() {
   return cudaFuncSetAttribute(lstm_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
-// Chooses the decomposition for hidden size H on a device with `sms` SMs; returns false if none fits.
+// Chooses the decomposition for hidden size H, batch B on a device with `sms` SMs; false if none fits.
 bool lstm_tc_plan(int H, int B, int sms, LstmTcPlan* pl) {
   if (B < 1 || B > 128 || H % 64) return false;
   int U = 0;
@@ -270,28 +374,48 @@ bool lstm_tc_plan(int H, int B, int sms, LstmTcPlan* pl) {
   pl->grid = H / U;
   pl->KB = H / 64;
   pl->Bpad8 = (int)round_up(B, 8);
-  const size_t xstage = (size_t)2 * pl->Bpad8 * 128, wtile = (size_t)pl->NC * 256;
-  const size_t budget = 227 * 1024 - 2048 /*align + barriers*/ - 16384 /*guard rows*/;
-  pl->w_resident = ((size_t)pl->KB * wtile + 4 * xstage <= budget) ? 1 : 0;
-  const size_t stage = xstage + (pl->w_resident ? 0 : wtile);
-  size_t avail = budget - (pl->w_resident ? (size_t)pl->KB * wtile : 0);
-  int S = (int)(avail / stage);
-  if (S > 8) S = 8;
-  if (S < 2) return false;
-  pl->stages = S;
-  const size_t used = (size_t)S * stage + (pl->w_resident ? (size_t)pl->KB * wtile : 0) + 16384;
-  pl->bar_offset = (int)round_up(used, 1024);
-  pl->smem_bytes = pl->bar_offset + 1024 + 1024;
+  pl->small = B <= 32 ? 1 : 0;
+  pl->mma_m = pl->small ? 64 : 128;
+  pl->nk = 1;
+  for (int n : {4, 2})
+    if (n * 3 * pl->NC <= 512) { pl->nk = n; break; }
   int cols = 32;
-  while (cols < 2 * pl->NC) cols *= 2;
+  while (cols < pl->nk * 3 * pl->NC) cols *= 2;
   pl->tmem_cols = cols;
-  return pl->smem_bytes <= 227 * 1024;
+  const size_t xr = (size_t)pl->Bpad8 * 128, wtile = (size_t)pl->NC * 256;
+  const size_t guard = (size_t)pl->mma_m * 128;   // an A tile is read as mma_m rows; rows >= Bpad8 alias what follows
+  const size_t pre_bytes = pl->small ? round_up((size_t)32 * (pl->NC + 1) * 4, 1024) : 0;
+  const size_t budget = 227 * 1024 - 2048 /*alignment slack + barriers*/ - guard - pre_bytes;
+  const size_t wall = (size_t)pl->KB * wtile;
+  for (int want_res = 1; want_res >= 0; --want_res) {   // prefer the W-resident layout
+    for (int kps : {4, 2, 1}) {
+      if (pl->KB % kps) continue;
+      const size_t xstage = (size_t)kps * 2 * xr;
+      const bool res = wall + 3 * xstage <= budget;
+      if (res != (want_res != 0)) continue;
+      const size_t stage = xstage + (res ? 0 : kps * wtile);
+      const size_t avail = budget - (res ? wall : 0);
+      int S = (int)(avail / stage);
+      if (S > 8) S = 8;
+      if (S < 3 && !(kps == 1 && S >= 2)) continue;
+      pl->kps = kps;
+      pl->w_resident = res ? 1 : 0;
+      pl->stages = S;
+      const size_t used = (size_t)S * stage + (res ? wall : 0) + guard;
+      pl->pre_offset = (int)round_up(used, 1024);
+      pl->bar_offset = pl->pre_offset + (int)pre_bytes;
+      pl->smem_bytes = pl->bar_offset + 1024 + 1024;
+      return pl->smem_bytes <= 227 * 1024;
+    }
+  }
+  return false;
 }
 
 cudaError_t launch_lstm_layer_tc(const LstmTcArgs& a, const LstmTcPlan& pl, cudaStream_t st) {
   LstmTcArgs args = a;
   args.U = pl.U; args.NC = pl.NC; args.KB = pl.KB; args.Bpad8 = pl.Bpad8; args.stages = pl.stages;
   args.w_resident = pl.w_resident; args.bar_offset = pl.bar_offset; args.tmem_cols = pl.tmem_cols;
+  args.kps = pl.kps; args.nk = pl.nk; args.mma_m = pl.mma_m; args.small = pl.small; args.pre_offset = pl.pre_offset;
   void* kargs[] = {&args};
   return cudaLaunchCooperativeKernel((void*)lstm_layer_tc_kernel, dim3(pl.grid), dim3(LT_THREADS), kargs, pl.smem_bytes, st);
 }
