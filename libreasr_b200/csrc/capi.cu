@@ -691,11 +691,11 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
         double w = 0, ld = 0, mma = 0, epi = 0;
         for (int t = 1; t < T; ++t) {
           w += (double)(hb[t * 4 + 0] - hb[(t - 1) * 4 + 3]);   // counter visible after previous arrive
-          ld += (double)(hb[t * 4 + 1] - hb[t * 4 + 0]);        // producer issue time
+          ld += (double)(hb[t * 4 + 1] - hb[t * 4 + 0]);        // barrier passed -> last operand stage landed
           mma += (double)(hb[t * 4 + 2] - hb[t * 4 + 0]);       // barrier passed -> accumulators ready
           epi += (double)(hb[t * 4 + 3] - hb[t * 4 + 2]);       // epilogue incl. fences and arrive
         }
-        fprintf(stderr, "[lstm_tc dbg] B=%d T=%d steps avg ns: wait-after-arrive %.0f | issue %.0f | barrier->tmem_full %.0f | epilogue %.0f | total/step %.0f\n",
+        fprintf(stderr, "[lstm_tc dbg] B=%d T=%d steps avg ns: wait-after-arrive %.0f | barrier->last-stage-landed %.0f | barrier->tmem_full %.0f | epilogue %.0f | total/step %.0f\n",
                 B, T, w / (T - 1), ld / (T - 1), mma / (T - 1), epi / (T - 1), (double)(hb[(T - 1) * 4 + 3] - hb[3]) / (T - 1));
       }
       continue;

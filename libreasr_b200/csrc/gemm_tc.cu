@@ -61,42 +61,45 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_f16x3_kernel(GemmTcArgs
   const uint32_t tmem = *tptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < p.KB; ++kb) {
-        const int s = kb % GT_STAGES;
-        const uint32_t ph = (kb / GT_STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+    // producer: warp-uniform loop, one elected lane issues the TMA bulk copies
+    for (int kb = 0; kb < p.KB; ++kb) {
+      const int s = kb % GT_STAGES;
+      const uint32_t ph = (kb / GT_STAGES) & 1;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full[s], GT_STAGE_BYTES);
         uint8_t* dst = smem + s * GT_STAGE_BYTES;
         tma_bulk_g2s(dst, p.a_img + img_tile_offset(mt, kb, 0, p.KB, GT_BM), GT_A_BYTES, &full[s]);
         tma_bulk_g2s(dst + GT_A_BYTES, p.b_img + img_tile_offset(nt, kb, 0, p.KB, GT_BN), GT_B_BYTES, &full[s]);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(GT_BM, GT_BN);
-      for (int kb = 0; kb < p.KB; ++kb) {
-        const int s = kb % GT_STAGES;
-        const uint32_t ph = (kb / GT_STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + s * GT_STAGE_BYTES);
-        const uint32_t b_base = a_base + GT_A_BYTES;
+    // MMA issuer: warp-uniform so that the descriptors stay in uniform registers
+    const uint32_t idesc = umma_idesc_f16(GT_BM, GT_BN);
+    for (int kb = 0; kb < p.KB; ++kb) {
+      const int s = kb % GT_STAGES;
+      const uint32_t ph = (kb / GT_STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(smem + s * GT_STAGE_BYTES);
+      const uint32_t b_base = a_base + GT_A_BYTES;
+      const uint64_t a_hi = umma_desc_sw128(a_base), a_lo = umma_desc_sw128(a_base + GT_BM * 128);
+      const uint64_t b_hi = umma_desc_sw128(b_base), b_lo = umma_desc_sw128(b_base + GT_BN * 128);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const uint64_t a_hi = umma_desc_sw128(a_base + k4 * 32);
-          const uint64_t a_lo = umma_desc_sw128(a_base + GT_BM * 128 + k4 * 32);
-          const uint64_t b_hi = umma_desc_sw128(b_base + k4 * 32);
-          const uint64_t b_lo = umma_desc_sw128(b_base + GT_BN * 128 + k4 * 32);
-          const uint32_t acc = (kb > 0 || k4 > 0) ? 1u : 0u;
-          tc_mma_f16(tmem, a_hi, b_hi, idesc, acc);
-          tc_mma_f16(tmem + GT_BN, a_hi, b_lo, idesc, acc);
-          tc_mma_f16(tmem + GT_BN, a_lo, b_hi, idesc, 1u);
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const uint32_t acc = (kb > 0 || k4 > 0) ? 1u : 0u;
+        if (elect_one()) {  // descriptor start addresses are in 16-byte units: +2 per 16-deep k slice
+          tc_mma_f16(tmem, a_hi + 2 * k4, b_hi + 2 * k4, idesc, acc);
+          tc_mma_f16(tmem + GT_BN, a_hi + 2 * k4, b_lo + 2 * k4, idesc, acc);
+          tc_mma_f16(tmem + GT_BN, a_lo + 2 * k4, b_hi + 2 * k4, idesc, 1u);
         }
-        tc_commit(&empty[s]);
       }
-      tc_commit(tfull);
+      if (elect_one()) tc_commit(&empty[s]);
+      __syncwarp();
     }
+    if (elect_one()) tc_commit(tfull);
+    __syncwarp();
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int64_t row = mt * GT_BM + q * 32 + lane;

@@ -52,10 +52,9 @@ cudaError_t launch_gemm_tc(const uint8_t* a_img, const uint8_t* w_img, const flo
 struct LstmTcPlan {
   int U, NC, grid, KB, Bpad8, stages, w_resident, bar_offset, smem_bytes, tmem_cols;
   int kps;         // k-blocks (64 k) per pipeline stage / TMA bulk copy
-  int nk;          // interleaved accumulator sets (breaks the MMA accumulate dependency chain)
-  int mma_m;       // 64 (B <= 32) or 128
-  int small;       // B <= 32: epilogue redistributes the tile over all 128 threads through smem
-  int pre_offset;  // smem offset of that exchange buffer
+  int mma_m;       // MMA M: 64 when hi+lo rows of the batch fit (B <= 32), else 128
+  int fused;       // B <= 64: [A_hi;A_lo] stacked in one A tile -> one tcgen05.mma per 16-deep k slice
+  int pre_offset;  // smem offset of the accumulator exchange buffers (fused mode)
 };
 struct LstmTcArgs {
   const uint8_t* w_img;      // operand image (TR = NC) of the interleaved W_hh [4H][H]
@@ -72,7 +71,7 @@ struct LstmTcArgs {
   unsigned long long* dbg;   // optional [T][4] globaltimer stamps of CTA 0 (tuning aid), or nullptr
   int T, B, H;
   // filled from the plan by the launcher
-  int U, NC, KB, Bpad8, stages, w_resident, bar_offset, tmem_cols, kps, nk, mma_m, small, pre_offset;
+  int U, NC, KB, Bpad8, stages, w_resident, bar_offset, tmem_cols, kps, mma_m, fused, pre_offset;
 };
 cudaError_t configure_lstm_tc();
 bool lstm_tc_plan(int H, int B, int sms, LstmTcPlan* pl);

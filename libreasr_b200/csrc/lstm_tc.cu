@@ -8,8 +8,12 @@
 // keeps that slice (hi+lo fp16 operand image, NC x H x 4 bytes) RESIDENT in shared memory
 // for the whole layer when it fits (H = 1024: 128 KB); otherwise it is streamed per step.
 // Each step is one skinny GEMM with the BATCH on the MMA M axis and the CTA's gate rows on
-// N:   D[128 x NC] = h_{t-1}[B x H] * W_slice[NC x H]^T   (3xFP16 split, see gemm_tc.cu),
-// so all H/U CTAs (128 of the 148 SMs at H = 1024) share every step.
+// N, so all H/U CTAs (128 of the 148 SMs at H = 1024) share every step.  The 3xFP16 split
+// (gemm_tc.cu) is folded into ONE instruction per 16-deep k slice: the A tile stacks the hi
+// rows of the batch on top of its lo rows, the B tile the hi rows of the weight slice on top
+// of its lo rows, so  [A_hi;A_lo] x [B_hi;B_lo]^T  yields hi*hi, hi*lo, lo*hi (and lo*lo) in
+// four quadrants of one M64/M128 x 2NC accumulator (measured: a tcgen05.mma costs >= ~25-50
+// cycles however small it is, so instruction count is what matters at batch 32).
 //   warp 0     producer: waits for the grid-wide "h_{t-1} complete" counter, then streams the
 //              h_{t-1} operand image (B rows x 64 k, hi|lo) per k-block with TMA bulk copies
 //   warp 1     one thread issues 12 tcgen05.mma (M128 x NC x K16) per k-block into TMEM
@@ -45,30 +49,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 struct Smem {
   uint8_t* ring;
   uint8_t* wres;
-  float* pre;
+  float* pre_hi;
+  float* pre_lo;
   uint64_t *full, *empty, *tfull, *tempty, *wfull;
   uint32_t* tptr;
 };
-
-// Sum of the interleaved partial accumulators for 16 gate columns starting at c0:
-//   pre = sum_a D0_a + 2^-11 * sum_a (D1a_a + D1b_a)      (fixed order: deterministic)
-__device__ __forceinline__ void load_pre16(uint32_t tlane, int c0, int NC, int nk, float (&pre)[16]) {
-  float s0[16], s1[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
-  for (int a = 0; a < nk; ++a) {
-    float d0[16], d1[16], d2[16];
-    const uint32_t base = tlane + a * 3 * NC + c0;
-    tmem_ld16(base, d0);
-    tmem_ld16(base + NC, d1);
-    tmem_ld16(base + 2 * NC, d2);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { s0[i] += d0[i]; s1[i] += d1[i] + d2[i]; }
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) pre[i] = fmaf(s1[i], kLoInv, s0[i]);
-}
 
 // n (1, 2 or 4) consecutive k of one image row as hi / lo halves
 __device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, int r, int k, int n, const float* v) {
@@ -95,7 +80,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
   uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x, G = gridDim.x;
-  const int NC = p.NC, U = p.U, KB = p.KB, S = p.stages, KPS = p.kps, NK = p.nk, MM = p.mma_m;
+  const int NC = p.NC, U = p.U, KB = p.KB, S = p.stages, KPS = p.kps, MM = p.mma_m;
+  const bool fused = p.fused != 0;                       // hi and lo rows of the batch share one A tile
   const uint32_t xr = (uint32_t)p.Bpad8 * 128;          // valid rows of one part of an h tile
   const uint32_t wtile = (uint32_t)NC * 256;            // hi + lo weight tile of one k-block
   const uint32_t xstage = (uint32_t)KPS * 2 * xr;
@@ -104,7 +90,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
   Smem sm;
   sm.ring = base;
   sm.wres = base + (size_t)S * stage_bytes;
-  sm.pre = reinterpret_cast<float*>(base + p.pre_offset);
+  sm.pre_hi = reinterpret_cast<float*>(base + p.pre_offset);
+  sm.pre_lo = sm.pre_hi + 64 * (NC + 1);
   uint8_t* bars = base + p.bar_offset;
   sm.full = reinterpret_cast<uint64_t*>(bars);
   sm.empty = sm.full + S;
@@ -130,67 +117,69 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
   const uint32_t tmem = *sm.tptr;
 
   if (warp == 0) {
-    // =========================== producer ===========================
-    if (lane == 0) {
-      if (p.w_resident) {
-        mbar_arrive_expect_tx(sm.wfull, (uint32_t)KB * wtile);
-        tma_bulk_g2s(sm.wres, p.w_img + img_tile_offset(cta, 0, 0, KB, NC), (uint32_t)KB * wtile, sm.wfull);
+    // =========================== producer (warp-uniform, one elected lane issues) ===========================
+    if (p.w_resident && elect_one()) {
+      mbar_arrive_expect_tx(sm.wfull, (uint32_t)KB * wtile);
+      tma_bulk_g2s(sm.wres, p.w_img + img_tile_offset(cta, 0, 0, KB, NC), (uint32_t)KB * wtile, sm.wfull);
+    }
+    uint32_t g = 0;
+    for (int t = 0; t < p.T; ++t) {
+      const unsigned target = (unsigned)(t + 1) * (unsigned)G;
+      while (ld_acquire_u32(p.barrier) < target) {
       }
-      uint32_t g = 0;
-      for (int t = 0; t < p.T; ++t) {
-        const unsigned target = (unsigned)(t + 1) * (unsigned)G;
-        while (ld_acquire_u32(p.barrier) < target) {
-        }
-        fence_proxy_async_global();
-        if (p.dbg && cta == 0) p.dbg[t * 4 + 0] = gtimer();
-        const uint8_t* ximg = p.x_img[t & 1];
-        for (int gi = 0; gi < n_groups; ++gi, ++g) {
-          const int s = g % S;
-          const uint32_t ph = (g / S) & 1;
-          mbar_wait(&sm.empty[s], ph ^ 1);
+      fence_proxy_async_global();
+      if (p.dbg && cta == 0 && lane == 0) p.dbg[t * 4 + 0] = gtimer();
+      const uint8_t* ximg = p.x_img[t & 1];
+      for (int gi = 0; gi < n_groups; ++gi, ++g) {
+        const int s = g % S;
+        const uint32_t ph = (g / S) & 1;
+        mbar_wait(&sm.empty[s], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&sm.full[s], stage_bytes);
           uint8_t* dst = sm.ring + (size_t)s * stage_bytes;
           tma_bulk_g2s(dst, ximg + (size_t)gi * xstage, xstage, &sm.full[s]);
           if (!p.w_resident)
             tma_bulk_g2s(dst + xstage, p.w_img + img_tile_offset(cta, gi * KPS, 0, KB, NC), KPS * wtile, &sm.full[s]);
         }
-        if (p.dbg && cta == 0) p.dbg[t * 4 + 1] = gtimer();
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      const uint32_t idesc_cat = umma_idesc_f16(MM, 2 * NC);   // A_hi x [B_hi ; B_lo]
-      const uint32_t idesc_one = umma_idesc_f16(MM, NC);       // A_lo x B_hi
-      if (p.w_resident) mbar_wait(sm.wfull, 0);
-      uint32_t g = 0;
-      for (int t = 0; t < p.T; ++t) {
-        if (t > 0) mbar_wait(sm.tempty, (t - 1) & 1);
+    // =========================== MMA issuer (warp-uniform) ===========================
+    const uint32_t idesc = umma_idesc_f16(MM, 2 * NC);   // [A_hi;A_lo] (or A_hi / A_lo) x [B_hi ; B_lo]
+    if (p.w_resident) mbar_wait(sm.wfull, 0);
+    uint32_t g = 0;
+    for (int t = 0; t < p.T; ++t) {
+      if (t > 0) mbar_wait(sm.tempty, (t - 1) & 1);
+      tc_fence_after();
+      for (int gi = 0; gi < n_groups; ++gi, ++g) {
+        const int s = g % S;
+        const uint32_t ph = (g / S) & 1;
+        mbar_wait(&sm.full[s], ph);
         tc_fence_after();
-        int k16 = 0;
-        for (int gi = 0; gi < n_groups; ++gi, ++g) {
-          const int s = g % S;
-          const uint32_t ph = (g / S) & 1;
-          mbar_wait(&sm.full[s], ph);
-          tc_fence_after();
-          const uint32_t st0 = smem_u32(sm.ring + (size_t)s * stage_bytes);
-          for (int i = 0; i < KPS; ++i) {
-            const int kb = gi * KPS + i;
-            const uint32_t a_hi0 = st0 + (uint32_t)i * 2 * xr;
-            const uint32_t a_lo0 = a_hi0 + xr;
-            const uint32_t b0 = p.w_resident ? smem_u32(sm.wres + (size_t)kb * wtile) : st0 + xstage + (uint32_t)i * wtile;
+        if (p.dbg && cta == 0 && gi == n_groups - 1 && lane == 0) p.dbg[t * 4 + 1] = gtimer();  // last operand stage landed
+        const uint32_t st0 = smem_u32(sm.ring + (size_t)s * stage_bytes);
+        for (int i = 0; i < KPS; ++i) {
+          const int kb = gi * KPS + i;
+          const uint64_t a_hi = umma_desc_sw128(st0 + (uint32_t)i * 2 * xr);
+          const uint64_t a_lo = umma_desc_sw128(st0 + (uint32_t)i * 2 * xr + xr);
+          const uint64_t bd = umma_desc_sw128(p.w_resident ? smem_u32(sm.wres + (size_t)kb * wtile) : st0 + xstage + (uint32_t)i * wtile);
+          const uint32_t first = (kb == 0) ? 1u : 0u;
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4, ++k16) {
-              const uint32_t acc_col = tmem + (uint32_t)((k16 % NK) * 3 * NC);
-              const uint32_t accumulate = (k16 >= NK) ? 1u : 0u;
-              tc_mma_f16(acc_col, umma_desc_sw128(a_hi0 + k4 * 32), umma_desc_sw128(b0 + k4 * 32), idesc_cat, accumulate);
-              tc_mma_f16(acc_col + 2 * NC, umma_desc_sw128(a_lo0 + k4 * 32), umma_desc_sw128(b0 + k4 * 32), idesc_one, accumulate);
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t accumulate = (first && k4 == 0) ? 0u : 1u;
+            if (elect_one()) {
+              // descriptor start addresses are in 16-byte units: +2 per 16-deep k slice (32 bytes)
+              tc_mma_f16(tmem, a_hi + 2 * k4, bd + 2 * k4, idesc, accumulate);
+              if (!fused) tc_mma_f16(tmem + 2 * NC, a_lo + 2 * k4, bd + 2 * k4, idesc, accumulate);
             }
           }
-          tc_commit(&sm.empty[s]);
         }
-        tc_commit(sm.tfull);
+        if (elect_one()) tc_commit(&sm.empty[s]);
+        __syncwarp();
       }
+      if (elect_one()) tc_commit(sm.tfull);
+      __syncwarp();
     }
   } else {
     // =========================== epilogue ===========================
@@ -198,12 +187,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
     const int et = (warp - 2) * 32 + lane;  // 0..127
     const int H = p.H;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-    // ownership: small batch (B <= 32, M = 64): thread -> (b = et % 32, U/4 units); else thread -> row, all U units
-    const bool small = p.small != 0;
-    const int upt = small ? U / 4 : U;                     // units per thread
-    const int b = small ? (et & 31) : q * 32 + lane;
-    const int unit0 = cta * U + (small ? (et >> 5) * upt : 0);
-    const bool valid = b < p.B;
+    // ownership.  fused (B <= 64): accumulator rows are redistributed through smem and thread et owns
+    // batch row et % Bq and U*Bq/128 units (Bq = 32 or 64); else (B > 64): thread = TMEM lane = batch row, all U units
+    const int Bq = fused ? (p.Bpad8 <= 32 ? 32 : 64) : 128;
+    const int upt = fused ? U * Bq / 128 : U;             // units per thread
+    const int b = fused ? (et % Bq) : q * 32 + lane;
+    const int unit0 = cta * U + (fused ? (et / Bq) * upt : 0);
+    const bool valid = b < p.B && upt > 0;
     float c[LT_MAX_U], h[LT_MAX_U], bsc[LT_MAX_U], bsh[LT_MAX_U];
     const int len = valid ? (p.lens_T ? min(p.lens_T[b], p.T) : p.T) : 0;
 #pragma unroll
@@ -249,7 +239,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
       atomicAdd(p.barrier, 1u);
     }
 
-    const int prs = NC + 1;  // row stride of the exchange buffer
+    const int prs = NC + 1;  // row stride of the exchange buffers
     for (int t = 0; t < p.T; ++t) {
       const int64_t row = (int64_t)b * p.T + t;
       // hoisted input projection of this thread's units for step t: issued before the accumulators are ready
@@ -261,16 +251,24 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
       tc_fence_after();
       if (p.dbg && cta == 0 && et == 0) p.dbg[t * 4 + 2] = gtimer();
       float hy[LT_MAX_U];
-      if (small) {
-        // M = 64: batch row r lives in TMEM lane (r % 16) + 32 * (r / 16): quarters 0 and 1 hold rows 0..31
-        if (q * 16 < p.Bpad8) {
-          const int r = q * 16 + lane;
+      if (fused) {
+        // accumulator row r: r < Bpad8 -> hi row of batch r; else lo row of batch r - Bpad8.
+        // M = 64: row r sits in TMEM lane (r % 16) + 32 * (r / 16); M = 128: lane r.
+        const int rows_per_warp = MM == 64 ? 16 : 32;
+        const int r = q * rows_per_warp + lane;
+        if (q * rows_per_warp < 2 * p.Bpad8) {
+          const bool mine = lane < rows_per_warp && r < 2 * p.Bpad8;
+          const bool is_lo = r >= p.Bpad8;
+          float* dstrow = (is_lo ? sm.pre_lo + (r - p.Bpad8) * prs : sm.pre_hi + r * prs);
+          const float sc = is_lo ? kLoInv : 1.0f;
           for (int c0 = 0; c0 < NC; c0 += 16) {
-            float pre[16];
-            load_pre16(tlane, c0, NC, NK, pre);
-            if (lane < 16) {
+            float d0[16], d1[16];
+            tmem_ld16(tlane + c0, d0);
+            tmem_ld16(tlane + NC + c0, d1);
+            tmem_ld_wait();
+            if (mine) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) sm.pre[r * prs + c0 + i] = pre[i];
+              for (int i = 0; i < 16; ++i) dstrow[c0 + i] = sc * fmaf(d1[i], kLoInv, d0[i]);
             }
           }
         }
@@ -278,13 +276,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
         mbar_arrive(sm.tempty);
         named_bar_sync(1, 128);
         if (valid) {
-          const float* pr = sm.pre + b * prs + (unit0 - cta * U) * 4;
+          const int lc = (unit0 - cta * U) * 4;
+          const float* ph = sm.pre_hi + b * prs + lc;
+          const float* pl = sm.pre_lo + b * prs + lc;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < LT_MAX_U; ++j) {
             if (j < upt) {
               if (t < len) {
-                const float vi = pr[4 * j + 0] + xv[j].x, vf = pr[4 * j + 1] + xv[j].y;
-                const float vg = pr[4 * j + 2] + xv[j].z, vo = pr[4 * j + 3] + xv[j].w;
+                const float vi = (ph[4 * j + 0] + pl[4 * j + 0]) + xv[j].x, vf = (ph[4 * j + 1] + pl[4 * j + 1]) + xv[j].y;
+                const float vg = (ph[4 * j + 2] + pl[4 * j + 2]) + xv[j].z, vo = (ph[4 * j + 3] + pl[4 * j + 3]) + xv[j].w;
                 const float cn = sigmoidf_acc(vf) * c[j] + sigmoidf_acc(vi) * tanhf(vg);
                 c[j] = cn;
                 h[j] = sigmoidf_acc(vo) * tanhf(cn);
@@ -297,14 +297,24 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
 #pragma unroll
         for (int j0 = 0; j0 < LT_MAX_U; j0 += 4) {  // 16 gate columns = 4 units per chunk
           if (j0 < U) {
-            float pre[16];
-            load_pre16(tlane, j0 * 4, NC, NK, pre);
+            float d0[16], d1[16], e0[16], e1[16];
+            tmem_ld16(tlane + j0 * 4, d0);                 // hi*hi
+            tmem_ld16(tlane + NC + j0 * 4, d1);            // hi*lo
+            tmem_ld16(tlane + 2 * NC + j0 * 4, e0);        // lo*hi
+            tmem_ld16(tlane + 3 * NC + j0 * 4, e1);        // lo*lo
+            tmem_ld_wait();
             if (valid) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 if (t < len) {
-                  const float vi = pre[4 * j + 0] + xv[j0 + j].x, vf = pre[4 * j + 1] + xv[j0 + j].y;
-                  const float vg = pre[4 * j + 2] + xv[j0 + j].z, vo = pre[4 * j + 3] + xv[j0 + j].w;
+                  float pre[4];
+#pragma unroll
+                  for (int gg = 0; gg < 4; ++gg) {
+                    const int i = 4 * j + gg;
+                    pre[gg] = fmaf(d1[i], kLoInv, d0[i]) + kLoInv * fmaf(e1[i], kLoInv, e0[i]);
+                  }
+                  const float vi = pre[0] + xv[j0 + j].x, vf = pre[1] + xv[j0 + j].y;
+                  const float vg = pre[2] + xv[j0 + j].z, vo = pre[3] + xv[j0 + j].w;
                   const float cn = sigmoidf_acc(vf) * c[j0 + j] + sigmoidf_acc(vi) * tanhf(vg);
                   c[j0 + j] = cn;
                   h[j0 + j] = sigmoidf_acc(vo) * tanhf(cn);
@@ -374,17 +384,16 @@ bool lstm_tc_plan(int H, int B, int sms, LstmTcPlan* pl) {
   pl->grid = H / U;
   pl->KB = H / 64;
   pl->Bpad8 = (int)round_up(B, 8);
-  pl->small = B <= 32 ? 1 : 0;
-  pl->mma_m = pl->small ? 64 : 128;
-  pl->nk = 1;
-  for (int n : {4, 2})
-    if (n * 3 * pl->NC <= 512) { pl->nk = n; break; }
+  pl->fused = pl->Bpad8 <= 64 ? 1 : 0;                     // hi + lo rows of the batch fit one MMA M tile
+  pl->mma_m = (pl->fused && 2 * pl->Bpad8 <= 64) ? 64 : 128;
+  if (pl->fused && (U * (pl->Bpad8 <= 32 ? 32 : 64)) % 128) return false;
   int cols = 32;
-  while (cols < pl->nk * 3 * pl->NC) cols *= 2;
+  while (cols < (pl->fused ? 2 : 4) * pl->NC) cols *= 2;
+  if (cols > 512) return false;
   pl->tmem_cols = cols;
   const size_t xr = (size_t)pl->Bpad8 * 128, wtile = (size_t)pl->NC * 256;
-  const size_t guard = (size_t)pl->mma_m * 128;   // an A tile is read as mma_m rows; rows >= Bpad8 alias what follows
-  const size_t pre_bytes = pl->small ? round_up((size_t)32 * (pl->NC + 1) * 4, 1024) : 0;
+  const size_t guard = (size_t)pl->mma_m * 128;   // an A tile is read as mma_m rows; rows beyond the valid ones alias what follows
+  const size_t pre_bytes = pl->fused ? round_up((size_t)2 * 64 * (pl->NC + 1) * 4, 1024) : 0;
   const size_t budget = 227 * 1024 - 2048 /*alignment slack + barriers*/ - guard - pre_bytes;
   const size_t wall = (size_t)pl->KB * wtile;
   for (int want_res = 1; want_res >= 0; --want_res) {   // prefer the W-resident layout
@@ -415,7 +424,7 @@ cudaError_t launch_lstm_layer_tc(const LstmTcArgs& a, const LstmTcPlan& pl, cuda
   LstmTcArgs args = a;
   args.U = pl.U; args.NC = pl.NC; args.KB = pl.KB; args.Bpad8 = pl.Bpad8; args.stages = pl.stages;
   args.w_resident = pl.w_resident; args.bar_offset = pl.bar_offset; args.tmem_cols = pl.tmem_cols;
-  args.kps = pl.kps; args.nk = pl.nk; args.mma_m = pl.mma_m; args.small = pl.small; args.pre_offset = pl.pre_offset;
+  args.kps = pl.kps; args.mma_m = pl.mma_m; args.fused = pl.fused; args.pre_offset = pl.pre_offset;
   void* kargs[] = {&args};
   return cudaLaunchCooperativeKernel((void*)lstm_layer_tc_kernel, dim3(pl.grid), dim3(LT_THREADS), kargs, pl.smem_bytes, st);
 }
