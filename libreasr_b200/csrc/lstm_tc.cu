@@ -43,6 +43,9 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -75,13 +78,14 @@ __device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, 
   }
 }
 
+template <bool FUSED>
 __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x, G = gridDim.x;
   const int NC = p.NC, U = p.U, KB = p.KB, S = p.stages, KPS = p.kps, MM = p.mma_m;
-  const bool fused = p.fused != 0;                       // hi and lo rows of the batch share one A tile
+  constexpr bool fused = FUSED;                          // hi and lo rows of the batch share one A tile
   const uint32_t xr = (uint32_t)p.Bpad8 * 128;          // valid rows of one part of an h tile
   const uint32_t wtile = (uint32_t)NC * 256;            // hi + lo weight tile of one k-block
   const uint32_t xstage = (uint32_t)KPS * 2 * xr;
@@ -145,9 +149,16 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer (warp-uniform) ===========================
+    // =========================== MMA issuer ===========================
+    // Warp-uniform control flow; ONE elected lane per pipeline stage issues all of the stage's
+    // tcgen05.mma.  Descriptors are a loop-invariant base plus small 16-byte-unit offsets (+2 per
+    // 16-deep k slice) so that the per-instruction overhead stays near the ~35-50 cycle issue floor.
     const uint32_t idesc = umma_idesc_f16(MM, 2 * NC);   // [A_hi;A_lo] (or A_hi / A_lo) x [B_hi ; B_lo]
-    if (p.w_resident) mbar_wait(sm.wfull, 0);
+    const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sm.ring));
+    const uint64_t b_desc0 = umma_desc_sw128(p.w_resident ? smem_u32(sm.wres) : smem_u32(sm.ring) + xstage);
+    const uint32_t stage_u = stage_bytes >> 4, kb_u = (2 * xr) >> 4, lo_u = xr >> 4, wt_u = wtile >> 4;
+    const bool wres = p.w_resident != 0;
+    if (wres) mbar_wait(sm.wfull, 0);
     uint32_t g = 0;
     for (int t = 0; t < p.T; ++t) {
       if (t > 0) mbar_wait(sm.tempty, (t - 1) & 1);
@@ -158,28 +169,25 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
         mbar_wait(&sm.full[s], ph);
         tc_fence_after();
         if (p.dbg && cta == 0 && gi == n_groups - 1 && lane == 0) p.dbg[t * 4 + 1] = gtimer();  // last operand stage landed
-        const uint32_t st0 = smem_u32(sm.ring + (size_t)s * stage_bytes);
-        for (int i = 0; i < KPS; ++i) {
-          const int kb = gi * KPS + i;
-          const uint64_t a_hi = umma_desc_sw128(st0 + (uint32_t)i * 2 * xr);
-          const uint64_t a_lo = umma_desc_sw128(st0 + (uint32_t)i * 2 * xr + xr);
-          const uint64_t bd = umma_desc_sw128(p.w_resident ? smem_u32(sm.wres + (size_t)kb * wtile) : st0 + xstage + (uint32_t)i * wtile);
-          const uint32_t first = (kb == 0) ? 1u : 0u;
+        if (elect_one()) {
+          uint64_t ad = a_desc0 + (uint64_t)(s * stage_u);
+          uint64_t bd = b_desc0 + (uint64_t)(wres ? (uint32_t)(gi * KPS) * wt_u : s * stage_u);
+          uint32_t accumulate = gi == 0 ? 0u : 1u;
+          for (int i = 0; i < KPS; ++i) {
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const uint32_t accumulate = (first && k4 == 0) ? 0u : 1u;
-            if (elect_one()) {
-              // descriptor start addresses are in 16-byte units: +2 per 16-deep k slice (32 bytes)
-              tc_mma_f16(tmem, a_hi + 2 * k4, bd + 2 * k4, idesc, accumulate);
-              if (!fused) tc_mma_f16(tmem + 2 * NC, a_lo + 2 * k4, bd + 2 * k4, idesc, accumulate);
+            for (int k4 = 0; k4 < 4; ++k4) {
+              tc_mma_f16(tmem, ad + 2 * k4, bd + 2 * k4, idesc, accumulate);
+              if (!FUSED) tc_mma_f16(tmem + 2 * NC, ad + lo_u + 2 * k4, bd + 2 * k4, idesc, accumulate);
+              accumulate = 1u;
             }
+            ad += kb_u;
+            bd += wt_u;
           }
+          tc_commit(&sm.empty[s]);
+          if (gi == n_groups - 1) tc_commit(sm.tfull);
         }
-        if (elect_one()) tc_commit(&sm.empty[s]);
         __syncwarp();
       }
-      if (elect_one()) tc_commit(sm.tfull);
-      __syncwarp();
     }
   } else {
     // =========================== epilogue ===========================
@@ -232,12 +240,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
       }
     };
     if (valid) store_h(p.x_img[0], h);
-    fence_proxy_async_global();
     named_bar_sync(1, 128);
-    if (et == 0) {
-      __threadfence();
-      atomicAdd(p.barrier, 1u);
-    }
+    if (et == 0) red_release_add(p.barrier, 1u);
 
     const int prs = NC + 1;  // row stride of the exchange buffers
     for (int t = 0; t < p.T; ++t) {
@@ -343,11 +347,11 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
         }
         if (p.y_img) store_yimg(row, hy);
       }
-      fence_proxy_async_global();
+      // h_t stores (generic proxy) -> CTA barrier -> one gpu-scope release on the step counter; the
+      // consumers pair it with ld.acquire + fence.proxy.async before their TMA reads of the image
       named_bar_sync(1, 128);
       if (et == 0) {
-        __threadfence();
-        atomicAdd(p.barrier, 1u);
+        red_release_add(p.barrier, 1u);
         if (p.dbg && cta == 0) p.dbg[t * 4 + 3] = gtimer();
       }
     }
@@ -369,7 +373,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
 }  // namespace
 
 cudaError_t configure_lstm_tc() {
-  return cudaFuncSetAttribute(lstm_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(lstm_layer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(lstm_layer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 // Chooses the decomposition for hidden size H, batch B on a device with `sms` SMs; false if none fits.
@@ -426,7 +432,8 @@ cudaError_t launch_lstm_layer_tc(const LstmTcArgs& a, const LstmTcPlan& pl, cuda
   args.w_resident = pl.w_resident; args.bar_offset = pl.bar_offset; args.tmem_cols = pl.tmem_cols;
   args.kps = pl.kps; args.mma_m = pl.mma_m; args.fused = pl.fused; args.pre_offset = pl.pre_offset;
   void* kargs[] = {&args};
-  return cudaLaunchCooperativeKernel((void*)lstm_layer_tc_kernel, dim3(pl.grid), dim3(LT_THREADS), kargs, pl.smem_bytes, st);
+  void* fn = pl.fused ? (void*)lstm_layer_tc_kernel<true> : (void*)lstm_layer_tc_kernel<false>;
+  return cudaLaunchCooperativeKernel(fn, dim3(pl.grid), dim3(LT_THREADS), kargs, pl.smem_bytes, st);
 }
 
 }  // namespace rnnt
