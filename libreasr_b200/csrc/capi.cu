@@ -70,6 +70,11 @@ struct rnnt_b200_handle_s {
   std::vector<uint8_t*> Wih_img;       // TC modes: operand images of the interleaved W_ih
   std::vector<uint8_t*> Whh_img;       // TC modes: operand images (TR = NC) of the interleaved W_hh
   bool lstm_tc_ok = false;             // persistent tcgen05 LSTM layer usable for this H / SM count
+  bool dec_tc_ok = false;              // tcgen05 decode kernel usable
+  uint8_t *W1p_img = nullptr, *W2_img = nullptr;
+  uint8_t* R_img[kMaxPredLayers] = {nullptr, nullptr, nullptr, nullptr};
+  uint8_t* K_img[kMaxPredLayers] = {nullptr, nullptr, nullptr, nullptr};
+  DevBuf dimg;                         // decode activation operand images
   DevBuf x_img[2], gbar;               // TC modes: h operand images (ping-pong), grid step counter
   DevBuf a_img;                        // TC modes: activation operand image (workspace)
   // workspaces
@@ -238,7 +243,7 @@ int32_t rnnt_b200_create(const rnnt_b200_config* cfg, rnnt_b200_handle* out) {
   h->cfg = *cfg;
   h->sm_count = prop.multiProcessorCount;
   if ((e = configure_lstm()) != cudaSuccess || (e = configure_gemm_tc()) != cudaSuccess ||
-      (e = configure_lstm_tc()) != cudaSuccess || (e = configure_decode(cfg->device, &h->coop_blocks)) != cudaSuccess) {
+      (e = configure_lstm_tc()) != cudaSuccess || (e = configure_decode_tc()) != cudaSuccess || (e = configure_decode(cfg->device, &h->coop_blocks)) != cudaSuccess) {
     delete h;
     return fail_cuda(nullptr, e, "kernel configuration");
   }
@@ -253,7 +258,7 @@ int32_t rnnt_b200_destroy(rnnt_b200_handle h) {
   for (void* p : h->weight_allocs) cudaFree(p);
   DevBuf* bufs[] = {&h->feats, &h->lnx, &h->xp, &h->ya, &h->yb, &h->ep, &h->ehT[0], &h->ehT[1], &h->ecT, &h->dhT, &h->dxT,
                     &h->dgT, &h->deT, &h->dppT, &h->dzT, &h->dpart, &h->dlse, &h->t_audio, &h->t_lens, &h->t_tokens,
-                    &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc, &h->a_img, &h->x_img[0], &h->x_img[1], &h->gbar};
+                    &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc, &h->a_img, &h->x_img[0], &h->x_img[1], &h->gbar, &h->dimg};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t* set : h->evsets) {
     for (int i = 0; i < 6; ++i) cudaEventDestroy(set[i]);
@@ -452,6 +457,16 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
     LAUNCH(1, launch_gather_rows(d_t1, d_t2, perm3, 3 * H, H, st));  // rows interleaved
     LAUNCH(1, launch_transpose(d_t2, H, Rt, 3 * H, H, st));          // [H][3H interleaved]
     dw.Rt[l] = Rt;
+    DecodeTcPlan dpl;
+    const bool dtc = c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && decode_tc_wplan(H, J, V, h->sm_count, &dpl);
+    h->dec_tc_ok = dtc;
+    if (dtc) {
+      void* img = nullptr;
+      CK(cudaMalloc(&img, img_bytes((int64_t)dpl.G * dpl.NC_C, H, dpl.NC_C)));
+      h->weight_allocs.push_back(img);
+      h->R_img[l] = (uint8_t*)img;
+      LAUNCH(1, launch_to_image(d_t2, H, 3 * H, H, dpl.NC_C, (uint8_t*)img, st));   // d_t2: [3H interleaved][H]
+    }
     float* d_k;
     CK(tmp_upload(*kern, &d_k));
     if (l == 0) {
@@ -486,6 +501,13 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
       LAUNCH(1, launch_transpose(d_k, 3 * H, d_a, H, 3 * H, st));
       LAUNCH(1, launch_gather_rows(d_a, d_b, perm3, 3 * H, H, st));
       LAUNCH(1, launch_transpose(d_b, H, Kt, 3 * H, H, st));
+      if (dtc) {
+        void* img = nullptr;
+        CK(cudaMalloc(&img, img_bytes((int64_t)dpl.G * dpl.NC_C, H, dpl.NC_C)));
+        h->weight_allocs.push_back(img);
+        h->K_img[l] = (uint8_t*)img;
+        LAUNCH(1, launch_to_image(d_b, H, 3 * H, H, dpl.NC_C, (uint8_t*)img, st));   // d_b: [3H interleaved][H]
+      }
       CK(upload(h, interleave(*kb, 3), &t_kb));
       dw.Kt[l] = Kt; dw.kbias[l] = t_kb;
     }
@@ -515,6 +537,18 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
       h->weight_allocs.push_back(img);
       h->W1e_img = (uint8_t*)img;
       LAUNCH(1, launch_to_image(h->W1 + H, 2 * H, J, H, 256, h->W1e_img, st));
+      DecodeTcPlan dpl;
+      if (h->dec_tc_ok && decode_tc_wplan(H, J, V, h->sm_count, &dpl)) {
+        void *ia = nullptr, *ib = nullptr;
+        CK(cudaMalloc(&ia, img_bytes((int64_t)dpl.G * dpl.NC_A, H, dpl.NC_A)));
+        CK(cudaMalloc(&ib, img_bytes((int64_t)dpl.G * dpl.NC_B, J, dpl.NC_B)));
+        h->weight_allocs.push_back(ia);
+        h->weight_allocs.push_back(ib);
+        h->W1p_img = (uint8_t*)ia;
+        h->W2_img = (uint8_t*)ib;
+        LAUNCH(1, launch_to_image(h->W1, 2 * H, J, H, dpl.NC_A, h->W1p_img, st));   // pred half: first H columns
+        LAUNCH(1, launch_to_image(d_w2, J, V, J, dpl.NC_B, h->W2_img, st));
+      }
     }
   }
 #undef NEED
@@ -794,6 +828,39 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     LAUNCH(1, launch_gemm_nt_f32(enc, H, h->W1 + H, 2 * H, h->dw.b1, h->ep.as<float>(), J, M, J, H, st));
   }
   if (h->ev) cudaEventRecord(h->ev[3], st);
+  DecodeTcPlan dpl;
+  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && decode_tc_plan(H, J, c.vocab_sz, B, h->sm_count, &dpl)) {
+    const size_t one = (size_t)(std::max(H, J) / 64) * 2 * dpl.Bpad8 * 128;
+    const int nimg = 4 + 2 * c.pred_layers;
+    CK(h->dimg.ensure(one * nimg));
+    CK(h->dpart.ensure((size_t)dpl.G * dpl.Bq * 16));
+    CK(h->gbar.ensure(64));
+    CK(cudaMemsetAsync(h->gbar.p, 0, 4, st));
+    if (trace_logp) {
+      CK(cudaMemsetAsync(h->dlse.p, 0, (size_t)B * trace_cap * 4, st));
+      CK(cudaMemsetAsync(trace_logp, 0, (size_t)B * trace_cap * c.vocab_sz * 4, st));
+    }
+    if (iters_out) CK(cudaMemsetAsync(iters_out, 0, (size_t)B * T, st));
+    DecodeTcArgs t;
+    memset(&t, 0, sizeof(t));
+    t.w = h->dw;
+    t.w1p_img = h->W1p_img; t.w2_img = h->W2_img;
+    uint8_t* ib = h->dimg.as<uint8_t>();
+    t.g_img = ib; t.z_img = ib + one; t.x_img[0] = ib + 2 * one; t.x_img[1] = ib + 3 * one;
+    for (int l = 0; l < c.pred_layers; ++l) {
+      t.r_img[l] = h->R_img[l]; t.k_img[l] = h->K_img[l];
+      t.h_img[l][0] = ib + (4 + 2 * l) * one; t.h_img[l][1] = ib + (5 + 2 * l) * one;
+    }
+    t.ep = h->ep.as<float>(); t.lens_T = lens_T; t.B = B; t.T = T; t.max_iters = max_iters; t.use_state_in = use_state_in;
+    t.part = h->dpart.as<float>(); t.trace_lse = h->dlse.as<float>();
+    t.state_h = pred_state_h; t.pred_out = pred_out;
+    t.tokens = tokens_out; t.U_cap = U_cap; t.ntok = ntok_out; t.neg_logp = neg_logp_out; t.iters = iters_out;
+    t.trace = trace_logp; t.trace_cap = trace_logp ? trace_cap : 0;
+    t.barrier = h->gbar.as<unsigned int>();
+    LAUNCH(trace_logp ? 2 : 1, launch_decode_tc(t, dpl, st));
+    if (h->ev) cudaEventRecord(h->ev[4], st);
+    return RNNT_B200_OK;
+  }
   const size_t hb = (size_t)H * Bp;
   float* dh = h->dhT.as<float>();
   DecodeArgs a;

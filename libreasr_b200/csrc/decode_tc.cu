@@ -1,0 +1,638 @@
+// Device-resident batched greedy RNN-T decode on the tcgen05 tensor cores (gemm_mode 1).
+//
+// Same loop as decode.cu (reference libreasr/lib/models.py:403-443 / 528-571): per lock-step
+//   A  pp = W1p * g (utterances whose predictor output changed), z = tanh(pp + ep[b, t_b])
+//   B  logits slice = W2 * z + b2 -> per-CTA (max, argmax, sum exp) partials
+//   R  every CTA folds the partials and applies the blank / max_iters rule to its own copy
+//      of the control state
+//   C..  one phase per predictor layer (GRU cell + BatchNorm eval; layer 0 input = table lookup)
+// but every contraction is a skinny tcgen05 GEMM in the formulation of lstm_tc.cu: the BATCH is
+// on the MMA M axis with the hi rows stacked on the lo rows of the 3xFP16 split, the CTA's slice
+// of weight rows [hi;lo] on N -- ONE tcgen05.mma per 16-deep k slice gives all four split
+// products -- and both operands stream from their operand images (tc_common.cuh) with TMA bulk
+// copies through one mbarrier ring.  All G = H / Uc CTAs take a slice of every phase.
+//   warp 0     producer (TMA bulk copies; waits on the grid phase counter before touching an
+//              activation image another CTA wrote)
+//   warp 1     MMA issuer (one elected lane per stage)
+//   warps 2-5  epilogue: TMEM -> smem exchange -> thread (b, rows) math; predictor state h, the
+//              joint pre-activation pp and the control state live in registers / smem for the
+//              whole decode; results are written straight into the next phase's operand image
+// Grid-wide synchronisation = one release-add on a phase counter per phase.
+#include <algorithm>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace rnnt {
+namespace {
+
+constexpr int DT_THREADS = 192;
+constexpr int DT_MAXB = 64;
+constexpr int DT_MAX_RPT = 8;   // rows (or units) per epilogue thread
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct Ctrl {
+  double nlp[DT_MAXB];
+  int t[DT_MAXB], it[DT_MAXB], ntok[DT_MAXB], tok[DT_MAXB], n_eval[DT_MAXB], len[DT_MAXB];
+  float red[4][DT_MAXB][4];   // partial (max, argmax, sumexp) exchange between the threads of one batch row
+  unsigned char active[DT_MAXB], emit[DT_MAXB];
+  int flags[2];               // any_emit, any_active of the current step
+};
+
+// n (1, 2 or 4) consecutive k of one image row as hi / lo halves
+__device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, int r, int k, int n, const float* v) {
+  __align__(8) __half hi[4];
+  __align__(8) __half lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < n) split_f16x3(v[j], hi[j], lo[j]);
+  const uint32_t off = img_elem_offset(r, k);
+  if (n == 4) {
+    *reinterpret_cast<uint2*>(hi_tile + off) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(lo_tile + off) = *reinterpret_cast<const uint2*>(lo);
+  } else if (n == 2) {
+    *reinterpret_cast<uint32_t*>(hi_tile + off) = *reinterpret_cast<const uint32_t*>(hi);
+    *reinterpret_cast<uint32_t*>(lo_tile + off) = *reinterpret_cast<const uint32_t*>(lo);
+  } else {
+    *reinterpret_cast<__half*>(hi_tile + off) = hi[0];
+    *reinterpret_cast<__half*>(lo_tile + off) = lo[0];
+  }
+}
+
+// One GEMM of a phase: activation image x weight-slice image -> TMEM columns [col, col + 2*NC)
+struct Gemm {
+  const uint8_t* act;   // activation image (TR = Bpad8 tiles, [kb][part] contiguous)
+  const uint8_t* w;     // this CTA's weight tiles ([kb][part] contiguous, NC rows each)
+  int KB, NC, col;
+};
+
+__global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x, G = gridDim.x;
+  const DecodeWeights& w = p.w;
+  const int H = w.H, J = w.J, V = w.V, Lp = w.Lp;
+  const int S = p.stages, KPS = p.kps, MM = p.mma_m, Bq = p.Bq, B = p.B, T = p.T;
+  const uint32_t xr = (uint32_t)p.Bpad8 * 128;
+  const uint32_t xkb = 2 * xr;                                  // activation bytes per k-block (hi | lo rows)
+  const uint32_t wmax = (uint32_t)p.NC_max * 256;               // weight bytes per k-block reserved in a stage
+  const uint32_t stage_bytes = (uint32_t)KPS * (xkb + wmax);
+  uint8_t* ring = base;
+  float* pre_hi = reinterpret_cast<float*>(base + p.pre_offset);
+  const int prs = 4 * p.NC_max + 1;                             // exchange row stride (two GEMMs of 2*NC_max columns)
+  float* pre_lo = pre_hi + Bq * prs;
+  Ctrl& c = *reinterpret_cast<Ctrl*>(base + p.ctl_offset);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + p.bar_offset);
+  uint64_t* empty = full + S;
+  uint64_t* tfull = empty + S;
+  uint64_t* tempty = tfull + 1;
+  uint64_t* ctlbar = tempty + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(ctlbar + 1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 128);
+    mbar_init(ctlbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tptr, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr;
+
+  // ---- per-phase slices of this CTA (CTAs beyond the slice count sit a phase out but keep the barriers) ----
+  const int KBH = H / 64, KBJ = J / 64;
+  const bool in_A = cta * p.NC_A < J, in_B = cta * p.NC_B < V;   // GRU phases: every CTA owns Uc units
+  const uint8_t* wA = p.w1p_img + img_tile_offset(cta, 0, 0, KBH, p.NC_A);
+  const uint8_t* wB = p.w2_img + img_tile_offset(cta, 0, 0, KBJ, p.NC_B);
+
+  // The three roles walk the same phase sequence; `phase_gemms` describes the GEMMs of a phase.
+  //   phase 0 = A (pp), 1 = B (logits), 2 + l = predictor layer l.  par = parity of the h images.
+  auto phase_gemms = [&](int phase, int par, Gemm (&gm)[2]) -> int {
+    if (phase == 0) {
+      if (!in_A) return 0;
+      gm[0] = Gemm{p.g_img, wA, KBH, p.NC_A, 0};
+      return 1;
+    }
+    if (phase == 1) {
+      if (!in_B) return 0;
+      gm[0] = Gemm{p.z_img, wB, KBJ, p.NC_B, 0};
+      return 1;
+    }
+    const int l = phase - 2;
+    int n = 0;
+    if (l > 0) gm[n++] = Gemm{p.x_img[(l - 1) & 1], p.k_img[l] + img_tile_offset(cta, 0, 0, KBH, p.NC_C), KBH, p.NC_C, 0};
+    gm[n] = Gemm{p.h_img[l][par], p.r_img[l] + img_tile_offset(cta, 0, 0, KBH, p.NC_C), KBH, p.NC_C, n * 2 * p.NC_C};
+    return n + 1;
+  };
+
+  if (warp == 0) {
+    // =========================== producer ===========================
+    uint32_t g = 0;
+    unsigned nbar = 1;   // grid barriers to wait for before a phase reads activations (1 = initial images)
+    auto run_phase = [&](int phase, int par) {
+      Gemm gm[2];
+      const int ng = phase_gemms(phase, par, gm);
+      if (ng > 0) {
+        while (ld_acquire_u32(p.barrier) < nbar * (unsigned)G) {
+        }
+        fence_proxy_async_global();
+      }
+      for (int q = 0; q < ng; ++q) {
+        const uint32_t wkb = (uint32_t)gm[q].NC * 256;
+        for (int kb0 = 0; kb0 < gm[q].KB; kb0 += KPS, ++g) {
+          const int s = g % S;
+          const uint32_t ph = (g / S) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          if (elect_one()) {
+            const int nkb = min(KPS, gm[q].KB - kb0);
+            mbar_arrive_expect_tx(&full[s], (uint32_t)nkb * (xkb + wkb));
+            uint8_t* dst = ring + (size_t)s * stage_bytes;
+            tma_bulk_g2s(dst, gm[q].act + (size_t)kb0 * xkb, (uint32_t)nkb * xkb, &full[s]);
+            tma_bulk_g2s(dst + KPS * xkb, gm[q].w + (size_t)kb0 * wkb, (uint32_t)nkb * wkb, &full[s]);
+          }
+          __syncwarp();
+        }
+      }
+      ++nbar;
+    };
+    int par = 0;
+    if (!p.use_state_in) {
+      for (int l = 0; l < Lp; ++l) run_phase(2 + l, par);
+      par ^= 1;
+    }
+    bool any_upd = true;
+    for (int step = 0;; ++step) {
+      if (any_upd) run_phase(0, par); else ++nbar;
+      run_phase(1, par);
+      mbar_wait(ctlbar, step & 1);
+      const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
+      if (any_emit) {
+        for (int l = 0; l < Lp; ++l) run_phase(2 + l, par);
+        par ^= 1;
+      }
+      any_upd = any_emit;
+      if (!any_active) break;
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    const uint64_t a_desc0 = umma_desc_sw128(smem_u32(ring));
+    const uint64_t b_desc0 = umma_desc_sw128(smem_u32(ring) + KPS * xkb);
+    const uint32_t stage_u = stage_bytes >> 4, xkb_u = xkb >> 4;
+    uint32_t g = 0, nacc = 0;
+    auto run_phase = [&](int phase, int par) {
+      Gemm gm[2];
+      const int ng = phase_gemms(phase, par, gm);
+      if (ng == 0) return;
+      if (nacc > 0) mbar_wait(tempty, (nacc - 1) & 1);
+      tc_fence_after();
+      for (int q = 0; q < ng; ++q) {
+        const uint32_t idesc = umma_idesc_f16(MM, 2 * gm[q].NC);
+        const uint32_t wkb_u = ((uint32_t)gm[q].NC * 256) >> 4;
+        const uint32_t dcol = tmem + (uint32_t)gm[q].col;
+        for (int kb0 = 0; kb0 < gm[q].KB; kb0 += KPS, ++g) {
+          const int s = g % S;
+          const uint32_t ph = (g / S) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const int nkb = min(KPS, gm[q].KB - kb0);
+            uint64_t ad = a_desc0 + (uint64_t)(s * stage_u);
+            uint64_t bd = b_desc0 + (uint64_t)(s * stage_u);
+            uint32_t accumulate = kb0 == 0 ? 0u : 1u;
+            for (int i = 0; i < nkb; ++i) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                tc_mma_f16(dcol, ad + 2 * k4, bd + 2 * k4, idesc, accumulate);
+                accumulate = 1u;
+              }
+              ad += xkb_u;
+              bd += wkb_u;
+            }
+            tc_commit(&empty[s]);
+            if (q == ng - 1 && kb0 + KPS >= gm[q].KB) tc_commit(tfull);
+          }
+          __syncwarp();
+        }
+      }
+      ++nacc;
+    };
+    int par = 0;
+    if (!p.use_state_in) {
+      for (int l = 0; l < Lp; ++l) run_phase(2 + l, par);
+      par ^= 1;
+    }
+    bool any_upd = true;
+    for (int step = 0;; ++step) {
+      if (any_upd) run_phase(0, par);
+      run_phase(1, par);
+      mbar_wait(ctlbar, step & 1);
+      const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
+      if (any_emit) {
+        for (int l = 0; l < Lp; ++l) run_phase(2 + l, par);
+        par ^= 1;
+      }
+      any_upd = any_emit;
+      if (!any_active) break;
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int q = warp & 3;
+    const int et = (warp - 2) * 32 + lane;               // 0..127
+    const int tpr = 128 / Bq;                            // threads per batch row (4 or 2)
+    const int b = et % Bq, sub = et / Bq;
+    const bool bvalid = b < B;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    const int rows_per_warp = MM == 64 ? 16 : 32;
+    uint32_t nacc = 0;
+
+    // control state (identical in every CTA)
+    for (int i = et; i < DT_MAXB; i += 128) {
+      const int len = (i < B) ? (p.lens_T ? min(p.lens_T[i], T) : T) : 0;
+      c.len[i] = len; c.t[i] = 0; c.it[i] = 0; c.ntok[i] = 0; c.n_eval[i] = 0; c.nlp[i] = 0.0;
+      c.tok[i] = w.bos; c.active[i] = len > 0; c.emit[i] = i < B;
+    }
+
+    // TMEM accumulator rows -> exchange buffers (row r < Bpad8: hi row of batch r, else lo row of batch r - Bpad8)
+    auto drain = [&](int ncols /*multiple of 8*/) {
+      mbar_wait(tfull, nacc & 1);
+      tc_fence_after();
+      const int r = q * rows_per_warp + lane;
+      if (q * rows_per_warp < 2 * p.Bpad8) {
+        const bool mine = lane < rows_per_warp && r < 2 * p.Bpad8;
+        const bool is_lo = r >= p.Bpad8;
+        float* dstrow = is_lo ? pre_lo + (r - p.Bpad8) * prs : pre_hi + r * prs;
+        const float sc = is_lo ? kLoInv : 1.0f;
+        // a GEMM with NC rows occupies 2*NC columns: [0,NC) x*hi, [NC,2NC) x*lo
+        for (int c0 = 0; c0 < ncols; c0 += 16) {
+          float d[16];
+          tmem_ld16(tlane + c0, d);
+          tmem_ld_wait();
+          if (mine) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < ncols) dstrow[c0 + i] = sc * d[i];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty);
+      ++nacc;
+      named_bar_sync(1, 128);
+    };
+    // value of GEMM `gi` (NC rows at TMEM column base gi*2*NC), row `rr`, batch b:  hi-row and lo-row pieces summed
+    auto pre_val = [&](int gbase, int NC, int rr) -> float {
+      const float* ph = pre_hi + b * prs + gbase;
+      const float* pl = pre_lo + b * prs + gbase;
+      return (ph[rr] + kLoInv * ph[NC + rr]) + (pl[rr] + kLoInv * pl[NC + rr]);
+    };
+    unsigned ebar = 0;   // grid arrivals so far (same count in every CTA)
+    auto grid_arrive = [&]() {
+      named_bar_sync(1, 128);
+      if (et == 0) red_release_add(p.barrier, 1u);
+      ++ebar;
+    };
+    auto grid_wait = [&]() {   // every CTA has made its ebar-th arrival
+      if (et == 0) {
+        while (ld_acquire_u32(p.barrier) < ebar * (unsigned)G) {
+        }
+      }
+      named_bar_sync(1, 128);
+    };
+
+    // ---- persistent per-thread state ----
+    const int rptA = p.NC_A * Bq / 128, rptB = p.NC_B * Bq / 128, upt = p.Uc * Bq / 128;
+    const int jA0 = cta * p.NC_A + sub * rptA, vB0 = cta * p.NC_B + sub * rptB, unit0 = cta * p.Uc + sub * upt;
+    float ppv[DT_MAX_RPT];
+    float hst[kMaxPredLayers][DT_MAX_RPT];
+    float gval[DT_MAX_RPT];
+#pragma unroll
+    for (int i = 0; i < DT_MAX_RPT; ++i) { ppv[i] = 0.f; gval[i] = 0.f; }
+#pragma unroll
+    for (int l = 0; l < kMaxPredLayers; ++l)
+#pragma unroll
+      for (int i = 0; i < DT_MAX_RPT; ++i)
+        hst[l][i] = (l < Lp && i < upt && bvalid)
+                        ? (p.use_state_in ? p.state_h[((size_t)l * B + b) * H + unit0 + i] : w.h0[l][unit0 + i]) : 0.f;
+    auto store_act = [&](uint8_t* img, int k0, int n, const float* v) {   // n consecutive k of batch row b
+#pragma unroll
+      for (int j0 = 0; j0 < DT_MAX_RPT; j0 += 4) {
+        if (j0 < n) {
+          const int k = k0 + j0;
+          uint8_t* hi = img + (size_t)((k >> 6) * 2) * xr;
+          store_split(hi, hi + xr, b, k & 63, (n - j0) < 4 ? (n - j0) : 4, v + j0);
+        }
+      }
+    };
+    int par = 0;
+    // initial operand images: h of every layer (and g when the caller supplied the state)
+    if (bvalid) {
+      for (int l = 0; l < Lp; ++l) store_act(p.h_img[l][0], unit0, upt, hst[l]);
+      if (p.use_state_in) {
+#pragma unroll
+        for (int i = 0; i < DT_MAX_RPT; ++i)
+          if (i < upt) gval[i] = p.pred_out[(size_t)b * H + unit0 + i];
+        store_act(p.g_img, unit0, upt, gval);
+      }
+    }
+    grid_arrive();
+
+    // ---- predictor layer l (GRU cell + BatchNorm), haste/nbrc.py:46-56 ----
+    auto predictor_phase = [&](int l) {
+      const int NC = p.NC_C;
+      drain((l > 0 ? 4 : 2) * NC);
+      const int gh = (l > 0) ? 2 * NC : 0;   // column base of the recurrent GEMM (after the input GEMM for l > 0)
+      float xo[DT_MAX_RPT];
+      if (bvalid) {
+        const bool em = c.emit[b] != 0;
+#pragma unroll
+        for (int i = 0; i < DT_MAX_RPT; ++i) {
+          if (i < upt) {
+            const int unit = unit0 + i, lr = (sub * upt + i) * 3;
+            if (em) {
+              float vx[3];
+              if (l == 0) {
+                const float* row = w.table0 + (size_t)c.tok[b] * (3 * H);
+                vx[0] = row[unit]; vx[1] = row[H + unit]; vx[2] = row[2 * H + unit];
+              } else {
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) vx[gg] = pre_val(0, NC, lr + gg) + w.kbias[l][unit * 3 + gg];
+              }
+              const float* rb = w.rbias[l] + unit * 3;
+              const float z = sigmoidf_acc(vx[0] + (pre_val(gh, NC, lr + 0) + rb[0]));
+              const float r = sigmoidf_acc(vx[1] + (pre_val(gh, NC, lr + 1) + rb[1]));
+              const float gg_ = tanhf(vx[2] + r * (pre_val(gh, NC, lr + 2) + rb[2]));
+              hst[l][i] = z * hst[l][i] + (1.0f - z) * gg_;
+            }
+            xo[i] = hst[l][i] * w.bn_scale[l][unit] + w.bn_shift[l][unit];
+          }
+        }
+        store_act(p.h_img[l][par ^ 1], unit0, upt, hst[l]);
+        if (l == Lp - 1) {
+#pragma unroll
+          for (int i = 0; i < DT_MAX_RPT; ++i) gval[i] = xo[i];
+          store_act(p.g_img, unit0, upt, xo);
+        } else {
+          store_act(p.x_img[l & 1], unit0, upt, xo);
+        }
+      }
+      grid_arrive();
+    };
+
+    if (!p.use_state_in) {   // feed BOS from the learnable initial state (models.py:397-398)
+      for (int l = 0; l < Lp; ++l) predictor_phase(l);
+      par ^= 1;
+    }
+
+    bool any_upd = true;
+    for (int step = 0;; ++step) {
+      // ---------------- phase A: pp and z ----------------
+      if (any_upd && in_A) drain(2 * p.NC_A);
+      if (in_A && bvalid) {
+        float zv[DT_MAX_RPT];
+        const bool act = c.active[b] != 0;
+        const float* epr = p.ep + ((size_t)b * T + (act ? c.t[b] : 0)) * J + jA0;
+#pragma unroll
+        for (int i = 0; i < DT_MAX_RPT; ++i) {
+          if (i < rptA) {
+            if (any_upd && c.emit[b]) ppv[i] = pre_val(0, p.NC_A, sub * rptA + i);
+            zv[i] = act ? tanhf(ppv[i] + epr[i]) : 0.f;
+          }
+        }
+        if (act) store_act(p.z_img, jA0, rptA, zv);
+      }
+      grid_arrive();
+
+      // ---------------- phase B: logits slice + softmax partials ----------------
+      if (in_B) {
+        drain(2 * p.NC_B);
+        float m = -INFINITY, s = 0.f;
+        int am = 0;
+        if (bvalid) {
+          float lv[DT_MAX_RPT];
+#pragma unroll
+          for (int i = 0; i < DT_MAX_RPT; ++i) {
+            if (i < rptB) {
+              const int v = vB0 + i;
+              lv[i] = (v < V) ? pre_val(0, p.NC_B, sub * rptB + i) + w.b2[v] : -INFINITY;
+              if (lv[i] > m) { m = lv[i]; am = v; }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < DT_MAX_RPT; ++i)
+            if (i < rptB && vB0 + i < V) s += expf(lv[i] - m);
+          if (p.trace && c.active[b] && c.n_eval[b] < p.trace_cap) {
+            float* tr = p.trace + ((size_t)b * p.trace_cap + c.n_eval[b]) * V + vB0;
+#pragma unroll
+            for (int i = 0; i < DT_MAX_RPT; ++i)
+              if (i < rptB && vB0 + i < V) tr[i] = lv[i];
+          }
+          c.red[sub][b][0] = m; c.red[sub][b][1] = __int_as_float(am); c.red[sub][b][2] = s;
+        }
+        named_bar_sync(1, 128);
+        if (bvalid && sub == 0) {
+          for (int k = 1; k < tpr; ++k) {   // ascending vocabulary order, strict > keeps the first maximum
+            const float m2 = c.red[k][b][0], s2 = c.red[k][b][2];
+            if (m2 > m) { s = s * expf(m - m2) + s2; m = m2; am = __float_as_int(c.red[k][b][1]); }
+            else s += s2 * expf(m2 - m);
+          }
+          *reinterpret_cast<float4*>(p.part + ((size_t)cta * Bq + b) * 4) = make_float4(m, __int_as_float(am), s, 0.f);
+        }
+      }
+      grid_arrive();
+      grid_wait();   // R reads the partials of every CTA
+
+      // ---------------- R: fold the partials; greedy rule (models.py:408-437) ----------------
+      {
+        const int nB = (V + p.NC_B - 1) / p.NC_B;   // CTAs that produced a partial, ascending vocabulary order
+        float M = -INFINITY, Ssum = 0.f;
+        int am = 0;
+        if (bvalid && c.active[b]) {
+          const int per = (nB + tpr - 1) / tpr;
+          const int lo = sub * per, hi = min(nB, lo + per);
+          for (int k = lo; k < hi; ++k) {
+            const float4 qv = __ldcg(reinterpret_cast<const float4*>(p.part + ((size_t)k * Bq + b) * 4));
+            if (qv.x > M) { Ssum = Ssum * expf(M - qv.x) + qv.z; M = qv.x; am = __float_as_int(qv.y); }
+            else Ssum += qv.z * expf(qv.x - M);
+          }
+          c.red[sub][b][0] = M; c.red[sub][b][1] = __int_as_float(am); c.red[sub][b][2] = Ssum;
+        }
+        named_bar_sync(1, 128);
+        if (et < B) {
+          const int bb = et;
+          unsigned char emit = 0;
+          if (c.active[bb]) {
+            float M2 = c.red[0][bb][0], S2 = c.red[0][bb][2];
+            int am2 = __float_as_int(c.red[0][bb][1]);
+            for (int k = 1; k < tpr; ++k) {
+              const float m2 = c.red[k][bb][0], s2 = c.red[k][bb][2];
+              if (m2 > M2) { S2 = S2 * expf(M2 - m2) + s2; M2 = m2; am2 = __float_as_int(c.red[k][bb][1]); }
+              else S2 += s2 * expf(m2 - M2);
+            }
+            const float lse = M2 + logf(S2);
+            const float prob = M2 - lse;
+            const int t = c.t[bb], ne = c.n_eval[bb];
+            if (cta == 0 && p.trace && ne < p.trace_cap) p.trace_lse[(size_t)bb * p.trace_cap + ne] = lse;
+            c.n_eval[bb] = ne + 1;
+            c.nlp[bb] += (double)prob;
+            const int it = c.it[bb] + 1;
+            bool advance;
+            if (am2 == w.blank) {
+              advance = true;
+            } else {
+              const int n = c.ntok[bb];
+              if (cta == 0 && n < p.U_cap) p.tokens[(size_t)bb * p.U_cap + n] = am2;
+              c.ntok[bb] = n + 1;
+              c.tok[bb] = am2;
+              emit = 1;
+              advance = it >= p.max_iters;
+            }
+            if (advance) {
+              if (cta == 0 && p.iters) p.iters[(size_t)bb * T + t] = (uint8_t)it;
+              c.t[bb] = t + 1;
+              c.it[bb] = 0;
+              if (t + 1 >= c.len[bb]) c.active[bb] = 0;
+            } else {
+              c.it[bb] = it;
+            }
+          }
+          c.emit[bb] = emit;
+        }
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          int ae = 0, aa = 0;
+          for (int i = 0; i < B; ++i) { ae |= c.emit[i]; aa |= c.active[i]; }
+          c.flags[0] = ae; c.flags[1] = aa;
+          mbar_arrive(ctlbar);
+        }
+        named_bar_sync(1, 128);
+      }
+      const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
+      if (any_emit) {
+        for (int l = 0; l < Lp; ++l) predictor_phase(l);
+        par ^= 1;
+      }
+      any_upd = any_emit;
+      if (!any_active) break;
+    }
+
+    // ---- results and state ----
+    if (cta == 0 && et < B) {
+      p.ntok[et] = c.ntok[et];
+      if (p.neg_logp) p.neg_logp[et] = -c.nlp[et];
+    }
+    if (bvalid) {
+      if (p.state_h)
+        for (int l = 0; l < Lp; ++l)
+#pragma unroll
+          for (int i = 0; i < DT_MAX_RPT; ++i)
+            if (i < upt) p.state_h[((size_t)l * B + b) * H + unit0 + i] = hst[l][i];
+      if (p.pred_out)
+#pragma unroll
+        for (int i = 0; i < DT_MAX_RPT; ++i)
+          if (i < upt) p.pred_out[(size_t)b * H + unit0 + i] = gval[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, p.tmem_cols);
+}
+
+// trace post-pass: raw logits -> log_softmax (separate tiny kernel: avoids one more grid-wide phase)
+__global__ void trace_normalize_kernel(float* trace, const float* lse, int B, int cap, int V) {
+  const size_t n = (size_t)B * cap * V;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    trace[i] -= lse[i / V];   // rows never evaluated hold 0 - 0
+}
+
+}  // namespace
+
+cudaError_t configure_decode_tc() {
+  return cudaFuncSetAttribute(decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+// weight-side plan (independent of the batch): slices per CTA
+bool decode_tc_wplan(int H, int J, int V, int sms, DecodeTcPlan* pl) {
+  if (H % 64 || J % 64) return false;
+  int Uc = 0;
+  for (int u : {8, 16, 32})
+    if (H % u == 0 && H / u <= sms) { Uc = u; break; }
+  if (!Uc) return false;
+  pl->Uc = Uc;
+  pl->G = H / Uc;
+  pl->NC_C = 3 * Uc;
+  pl->NC_A = (int)round_up(ceil_div(J, pl->G), 8);
+  pl->NC_B = (int)round_up(ceil_div(V, pl->G), 8);
+  pl->NC_max = std::max(pl->NC_C, std::max(pl->NC_A, pl->NC_B));
+  return 2 * pl->NC_max <= 256;
+}
+
+bool decode_tc_plan(int H, int J, int V, int B, int sms, DecodeTcPlan* pl) {
+  if (B < 1 || B > DT_MAXB) return false;
+  if (!decode_tc_wplan(H, J, V, sms, pl)) return false;
+  pl->Bpad8 = (int)round_up(B, 8);
+  pl->Bq = pl->Bpad8 <= 32 ? 32 : 64;
+  pl->mma_m = 2 * pl->Bpad8 <= 64 ? 64 : 128;
+  // rows per epilogue thread must be whole and small
+  for (int n : {pl->NC_A, pl->NC_B, pl->Uc}) {
+    if ((n * pl->Bq) % 128) return false;
+    if (n * pl->Bq / 128 > DT_MAX_RPT) return false;
+  }
+  int cols = 32;
+  while (cols < 4 * pl->NC_max) cols *= 2;
+  if (cols > 512) return false;
+  pl->tmem_cols = cols;
+  const size_t xkb = (size_t)2 * pl->Bpad8 * 128, wmax = (size_t)pl->NC_max * 256;
+  const size_t guard = (size_t)pl->mma_m * 128;
+  const size_t pre_bytes = round_up((size_t)2 * pl->Bq * (4 * pl->NC_max + 1) * 4, 1024);
+  const size_t ctl_bytes = round_up(sizeof(Ctrl), 1024);
+  const size_t budget = 227 * 1024 - 2048 - guard - pre_bytes - ctl_bytes;
+  for (int kps : {4, 2, 1}) {
+    const size_t stage = kps * (xkb + wmax);
+    int S = (int)(budget / stage);
+    if (S > 8) S = 8;
+    if (S < 3 && !(kps == 1 && S >= 2)) continue;
+    pl->kps = kps;
+    pl->stages = S;
+    const size_t used = (size_t)S * stage + guard;
+    pl->pre_offset = (int)round_up(used, 1024);
+    pl->ctl_offset = pl->pre_offset + (int)pre_bytes;
+    pl->bar_offset = pl->ctl_offset + (int)ctl_bytes;
+    pl->smem_bytes = pl->bar_offset + 1024 + 1024;
+    return pl->smem_bytes <= 227 * 1024;
+  }
+  return false;
+}
+
+cudaError_t launch_decode_tc(const DecodeTcArgs& a, const DecodeTcPlan& pl, cudaStream_t st) {
+  DecodeTcArgs args = a;
+  args.Uc = pl.Uc; args.NC_A = pl.NC_A; args.NC_B = pl.NC_B; args.NC_C = pl.NC_C; args.NC_max = pl.NC_max;
+  args.Bpad8 = pl.Bpad8; args.Bq = pl.Bq; args.mma_m = pl.mma_m; args.kps = pl.kps; args.stages = pl.stages;
+  args.pre_offset = pl.pre_offset; args.ctl_offset = pl.ctl_offset; args.bar_offset = pl.bar_offset; args.tmem_cols = pl.tmem_cols;
+  void* kargs[] = {&args};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)decode_tc_kernel, dim3(pl.G), dim3(DT_THREADS), kargs, pl.smem_bytes, st);
+  if (e != cudaSuccess) return e;
+  if (a.trace) {
+    trace_normalize_kernel<<<148, 256, 0, st>>>(a.trace, a.trace_lse, a.B, a.trace_cap, a.w.V);
+    return cudaGetLastError();
+  }
+  return cudaSuccess;
+}
+
+}  // namespace rnnt

@@ -141,6 +141,34 @@ size_t decode_smem_bytes();
 cudaError_t configure_decode(int device, int* max_coop_blocks);
 cudaError_t launch_decode(const DecodeArgs& a, int grid_blocks, cudaStream_t st);
 
+// ---------------- decode_tc.cu (tcgen05 greedy decode) ----------------
+struct DecodeTcPlan {
+  int G, Uc, NC_A, NC_B, NC_C, NC_max;                 // weight-side plan (batch independent)
+  int Bpad8, Bq, mma_m, kps, stages, pre_offset, ctl_offset, bar_offset, smem_bytes, tmem_cols;
+};
+struct DecodeTcArgs {
+  DecodeWeights w;                 // fp32 vectors / tables (table0, biases, h0, BatchNorm, b2)
+  const uint8_t* w1p_img;          // operand images of the weight slices (TR = NC_A / NC_B / NC_C rows per CTA)
+  const uint8_t* w2_img;
+  const uint8_t* r_img[kMaxPredLayers];
+  const uint8_t* k_img[kMaxPredLayers];
+  const float* ep;                 // [B][T][J] encoder half of the joint incl. b1
+  const int32_t* lens_T;
+  int B, T, max_iters, use_state_in;
+  uint8_t* g_img; uint8_t* z_img; uint8_t* x_img[2]; uint8_t* h_img[kMaxPredLayers][2];   // activation images (TR = Bpad8)
+  float* part;                     // [G][Bq][4] softmax partials
+  float* trace_lse;
+  float* state_h; float* pred_out; // [Lp][B][H], [B][H] in/out (nullable unless use_state_in)
+  int32_t* tokens; int U_cap; int32_t* ntok; double* neg_logp; uint8_t* iters; float* trace; int trace_cap;
+  unsigned int* barrier;           // grid phase counter, zero at launch
+  // filled from the plan by the launcher
+  int Uc, NC_A, NC_B, NC_C, NC_max, Bpad8, Bq, mma_m, kps, stages, pre_offset, ctl_offset, bar_offset, tmem_cols;
+};
+cudaError_t configure_decode_tc();
+bool decode_tc_wplan(int H, int J, int V, int sms, DecodeTcPlan* pl);
+bool decode_tc_plan(int H, int J, int V, int B, int sms, DecodeTcPlan* pl);
+cudaError_t launch_decode_tc(const DecodeTcArgs& a, const DecodeTcPlan& pl, cudaStream_t st);
+
 // standalone predictor step / joint (same phase code, one launch per phase)
 struct PredictArgs {
   DecodeWeights w;
