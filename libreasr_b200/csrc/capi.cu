@@ -214,7 +214,7 @@ int32_t rnnt_b200_default_config(rnnt_b200_config* c) {
   c->sample_rate = 16000; c->n_fft = 1024; c->win_length = 400; c->hop_length = 160;
   c->n_mels = 128; c->n_stack = 10; c->downsample = 8;
   c->enc_layers = 6; c->pred_layers = 2; c->hidden_sz = 1024; c->embed_sz = 512; c->joint_sz = 1024; c->vocab_sz = 2048;
-  c->blank = 0; c->bos = 2; c->device = 0; c->gemm_mode = RNNT_B200_GEMM_FP32_SIMT;
+  c->blank = 0; c->bos = 2; c->device = 0; c->gemm_mode = RNNT_B200_GEMM_TC_FP16X3;
   c->log_offset = 1e-6f; c->ln_eps = 1e-5f; c->bn_eps = 1e-5f;
   return RNNT_B200_OK;
 }

@@ -33,7 +33,7 @@ class EngineConfig:
     n_fft: int = 1024
     win_length: int = 400
     hop_length: int = 160
-    gemm_mode: int = _capi.GEMM_FP32_SIMT
+    gemm_mode: int = _capi.GEMM_TC_FP16X3
     log_offset: float = 1e-6
     ln_eps: float = 1e-5
     bn_eps: float = 1e-5

@@ -146,7 +146,7 @@ class Transducer(nn.Module):
 
     def __init__(self, feature_sz, embed_sz, vocab_sz, hidden_sz, out_sz, joint_sz, lang, l_e=6, l_p=2, p_j=0.0,
                  blank=0, joint_method="concat", perf=False, act=None, use_tmp_bos=True, use_tmp_bos_pcent=0.99,
-                 encoder_kwargs={}, predictor_kwargs={}, n_stack=10, downsample=8, gemm_mode=0, **kwargs):
+                 encoder_kwargs={}, predictor_kwargs={}, n_stack=10, downsample=8, gemm_mode=1, **kwargs):
         super().__init__()
         import weakref
 
@@ -180,7 +180,7 @@ class Transducer(nn.Module):
             conf["model"]["hidden_sz"], conf["model"]["out_sz"], conf["model"]["joint_sz"], lang,
             p_j=conf["model"]["joint"].get("dropout", 0.0), joint_method=conf["model"]["joint"]["method"],
             encoder_kwargs=conf["model"]["encoder"], predictor_kwargs=conf["model"]["predictor"],
-            n_stack=ecfg.n_stack, downsample=ecfg.downsample, gemm_mode=conf.get("gemm_mode", 0),
+            n_stack=ecfg.n_stack, downsample=ecfg.downsample, gemm_mode=conf.get("gemm_mode", 1),
         ).to(conf["cuda"]["device"])
         m.mp = conf.get("mp", False)
         return m

@@ -18,7 +18,7 @@ from oracle import weights
 
 pytestmark = pytest.mark.gpu
 CHUNK = 1280
-GEMM_MODE = int(os.environ.get("RNNT_GEMM_MODE", "0"))  # 0 = fp32 CUDA cores, 1 = tcgen05 3xFP16
+GEMM_MODE = int(os.environ.get("RNNT_GEMM_MODE", "1"))  # 0 = fp32 CUDA cores, 1 = tcgen05 3xFP16
 
 
 class Lang:

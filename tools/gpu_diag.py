@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--config", nargs="+", default=["tiny"])
     ap.add_argument("--seconds", type=float, default=3.0)
     ap.add_argument("--utts", type=int, default=3)
-    ap.add_argument("--gemm-mode", type=int, default=0)
+    ap.add_argument("--gemm-mode", type=int, default=1)
     args = ap.parse_args()
     print("device:", torch.cuda.get_device_name(0), flush=True)
     results = {}
