@@ -182,8 +182,8 @@ def main():
         "tiny_offline": lambda: offline_fixture("tiny", n_utt=3, n_samples=40000, audio_seed=21, full=True),
         "tiny_stream": lambda: stream_fixture("tiny", n_chunks=40, audio_seed=22),
         "tiny_modules": lambda: modules_fixture("tiny"),
-        "cfg2_offline": lambda: offline_fixture("cfg2", n_utt=2, n_samples=80000, audio_seed=23),
-        "cfg2_stream": lambda: stream_fixture("cfg2", n_chunks=50, audio_seed=24),
+        "cfg2_offline": lambda: offline_fixture("cfg2", n_utt=2, n_samples=80000, audio_seed=105),
+        "cfg2_stream": lambda: stream_fixture("cfg2", n_chunks=50, audio_seed=47),
         "ref_offline": lambda: offline_fixture("ref", n_utt=1, n_samples=48000, audio_seed=25),
         "cfg4_offline": lambda: offline_fixture("cfg4", n_utt=1, n_samples=32000, audio_seed=26),
     }
