@@ -857,7 +857,29 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     t.tokens = tokens_out; t.U_cap = U_cap; t.ntok = ntok_out; t.neg_logp = neg_logp_out; t.iters = iters_out;
     t.trace = trace_logp; t.trace_cap = trace_logp ? trace_cap : 0;
     t.barrier = h->gbar.as<unsigned int>();
+    static const bool ddbg = getenv("RNNT_DEC_DBG") != nullptr;
+    unsigned long long* dbg = nullptr;
+    const int dcap = 8192;
+    if (ddbg) {
+      CK(cudaMalloc((void**)&dbg, (size_t)dcap * 16));
+      CK(cudaMemset(dbg, 0, (size_t)dcap * 16));
+      t.dbg = dbg; t.dbg_cap = dcap;
+    }
     LAUNCH(trace_logp ? 2 : 1, launch_decode_tc(t, dpl, st));
+    if (dbg) {
+      std::vector<unsigned long long> hb((size_t)dcap * 2);
+      CK(cudaStreamSynchronize(st));
+      CK(cudaMemcpy(hb.data(), dbg, (size_t)dcap * 16, cudaMemcpyDeviceToHost));
+      cudaFree(dbg);
+      double sum[8] = {0}; int cnt[8] = {0}; int n = 0;
+      for (int i = 1; i < dcap && hb[2 * i]; ++i, ++n) {
+        const int tag = (int)hb[2 * i + 1];
+        if (tag < 8) { sum[tag] += (double)(hb[2 * i] - hb[2 * i - 2]); cnt[tag]++; }
+      }
+      fprintf(stderr, "[decode_tc dbg] B=%d stamps=%d avg ns per segment: A(pp+z)->arrive %.0f (n=%d) | B(logits)->arrive %.0f (n=%d) | grid wait %.0f | R %.0f | gru0 %.0f (n=%d) | gru1 %.0f\n",
+              B, n, cnt[0] ? sum[0] / cnt[0] : 0, cnt[0], cnt[1] ? sum[1] / cnt[1] : 0, cnt[1], cnt[2] ? sum[2] / cnt[2] : 0,
+              cnt[3] ? sum[3] / cnt[3] : 0, cnt[4] ? sum[4] / cnt[4] : 0, cnt[4], cnt[5] ? sum[5] / cnt[5] : 0);
+    }
     if (h->ev) cudaEventRecord(h->ev[4], st);
     return RNNT_B200_OK;
   }

@@ -38,6 +38,11 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -303,6 +308,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
       return (ph[rr] + kLoInv * ph[NC + rr]) + (pl[rr] + kLoInv * pl[NC + rr]);
     };
     unsigned ebar = 0;   // grid arrivals so far (same count in every CTA)
+    int ndbg = 0;
+    auto stamp = [&](int tag) {   // tuning aid: (time, tag) trail of CTA 0
+      if (p.dbg && cta == 0 && et == 0 && ndbg < p.dbg_cap) { p.dbg[2 * ndbg] = gtimer(); p.dbg[2 * ndbg + 1] = (unsigned long long)tag; ++ndbg; }
+    };
     auto grid_arrive = [&]() {
       named_bar_sync(1, 128);
       if (et == 0) red_release_add(p.barrier, 1u);
@@ -418,6 +427,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
         if (act) store_act(p.z_img, jA0, rptA, zv);
       }
       grid_arrive();
+      stamp(0);
 
       // ---------------- phase B: logits slice + softmax partials ----------------
       if (in_B) {
@@ -456,7 +466,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
         }
       }
       grid_arrive();
+      stamp(1);
       grid_wait();   // R reads the partials of every CTA
+      stamp(2);
 
       // ---------------- R: fold the partials; greedy rule (models.py:408-437) ----------------
       {
@@ -524,8 +536,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
         named_bar_sync(1, 128);
       }
       const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
+      stamp(3);
       if (any_emit) {
-        for (int l = 0; l < Lp; ++l) predictor_phase(l);
+        for (int l = 0; l < Lp; ++l) { predictor_phase(l); stamp(4 + l); }
         par ^= 1;
       }
       any_upd = any_emit;

@@ -161,6 +161,7 @@ struct DecodeTcArgs {
   float* state_h; float* pred_out; // [Lp][B][H], [B][H] in/out (nullable unless use_state_in)
   int32_t* tokens; int U_cap; int32_t* ntok; double* neg_logp; uint8_t* iters; float* trace; int trace_cap;
   unsigned int* barrier;           // grid phase counter, zero at launch
+  unsigned long long* dbg; int dbg_cap;   // optional (time, tag) trail of CTA 0 (tuning aid)
   // filled from the plan by the launcher
   int Uc, NC_A, NC_B, NC_C, NC_max, Bpad8, Bq, mma_m, kps, stages, pre_offset, ctl_offset, bar_offset, tmem_cols;
 };
