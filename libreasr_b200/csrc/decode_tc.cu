@@ -103,7 +103,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
   uint64_t* tfull = empty + S;
   uint64_t* tempty = tfull + 1;
   uint64_t* ctlbar = tempty + 1;
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(ctlbar + 1);
+  uint64_t* pfull = ctlbar + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(pfull + 1);
+  const float* pbuf = p.pbuf_offset >= 0 ? reinterpret_cast<const float*>(base + p.pbuf_offset) : nullptr;
+  const int nB = (V + p.NC_B - 1) / p.NC_B;                     // CTAs that produce a softmax partial
+  const uint32_t part_bytes = (uint32_t)nB * Bq * 16;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -113,6 +117,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     mbar_init(tfull, 1);
     mbar_init(tempty, 128);
     mbar_init(ctlbar, 1);
+    mbar_init(pfull, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tptr, p.tmem_cols);
@@ -186,6 +191,16 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     for (int step = 0;; ++step) {
       if (any_upd) run_phase(0, par); else ++nbar;
       run_phase(1, par);
+      if (pbuf) {   // R: the softmax partials of every CTA, one TMA bulk copy into shared memory
+        while (ld_acquire_u32(p.barrier) < nbar * (unsigned)G) {
+        }
+        fence_proxy_async_global();
+        if (elect_one()) {
+          mbar_arrive_expect_tx(pfull, part_bytes);
+          tma_bulk_g2s(const_cast<float*>(pbuf), p.part, part_bytes, pfull);
+        }
+        __syncwarp();
+      }
       mbar_wait(ctlbar, step & 1);
       const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
       if (any_emit) {
@@ -365,25 +380,39 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     // ---- predictor layer l (GRU cell + BatchNorm), haste/nbrc.py:46-56 ----
     auto predictor_phase = [&](int l) {
       const int NC = p.NC_C;
+      // operands that do not depend on the accumulators are fetched before they are awaited
+      const bool em = bvalid && c.emit[b] != 0;
+      float vxin[DT_MAX_RPT][3], rbv[DT_MAX_RPT][3];
+      if (em) {
+#pragma unroll
+        for (int i = 0; i < DT_MAX_RPT; ++i) {
+          if (i < upt) {
+            const int unit = unit0 + i;
+            if (l == 0) {   // Embedding -> Linear -> kernel_0 folded into a [V][3H] table (models.py:182-183)
+              const float* row = w.table0 + (size_t)c.tok[b] * (3 * H);
+              vxin[i][0] = row[unit]; vxin[i][1] = row[H + unit]; vxin[i][2] = row[2 * H + unit];
+            } else {
+#pragma unroll
+              for (int gg = 0; gg < 3; ++gg) vxin[i][gg] = w.kbias[l][unit * 3 + gg];
+            }
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg) rbv[i][gg] = w.rbias[l][unit * 3 + gg];
+          }
+        }
+      }
       drain((l > 0 ? 4 : 2) * NC);
       const int gh = (l > 0) ? 2 * NC : 0;   // column base of the recurrent GEMM (after the input GEMM for l > 0)
       float xo[DT_MAX_RPT];
       if (bvalid) {
-        const bool em = c.emit[b] != 0;
 #pragma unroll
         for (int i = 0; i < DT_MAX_RPT; ++i) {
           if (i < upt) {
             const int unit = unit0 + i, lr = (sub * upt + i) * 3;
             if (em) {
               float vx[3];
-              if (l == 0) {
-                const float* row = w.table0 + (size_t)c.tok[b] * (3 * H);
-                vx[0] = row[unit]; vx[1] = row[H + unit]; vx[2] = row[2 * H + unit];
-              } else {
 #pragma unroll
-                for (int gg = 0; gg < 3; ++gg) vx[gg] = pre_val(0, NC, lr + gg) + w.kbias[l][unit * 3 + gg];
-              }
-              const float* rb = w.rbias[l] + unit * 3;
+              for (int gg = 0; gg < 3; ++gg) vx[gg] = (l == 0) ? vxin[i][gg] : pre_val(0, NC, lr + gg) + vxin[i][gg];
+              const float* rb = rbv[i];
               const float z = sigmoidf_acc(vx[0] + (pre_val(gh, NC, lr + 0) + rb[0]));
               const float r = sigmoidf_acc(vx[1] + (pre_val(gh, NC, lr + 1) + rb[1]));
               const float gg_ = tanhf(vx[2] + r * (pre_val(gh, NC, lr + 2) + rb[2]));
@@ -412,16 +441,23 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     bool any_upd = true;
     for (int step = 0;; ++step) {
       // ---------------- phase A: pp and z ----------------
+      float epv[DT_MAX_RPT];
+      const bool actA = in_A && bvalid && c.active[b] != 0;
+      if (actA) {   // issued before the accumulators are awaited
+        const float* epr = p.ep + ((size_t)b * T + c.t[b]) * J + jA0;
+#pragma unroll
+        for (int i = 0; i < DT_MAX_RPT; ++i)
+          if (i < rptA) epv[i] = epr[i];
+      }
       if (any_upd && in_A) drain(2 * p.NC_A);
       if (in_A && bvalid) {
         float zv[DT_MAX_RPT];
-        const bool act = c.active[b] != 0;
-        const float* epr = p.ep + ((size_t)b * T + (act ? c.t[b] : 0)) * J + jA0;
+        const bool act = actA;
 #pragma unroll
         for (int i = 0; i < DT_MAX_RPT; ++i) {
           if (i < rptA) {
             if (any_upd && c.emit[b]) ppv[i] = pre_val(0, p.NC_A, sub * rptA + i);
-            zv[i] = act ? tanhf(ppv[i] + epr[i]) : 0.f;
+            zv[i] = act ? tanhf(ppv[i] + epv[i]) : 0.f;
           }
         }
         if (act) store_act(p.z_img, jA0, rptA, zv);
@@ -467,19 +503,20 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
       }
       grid_arrive();
       stamp(1);
-      grid_wait();   // R reads the partials of every CTA
+      if (pbuf) mbar_wait(pfull, step & 1);   // the producer pulled every CTA's partials into smem after the barrier
+      else grid_wait();
       stamp(2);
 
       // ---------------- R: fold the partials; greedy rule (models.py:408-437) ----------------
       {
-        const int nB = (V + p.NC_B - 1) / p.NC_B;   // CTAs that produced a partial, ascending vocabulary order
-        float M = -INFINITY, Ssum = 0.f;
+        float M = -INFINITY, Ssum = 0.f;   // partials are folded in ascending vocabulary order
         int am = 0;
         if (bvalid && c.active[b]) {
           const int per = (nB + tpr - 1) / tpr;
           const int lo = sub * per, hi = min(nB, lo + per);
           for (int k = lo; k < hi; ++k) {
-            const float4 qv = __ldcg(reinterpret_cast<const float4*>(p.part + ((size_t)k * Bq + b) * 4));
+            const float4 qv = pbuf ? *reinterpret_cast<const float4*>(pbuf + ((size_t)k * Bq + b) * 4)
+                                   : __ldcg(reinterpret_cast<const float4*>(p.part + ((size_t)k * Bq + b) * 4));
             if (qv.x > M) { Ssum = Ssum * expf(M - qv.x) + qv.z; M = qv.x; am = __float_as_int(qv.y); }
             else Ssum += qv.z * expf(qv.x - M);
           }
@@ -615,7 +652,11 @@ bool decode_tc_plan(int H, int J, int V, int B, int sms, DecodeTcPlan* pl) {
   const size_t guard = (size_t)pl->mma_m * 128;
   const size_t pre_bytes = round_up((size_t)2 * pl->Bq * (4 * pl->NC_max + 1) * 4, 1024);
   const size_t ctl_bytes = round_up(sizeof(Ctrl), 1024);
-  const size_t budget = 227 * 1024 - 2048 - guard - pre_bytes - ctl_bytes;
+  const size_t part_bytes = round_up((size_t)ceil_div(V, pl->NC_B) * pl->Bq * 16, 1024);
+  size_t budget = 227 * 1024 - 2048 - guard - pre_bytes - ctl_bytes;
+  // keep a shared-memory landing buffer for the softmax partials when 2+ pipeline stages still fit
+  const bool with_pbuf = budget >= part_bytes + 2 * (xkb + wmax) + 16384;
+  if (with_pbuf) budget -= part_bytes;
   for (int kps : {4, 2, 1}) {
     const size_t stage = kps * (xkb + wmax);
     int S = (int)(budget / stage);
@@ -626,7 +667,8 @@ bool decode_tc_plan(int H, int J, int V, int B, int sms, DecodeTcPlan* pl) {
     const size_t used = (size_t)S * stage + guard;
     pl->pre_offset = (int)round_up(used, 1024);
     pl->ctl_offset = pl->pre_offset + (int)pre_bytes;
-    pl->bar_offset = pl->ctl_offset + (int)ctl_bytes;
+    pl->pbuf_offset = with_pbuf ? pl->ctl_offset + (int)ctl_bytes : -1;
+    pl->bar_offset = pl->ctl_offset + (int)ctl_bytes + (with_pbuf ? (int)part_bytes : 0);
     pl->smem_bytes = pl->bar_offset + 1024 + 1024;
     return pl->smem_bytes <= 227 * 1024;
   }
@@ -638,6 +680,7 @@ cudaError_t launch_decode_tc(const DecodeTcArgs& a, const DecodeTcPlan& pl, cuda
   args.Uc = pl.Uc; args.NC_A = pl.NC_A; args.NC_B = pl.NC_B; args.NC_C = pl.NC_C; args.NC_max = pl.NC_max;
   args.Bpad8 = pl.Bpad8; args.Bq = pl.Bq; args.mma_m = pl.mma_m; args.kps = pl.kps; args.stages = pl.stages;
   args.pre_offset = pl.pre_offset; args.ctl_offset = pl.ctl_offset; args.bar_offset = pl.bar_offset; args.tmem_cols = pl.tmem_cols;
+  args.pbuf_offset = pl.pbuf_offset;
   void* kargs[] = {&args};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)decode_tc_kernel, dim3(pl.G), dim3(DT_THREADS), kargs, pl.smem_bytes, st);
   if (e != cudaSuccess) return e;
