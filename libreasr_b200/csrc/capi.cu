@@ -75,6 +75,7 @@ struct rnnt_b200_handle_s {
   uint8_t* R_img[kMaxPredLayers] = {nullptr, nullptr, nullptr, nullptr};
   uint8_t* K_img[kMaxPredLayers] = {nullptr, nullptr, nullptr, nullptr};
   DevBuf dimg;                         // decode activation operand images
+  DevBuf dkeys;                        // decode arg-max keys + evaluation counts
   DevBuf x_img[2], gbar;               // TC modes: h operand images (ping-pong), grid step counter
   DevBuf a_img;                        // TC modes: activation operand image (workspace)
   // workspaces
@@ -258,7 +259,7 @@ int32_t rnnt_b200_destroy(rnnt_b200_handle h) {
   for (void* p : h->weight_allocs) cudaFree(p);
   DevBuf* bufs[] = {&h->feats, &h->lnx, &h->xp, &h->ya, &h->yb, &h->ep, &h->ehT[0], &h->ehT[1], &h->ecT, &h->dhT, &h->dxT,
                     &h->dgT, &h->deT, &h->dppT, &h->dzT, &h->dpart, &h->dlse, &h->t_audio, &h->t_lens, &h->t_tokens,
-                    &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc, &h->a_img, &h->x_img[0], &h->x_img[1], &h->gbar, &h->dimg};
+                    &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc, &h->a_img, &h->x_img[0], &h->x_img[1], &h->gbar, &h->dimg, &h->dkeys};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t* set : h->evsets) {
     for (int i = 0; i < 6; ++i) cudaEventDestroy(set[i]);
@@ -833,7 +834,12 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     const size_t one = (size_t)(std::max(H, J) / 64) * 2 * dpl.Bpad8 * 128;
     const int nimg = 4 + 2 * c.pred_layers;
     CK(h->dimg.ensure(one * nimg));
-    CK(h->dpart.ensure((size_t)dpl.G * dpl.Bq * 16));
+    const int max_steps = max_iters * T + 2;
+    const int nBp = (int)ceil_div(c.vocab_sz, dpl.NC_B);
+    CK(h->dpart.ensure((size_t)max_steps * nBp * dpl.Bq * 8));
+    CK(h->dkeys.ensure((size_t)max_steps * dpl.Bq * 8 + (size_t)B * 4 + 64));
+    CK(cudaMemsetAsync(h->dkeys.p, 0, (size_t)max_steps * dpl.Bq * 8, st));
+    CK(h->dlse.ensure(std::max<size_t>((size_t)B * (trace_logp ? trace_cap : 1), 1) * 4));
     CK(h->gbar.ensure(64));
     CK(cudaMemsetAsync(h->gbar.p, 0, 4, st));
     if (trace_logp) {
@@ -853,6 +859,9 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     }
     t.ep = h->ep.as<float>(); t.lens_T = lens_T; t.B = B; t.T = T; t.max_iters = max_iters; t.use_state_in = use_state_in;
     t.part = h->dpart.as<float>(); t.trace_lse = h->dlse.as<float>();
+    t.keys = h->dkeys.as<unsigned long long>();
+    t.n_eval = reinterpret_cast<int*>(h->dkeys.as<uint8_t>() + (size_t)max_steps * dpl.Bq * 8);
+    t.max_steps = max_steps;
     t.state_h = pred_state_h; t.pred_out = pred_out;
     t.tokens = tokens_out; t.U_cap = U_cap; t.ntok = ntok_out; t.neg_logp = neg_logp_out; t.iters = iters_out;
     t.trace = trace_logp; t.trace_cap = trace_logp ? trace_cap : 0;
@@ -865,7 +874,7 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
       CK(cudaMemset(dbg, 0, (size_t)dcap * 16));
       t.dbg = dbg; t.dbg_cap = dcap;
     }
-    LAUNCH(trace_logp ? 2 : 1, launch_decode_tc(t, dpl, st));
+    LAUNCH(trace_logp ? 3 : 2, launch_decode_tc(t, dpl, st));
     if (dbg) {
       std::vector<unsigned long long> hb((size_t)dcap * 2);
       CK(cudaStreamSynchronize(st));

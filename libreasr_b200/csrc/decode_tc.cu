@@ -103,11 +103,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
   uint64_t* tfull = empty + S;
   uint64_t* tempty = tfull + 1;
   uint64_t* ctlbar = tempty + 1;
-  uint64_t* pfull = ctlbar + 1;
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(pfull + 1);
-  const float* pbuf = p.pbuf_offset >= 0 ? reinterpret_cast<const float*>(base + p.pbuf_offset) : nullptr;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(ctlbar + 1);
   const int nB = (V + p.NC_B - 1) / p.NC_B;                     // CTAs that produce a softmax partial
-  const uint32_t part_bytes = (uint32_t)nB * Bq * 16;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -117,7 +114,6 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     mbar_init(tfull, 1);
     mbar_init(tempty, 128);
     mbar_init(ctlbar, 1);
-    mbar_init(pfull, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tptr, p.tmem_cols);
@@ -191,16 +187,6 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     for (int step = 0;; ++step) {
       if (any_upd) run_phase(0, par); else ++nbar;
       run_phase(1, par);
-      if (pbuf) {   // R: the softmax partials of every CTA, one TMA bulk copy into shared memory
-        while (ld_acquire_u32(p.barrier) < nbar * (unsigned)G) {
-        }
-        fence_proxy_async_global();
-        if (elect_one()) {
-          mbar_arrive_expect_tx(pfull, part_bytes);
-          tma_bulk_g2s(const_cast<float*>(pbuf), p.part, part_bytes, pfull);
-        }
-        __syncwarp();
-      }
       mbar_wait(ctlbar, step & 1);
       const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
       if (any_emit) {
@@ -498,48 +484,32 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
             if (m2 > m) { s = s * expf(m - m2) + s2; m = m2; am = __float_as_int(c.red[k][b][1]); }
             else s += s2 * expf(m2 - m);
           }
-          *reinterpret_cast<float4*>(p.part + ((size_t)cta * Bq + b) * 4) = make_float4(m, __int_as_float(am), s, 0.f);
+          // (max, sum exp) of this CTA's slice goes to the per-step log (log-probabilities are finished by a
+          // post-pass, off the critical path); the arg max -- all the control flow needs -- is one 64-bit
+          // atomicMax on a packed (orderable logit, ~index) key: lowest index wins ties like torch.max
+          if (c.active[b] && step < p.max_steps) {
+            *reinterpret_cast<float2*>(p.part + (((size_t)step * nB + cta) * Bq + b) * 2) = make_float2(m, s);
+            unsigned u = __float_as_uint(m);
+            u ^= (u & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u;
+            atomicMax(p.keys + (size_t)step * Bq + b, ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)am));
+          }
         }
       }
       grid_arrive();
       stamp(1);
-      if (pbuf) mbar_wait(pfull, step & 1);   // the producer pulled every CTA's partials into smem after the barrier
-      else grid_wait();
+      grid_wait();   // every CTA's atomicMax has landed
       stamp(2);
 
-      // ---------------- R: fold the partials; greedy rule (models.py:408-437) ----------------
+      // ---------------- R: greedy rule (models.py:408-437), identical in every CTA ----------------
       {
-        float M = -INFINITY, Ssum = 0.f;   // partials are folded in ascending vocabulary order
-        int am = 0;
-        if (bvalid && c.active[b]) {
-          const int per = (nB + tpr - 1) / tpr;
-          const int lo = sub * per, hi = min(nB, lo + per);
-          for (int k = lo; k < hi; ++k) {
-            const float4 qv = pbuf ? *reinterpret_cast<const float4*>(pbuf + ((size_t)k * Bq + b) * 4)
-                                   : __ldcg(reinterpret_cast<const float4*>(p.part + ((size_t)k * Bq + b) * 4));
-            if (qv.x > M) { Ssum = Ssum * expf(M - qv.x) + qv.z; M = qv.x; am = __float_as_int(qv.y); }
-            else Ssum += qv.z * expf(qv.x - M);
-          }
-          c.red[sub][b][0] = M; c.red[sub][b][1] = __int_as_float(am); c.red[sub][b][2] = Ssum;
-        }
-        named_bar_sync(1, 128);
         if (et < B) {
           const int bb = et;
           unsigned char emit = 0;
           if (c.active[bb]) {
-            float M2 = c.red[0][bb][0], S2 = c.red[0][bb][2];
-            int am2 = __float_as_int(c.red[0][bb][1]);
-            for (int k = 1; k < tpr; ++k) {
-              const float m2 = c.red[k][bb][0], s2 = c.red[k][bb][2];
-              if (m2 > M2) { S2 = S2 * expf(M2 - m2) + s2; M2 = m2; am2 = __float_as_int(c.red[k][bb][1]); }
-              else S2 += s2 * expf(m2 - M2);
-            }
-            const float lse = M2 + logf(S2);
-            const float prob = M2 - lse;
-            const int t = c.t[bb], ne = c.n_eval[bb];
-            if (cta == 0 && p.trace && ne < p.trace_cap) p.trace_lse[(size_t)bb * p.trace_cap + ne] = lse;
-            c.n_eval[bb] = ne + 1;
-            c.nlp[bb] += (double)prob;
+            const unsigned long long key = __ldcg(p.keys + (size_t)min(step, p.max_steps - 1) * Bq + bb);
+            const int am2 = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+            const int t = c.t[bb];
+            c.n_eval[bb] += 1;
             const int it = c.it[bb] + 1;
             bool advance;
             if (am2 == w.blank) {
@@ -585,7 +555,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     // ---- results and state ----
     if (cta == 0 && et < B) {
       p.ntok[et] = c.ntok[et];
-      if (p.neg_logp) p.neg_logp[et] = -c.nlp[et];
+      p.n_eval[et] = c.n_eval[et];
     }
     if (bvalid) {
       if (p.state_h)
@@ -604,7 +574,36 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
   if (warp == 1) tmem_dealloc(tmem, p.tmem_cols);
 }
 
-// trace post-pass: raw logits -> log_softmax (separate tiny kernel: avoids one more grid-wide phase)
+// Post-pass, off the decode loop's critical path: fold the per-step softmax partials into the
+// log-sum-exp of every evaluation (ascending vocabulary order, as the fp32 kernel does), accumulate
+// -sum(log p(arg max)) per utterance (models.py:422,455) and turn the traced raw logits into log_softmax rows.
+__global__ void __launch_bounds__(256) decode_finish_kernel(const float* __restrict__ part, const int* __restrict__ n_eval,
+                                                            int nB, int Bq, int max_steps, double* __restrict__ neg_logp,
+                                                            float* __restrict__ lse_out, int lse_cap) {
+  const int b = blockIdx.x;
+  const int ne = min(n_eval[b], max_steps);
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+    float M = -INFINITY, S = 0.f;
+    for (int k = 0; k < nB; ++k) {
+      const float2 q = *reinterpret_cast<const float2*>(part + (((size_t)e * nB + k) * Bq + b) * 2);
+      if (q.x > M) { S = S * expf(M - q.x) + q.y; M = q.x; }
+      else S += q.y * expf(q.x - M);
+    }
+    const float lse = M + logf(S);
+    acc += (double)(M - lse);
+    if (lse_out && e < lse_cap) lse_out[(size_t)b * lse_cap + e] = lse;
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && neg_logp) neg_logp[b] = -red[0];
+}
+
 __global__ void trace_normalize_kernel(float* trace, const float* lse, int B, int cap, int V) {
   const size_t n = (size_t)B * cap * V;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -652,11 +651,7 @@ bool decode_tc_plan(int H, int J, int V, int B, int sms, DecodeTcPlan* pl) {
   const size_t guard = (size_t)pl->mma_m * 128;
   const size_t pre_bytes = round_up((size_t)2 * pl->Bq * (4 * pl->NC_max + 1) * 4, 1024);
   const size_t ctl_bytes = round_up(sizeof(Ctrl), 1024);
-  const size_t part_bytes = round_up((size_t)ceil_div(V, pl->NC_B) * pl->Bq * 16, 1024);
-  size_t budget = 227 * 1024 - 2048 - guard - pre_bytes - ctl_bytes;
-  // keep a shared-memory landing buffer for the softmax partials when 2+ pipeline stages still fit
-  const bool with_pbuf = budget >= part_bytes + 2 * (xkb + wmax) + 16384;
-  if (with_pbuf) budget -= part_bytes;
+  const size_t budget = 227 * 1024 - 2048 - guard - pre_bytes - ctl_bytes;
   for (int kps : {4, 2, 1}) {
     const size_t stage = kps * (xkb + wmax);
     int S = (int)(budget / stage);
@@ -667,8 +662,7 @@ bool decode_tc_plan(int H, int J, int V, int B, int sms, DecodeTcPlan* pl) {
     const size_t used = (size_t)S * stage + guard;
     pl->pre_offset = (int)round_up(used, 1024);
     pl->ctl_offset = pl->pre_offset + (int)pre_bytes;
-    pl->pbuf_offset = with_pbuf ? pl->ctl_offset + (int)ctl_bytes : -1;
-    pl->bar_offset = pl->ctl_offset + (int)ctl_bytes + (with_pbuf ? (int)part_bytes : 0);
+    pl->bar_offset = pl->ctl_offset + (int)ctl_bytes;
     pl->smem_bytes = pl->bar_offset + 1024 + 1024;
     return pl->smem_bytes <= 227 * 1024;
   }
@@ -680,10 +674,12 @@ cudaError_t launch_decode_tc(const DecodeTcArgs& a, const DecodeTcPlan& pl, cuda
   args.Uc = pl.Uc; args.NC_A = pl.NC_A; args.NC_B = pl.NC_B; args.NC_C = pl.NC_C; args.NC_max = pl.NC_max;
   args.Bpad8 = pl.Bpad8; args.Bq = pl.Bq; args.mma_m = pl.mma_m; args.kps = pl.kps; args.stages = pl.stages;
   args.pre_offset = pl.pre_offset; args.ctl_offset = pl.ctl_offset; args.bar_offset = pl.bar_offset; args.tmem_cols = pl.tmem_cols;
-  args.pbuf_offset = pl.pbuf_offset;
   void* kargs[] = {&args};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)decode_tc_kernel, dim3(pl.G), dim3(DT_THREADS), kargs, pl.smem_bytes, st);
   if (e != cudaSuccess) return e;
+  const int nB = (int)ceil_div(a.w.V, pl.NC_B);
+  decode_finish_kernel<<<a.B, 256, 0, st>>>(a.part, a.n_eval, nB, pl.Bq, a.max_steps, a.neg_logp, a.trace ? a.trace_lse : nullptr, a.trace_cap);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (a.trace) {
     trace_normalize_kernel<<<148, 256, 0, st>>>(a.trace, a.trace_lse, a.B, a.trace_cap, a.w.V);
     return cudaGetLastError();

@@ -145,7 +145,6 @@ cudaError_t launch_decode(const DecodeArgs& a, int grid_blocks, cudaStream_t st)
 struct DecodeTcPlan {
   int G, Uc, NC_A, NC_B, NC_C, NC_max;                 // weight-side plan (batch independent)
   int Bpad8, Bq, mma_m, kps, stages, pre_offset, ctl_offset, bar_offset, smem_bytes, tmem_cols;
-  int pbuf_offset;   // smem landing buffer of all softmax partials (-1: read them from L2 instead)
 };
 struct DecodeTcArgs {
   DecodeWeights w;                 // fp32 vectors / tables (table0, biases, h0, BatchNorm, b2)
@@ -157,14 +156,17 @@ struct DecodeTcArgs {
   const int32_t* lens_T;
   int B, T, max_iters, use_state_in;
   uint8_t* g_img; uint8_t* z_img; uint8_t* x_img[2]; uint8_t* h_img[kMaxPredLayers][2];   // activation images (TR = Bpad8)
-  float* part;                     // [G][Bq][4] softmax partials
+  float* part;                     // [max_steps][nB][Bq][2] per-step (max, sum exp) of every CTA's vocabulary slice
+  unsigned long long* keys;        // [max_steps][Bq] packed arg-max keys (atomicMax), zero at launch
+  int* n_eval;                     // [B] evaluations per utterance (out)
+  int max_steps;
   float* trace_lse;
   float* state_h; float* pred_out; // [Lp][B][H], [B][H] in/out (nullable unless use_state_in)
   int32_t* tokens; int U_cap; int32_t* ntok; double* neg_logp; uint8_t* iters; float* trace; int trace_cap;
   unsigned int* barrier;           // grid phase counter, zero at launch
   unsigned long long* dbg; int dbg_cap;   // optional (time, tag) trail of CTA 0 (tuning aid)
   // filled from the plan by the launcher
-  int Uc, NC_A, NC_B, NC_C, NC_max, Bpad8, Bq, mma_m, kps, stages, pre_offset, ctl_offset, bar_offset, tmem_cols, pbuf_offset;
+  int Uc, NC_A, NC_B, NC_C, NC_max, Bpad8, Bq, mma_m, kps, stages, pre_offset, ctl_offset, bar_offset, tmem_cols;
 };
 cudaError_t configure_decode_tc();
 bool decode_tc_wplan(int H, int J, int V, int sms, DecodeTcPlan* pl);
