@@ -26,7 +26,7 @@
 namespace rnnt {
 namespace {
 
-constexpr int DT_THREADS = 192;
+constexpr int DT_THREADS = 224;   // warp 0 activation producer, 1 MMA, 2-5 epilogue, 6 weight producer
 constexpr int DT_MAXB = 64;
 constexpr int DT_MAX_RPT = 8;   // rows (or units) per epilogue thread
 
@@ -98,8 +98,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
   const int prs = 4 * p.NC_max + 1;                             // exchange row stride (two GEMMs of 2*NC_max columns)
   float* pre_lo = pre_hi + Bq * prs;
   Ctrl& c = *reinterpret_cast<Ctrl*>(base + p.ctl_offset);
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + p.bar_offset);
-  uint64_t* empty = full + S;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + p.bar_offset);   // activation part of a stage landed
+  uint64_t* fullw = full + S;                                          // weight part of a stage landed
+  uint64_t* empty = fullw + S;
   uint64_t* tfull = empty + S;
   uint64_t* tempty = tfull + 1;
   uint64_t* ctlbar = tempty + 1;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
+      mbar_init(&fullw[s], 1);
       mbar_init(&empty[s], 1);
     }
     mbar_init(tfull, 1);
@@ -148,14 +150,18 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     return n + 1;
   };
 
-  if (warp == 0) {
-    // =========================== producer ===========================
+  if (warp == 0 || warp == 6) {
+    // =========================== producers ===========================
+    // warp 0 streams ACTIVATION tiles (gated by the grid phase counter: another CTA wrote them);
+    // warp 6 streams WEIGHT tiles of the same stages and is never gated, so at a phase boundary the
+    // next phase's weight slices (up to S stages) are already landing while the barrier propagates.
+    const bool acts = warp == 0;
     uint32_t g = 0;
     unsigned nbar = 1;   // grid barriers to wait for before a phase reads activations (1 = initial images)
     auto run_phase = [&](int phase, int par) {
       Gemm gm[2];
       const int ng = phase_gemms(phase, par, gm);
-      if (ng > 0) {
+      if (acts && ng > 0) {
         while (ld_acquire_u32(p.barrier) < nbar * (unsigned)G) {
         }
         fence_proxy_async_global();
@@ -168,10 +174,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
           mbar_wait(&empty[s], ph ^ 1);
           if (elect_one()) {
             const int nkb = min(KPS, gm[q].KB - kb0);
-            mbar_arrive_expect_tx(&full[s], (uint32_t)nkb * (xkb + wkb));
             uint8_t* dst = ring + (size_t)s * stage_bytes;
-            tma_bulk_g2s(dst, gm[q].act + (size_t)kb0 * xkb, (uint32_t)nkb * xkb, &full[s]);
-            tma_bulk_g2s(dst + KPS * xkb, gm[q].w + (size_t)kb0 * wkb, (uint32_t)nkb * wkb, &full[s]);
+            if (acts) {
+              mbar_arrive_expect_tx(&full[s], (uint32_t)nkb * xkb);
+              tma_bulk_g2s(dst, gm[q].act + (size_t)kb0 * xkb, (uint32_t)nkb * xkb, &full[s]);
+            } else {
+              mbar_arrive_expect_tx(&fullw[s], (uint32_t)nkb * wkb);
+              tma_bulk_g2s(dst + KPS * xkb, gm[q].w + (size_t)kb0 * wkb, (uint32_t)nkb * wkb, &fullw[s]);
+            }
           }
           __syncwarp();
         }
@@ -215,6 +225,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
         for (int kb0 = 0; kb0 < gm[q].KB; kb0 += KPS, ++g) {
           const int s = g % S;
           const uint32_t ph = (g / S) & 1;
+          mbar_wait(&fullw[s], ph);
           mbar_wait(&full[s], ph);
           tc_fence_after();
           if (elect_one()) {
