@@ -204,18 +204,39 @@ def run_product(args):
     if rank == 0:
         peaks = load_peaks()
         work = model_flops_bytes(cfg, BATCH, T, evals, emitted)
-        # dominant kernel by device time: the persistent decode loop vs the encoder launches
-        dom = max(("decode", stage["decode"]), ("encoder", stage["encoder"]), key=lambda kv: kv[1])
-        if dom[0] == "decode":
-            flops, kname = work["decode_flops"], "decode_greedy_kernel (joint + predictor greedy loop)"
-        else:
-            flops, kname = work["encoder_flops"], "LSTM gate GEMMs (hoisted input GEMM + recurrent steps)"
-        ach = flops / (dom[1] * 1e-3) / 1e12
-        peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-        roofline = {"kernel": kname, "bound": "tensor", "achieved": round(ach, 3), "peak": peak, "unit": "TFLOP/s",
-                    "frac": round(ach / peak, 5), "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
-                    "ms_per_launch": round(dom[1], 4), "flops_per_launch": flops,
-                    "note": "3xFP16 split on tcgen05 issues 4 fp16 MACs per algorithmic MAC (mode 1) / fp32 FMA (mode 0); fraction = algorithmic flops vs the bf16 tensor peak"}
+        # per-kernel rooflines from the live CUDA-event stage times of the timed region.  Algorithmic work
+        # (DESIGN.md section 4): tensor-bound kernels in flops vs the sustained bf16 peak (the kernels sit inside
+        # a long step), the front end in bytes vs the measured HBM copy bandwidth.
+        tc = args.gemm_mode == 1
+        peak_t = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        H, X, L = cfg.hidden_sz, cfg.feature_sz, cfg.enc_layers
+        hoist_flops = BATCH * T * (2 * X * 4 * H + (L - 1) * 2 * H * 4 * H)
+        rec_flops = work["encoder_flops"] - hoist_flops
+        rec_ms = max(stage["encoder"] - stage["encoder_input_gemms"], 1e-6)
+        fe_bytes = BATCH * (4 * n + 4 * T * X)
+
+        def tens(name, flops, ms, launches):
+            a = flops / (ms * 1e-3) / 1e12
+            return {"kernel": name, "bound": "tensor", "achieved": round(a, 3), "peak": peak_t, "unit": "TFLOP/s",
+                    "frac": round(a / peak_t, 5), "ms_per_step": round(ms, 4), "launches_per_step": launches,
+                    "algorithmic_flops_per_step": int(flops)}
+        per_kernel = [
+            tens("decode_tc_kernel" if tc else "decode_greedy_kernel", work["decode_flops"], stage["decode"], 1),
+            tens("lstm_layer_tc_kernel" if tc else "lstm_step_kernel", rec_flops, rec_ms, L if tc else L * T),
+            tens("gemm_tc_f16x3_kernel" if tc else "gemm_nt_f32_kernel", hoist_flops, max(stage["encoder_input_gemms"], 1e-6), L),
+            {"kernel": "mel_stack_kernel", "bound": "hbm", "achieved": round(fe_bytes / (stage["features"] * 1e-3) / 1e9, 1),
+             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(fe_bytes / (stage["features"] * 1e-3) / 1e9 / peaks["hbm_gbs"], 5),
+             "ms_per_step": round(stage["features"], 4), "launches_per_step": 1, "algorithmic_bytes_per_step": fe_bytes,
+             "note": "FFT-compute-bound, not HBM-bound (DESIGN.md section 4)"},
+        ]
+        dom = max(per_kernel[:3], key=lambda k: k["ms_per_step"])
+        roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
+                    "frac": dom["frac"], "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 GEMM",
+                    "ms_per_launch": round(dom["ms_per_step"] / dom["launches_per_step"], 4),
+                    "flops_per_launch": int(dom["algorithmic_flops_per_step"] / dom["launches_per_step"]),
+                    "note": ("latency-bound at batch 32 (DESIGN.md section 4): fraction = algorithmic flops / sustained bf16 tensor peak; "
+                             "3xFP16 split issues 4 fp16 MACs per algorithmic MAC" if tc else "fp32 CUDA-core mode; fraction vs the bf16 tensor peak"),
+                    "per_kernel": per_kernel}
         cpu = cpu_baseline(cfg, n, budget_s=args.cpu_budget)
         line = {
             "metric": "streaming RTFx (audio-s/wall-s)", "value": round(value, 1), "unit": "x real-time",

@@ -222,8 +222,9 @@ int32_t rnnt_b200_selftest_gemm(rnnt_b200_handle h, const float* A_dev, const fl
 int64_t rnnt_b200_kernel_launches(rnnt_b200_handle h);
 
 /* Device time (ms) the most recent transcribe*() spent per stage, measured with CUDA
- * events on `stream`: out[0]=features, [1]=encoder (LayerNorm + hoisted input GEMMs +
- * recurrent steps), [2]=reserved (0), [3]=joint enc projection GEMM, [4]=decode loop.
+ * events on `stream`: out[0]=features, [1]=encoder total (LayerNorm + hoisted input GEMMs +
+ * recurrent kernels), [2]=the hoisted input GEMMs' share of [1] (incl. operand-image conversion),
+ * [3]=joint enc projection GEMM, [4]=decode loop.
  * Synchronises.  Profiling must have been enabled with rnnt_b200_set_profiling(h, 1). */
 int32_t rnnt_b200_set_profiling(rnnt_b200_handle h, int32_t enable);
 int32_t rnnt_b200_stage_times_ms(rnnt_b200_handle h, float* out5_host);

@@ -83,12 +83,14 @@ struct rnnt_b200_handle_s {
   DevBuf t_audio, t_lens, t_tokens, t_ntok, t_nlp, t_iters, t_enc;
   // profiling
   bool profiling = false;
-  std::vector<cudaEvent_t*> evsets;  // one set of 6 events per profiled transcribe() call
+  std::vector<cudaEvent_t*> evsets;  // one set of events per profiled transcribe() call: 6 stage marks + 2 per encoder layer
   int ev_used = 0;                   // sets holding a complete recording
   cudaEvent_t* ev = nullptr;         // set being recorded
 };
 
 namespace {
+
+constexpr int kEvPerSet = 6 + 2 * 16;
 
 thread_local std::string g_create_err;
 
@@ -262,7 +264,7 @@ int32_t rnnt_b200_destroy(rnnt_b200_handle h) {
                     &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc, &h->a_img, &h->x_img[0], &h->x_img[1], &h->gbar, &h->dimg, &h->dkeys};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t* set : h->evsets) {
-    for (int i = 0; i < 6; ++i) cudaEventDestroy(set[i]);
+    for (int i = 0; i < kEvPerSet; ++i) cudaEventDestroy(set[i]);
     delete[] set;
   }
   delete h;
@@ -680,6 +682,7 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
     const float* A = l == 0 ? h->lnx.as<float>() : ((l - 1) & 1 ? h->yb.as<float>() : h->ya.as<float>());
     float* y = (l == c.enc_layers - 1) ? enc_out : (l & 1 ? h->yb.as<float>() : h->ya.as<float>());
     const bool tc = c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3;
+    if (h->ev) cudaEventRecord(h->ev[6 + 2 * l], st);
     LstmTcPlan pl;
     const bool tc_rec = tc && h->lstm_tc_ok && B <= 128 && lstm_tc_plan(H, B, h->sm_count, &pl);
     if (tc) {
@@ -691,6 +694,7 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
     } else {
       LAUNCH(1, launch_gemm_nt_f32(A, L.in, L.Wih_r, L.in, L.bias_r, h->xp.as<float>(), 4 * H, M, 4 * H, L.in, st));
     }
+    if (h->ev) cudaEventRecord(h->ev[7 + 2 * l], st);
     if (tc_rec) {
       const size_t ximg = img_bytes(128, H, 128);
       CK(h->x_img[0].ensure(ximg));
@@ -938,8 +942,8 @@ int32_t rnnt_b200_transcribe(rnnt_b200_handle h, const float* audio, const int32
   }
   if (h->profiling) {
     if (h->ev_used >= (int)h->evsets.size()) {
-      cudaEvent_t* set = new cudaEvent_t[6];
-      for (int i = 0; i < 6; ++i) cudaEventCreate(&set[i]);
+      cudaEvent_t* set = new cudaEvent_t[kEvPerSet];
+      for (int i = 0; i < kEvPerSet; ++i) cudaEventCreate(&set[i]);
       h->evsets.push_back(set);
     }
     h->ev = h->evsets[h->ev_used++];
@@ -1025,6 +1029,11 @@ int32_t rnnt_b200_stage_times_ms(rnnt_b200_handle h, float* out) {
     cudaEvent_t* ev = h->evsets[s];
     CK(cudaEventSynchronize(ev[4]));
     float f = 0, e = 0, j = 0, d = 0;
+    for (int l = 0; l < h->cfg.enc_layers; ++l) {
+      float gl = 0;
+      CK(cudaEventElapsedTime(&gl, ev[6 + 2 * l], ev[7 + 2 * l]));
+      acc[2] += gl;
+    }
     CK(cudaEventElapsedTime(&f, ev[5], ev[0]));
     CK(cudaEventElapsedTime(&e, ev[0], ev[1]));
     CK(cudaEventElapsedTime(&j, ev[2], ev[3]));

@@ -325,7 +325,7 @@ class Engine:
     def stage_times_ms(self):
         buf = (C.c_float * 5)()
         self._ck(self.lib.rnnt_b200_stage_times_ms(self._h, buf))
-        return dict(zip(("features", "encoder", "reserved", "joint_enc_gemm", "decode"), [float(x) for x in buf]))
+        return dict(zip(("features", "encoder", "encoder_input_gemms", "joint_enc_gemm", "decode"), [float(x) for x in buf]))
 
 
 def tokens_to_lists(tokens, ntok):
