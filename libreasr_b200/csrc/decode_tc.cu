@@ -591,28 +591,41 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
 __global__ void __launch_bounds__(256) decode_finish_kernel(const float* __restrict__ part, const int* __restrict__ n_eval,
                                                             int nB, int Bq, int max_steps, double* __restrict__ neg_logp,
                                                             float* __restrict__ lse_out, int lse_cap) {
-  const int b = blockIdx.x;
+  // one block per utterance, one warp per evaluation; lanes fold contiguous runs of the vocabulary partials and are
+  // combined in a fixed shuffle tree (deterministic)
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ne = min(n_eval[b], max_steps);
+  const int per = (nB + 31) / 32;
   double acc = 0.0;
-  for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+  for (int e = warp; e < ne; e += 8) {
     float M = -INFINITY, S = 0.f;
-    for (int k = 0; k < nB; ++k) {
+    for (int k = lane * per; k < min(nB, (lane + 1) * per); ++k) {
       const float2 q = *reinterpret_cast<const float2*>(part + (((size_t)e * nB + k) * Bq + b) * 2);
       if (q.x > M) { S = S * expf(M - q.x) + q.y; M = q.x; }
       else S += q.y * expf(q.x - M);
     }
-    const float lse = M + logf(S);
-    acc += (double)(M - lse);
-    if (lse_out && e < lse_cap) lse_out[(size_t)b * lse_cap + e] = lse;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {   // lane l absorbs lane l + o
+      const float M2 = __shfl_down_sync(0xffffffffu, M, o), S2 = __shfl_down_sync(0xffffffffu, S, o);
+      if ((lane & (2 * o - 1)) == 0 && lane + o < 32) {
+        if (M2 > M) { S = (M == -INFINITY ? 0.f : S * expf(M - M2)) + S2; M = M2; }
+        else if (M2 != -INFINITY) S += S2 * expf(M2 - M);
+      }
+    }
+    if (lane == 0) {
+      const float lse = M + logf(S);
+      acc += (double)(M - lse);
+      if (lse_out && e < lse_cap) lse_out[(size_t)b * lse_cap + e] = lse;
+    }
   }
-  __shared__ double red[256];
-  red[threadIdx.x] = acc;
+  __shared__ double red[8];
+  if (lane == 0) red[warp] = acc;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
+  if (threadIdx.x == 0 && neg_logp) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    neg_logp[b] = -t;
   }
-  if (threadIdx.x == 0 && neg_logp) neg_logp[b] = -red[0];
 }
 
 __global__ void trace_normalize_kernel(float* trace, const float* lse, int B, int cap, int V) {
