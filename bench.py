@@ -230,8 +230,12 @@ def run_product(args):
              "note": "FFT-compute-bound, not HBM-bound (DESIGN.md section 4)"},
         ]
         dom = max(per_kernel[:3], key=lambda k: k["ms_per_step"])
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
+        ncu_traffic = {"decode_tc_kernel": {"bytes": 69243392 + 4359936, "source": "profiles/r1_ncu_full_decode_tc_kernel.csv"},
+                       "lstm_layer_tc_kernel": {"bytes": 81891840 + 6472448, "source": "profiles/r1_ncu_full_lstm_layer_tc_kernel.csv"}}
         roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
-                    "frac": dom["frac"], "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 GEMM",
+                    "frac": dom["frac"], "traffic": ncu_traffic.get(dom["kernel"], {}).get("bytes"),
+                    "traffic_source": ncu_traffic.get(dom["kernel"], {}).get("source"), "peak_source": peaks["source"] + ", sustained bf16 GEMM",
                     "ms_per_launch": round(dom["ms_per_step"] / dom["launches_per_step"], 4),
                     "flops_per_launch": int(dom["algorithmic_flops_per_step"] / dom["launches_per_step"]),
                     "note": ("latency-bound at batch 32 (DESIGN.md section 4): fraction = algorithmic flops / sustained bf16 tensor peak; "
