@@ -331,8 +331,16 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
         tc_fence_before();
         mbar_arrive(sm.tempty);
       }
+      // Only h_t gates the next step: publish it first (stores -> CTA barrier -> one gpu-scope release on the
+      // step counter, paired with the consumers' ld.acquire + fence.proxy.async before their TMA reads);
+      // the BatchNorm(h_t) outputs for the next layer are written after the release, off the critical path.
+      if (valid) store_h(p.x_img[(t + 1) & 1], h);
+      named_bar_sync(1, 128);
+      if (et == 0) {
+        red_release_add(p.barrier, 1u);
+        if (p.dbg && cta == 0) p.dbg[t * 4 + 3] = gtimer();
+      }
       if (valid) {
-        store_h(p.x_img[(t + 1) & 1], h);
         if (p.y) {
           float* yo = p.y + row * H + unit0;
           if (upt >= 4) {
@@ -346,13 +354,6 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
           }
         }
         if (p.y_img) store_yimg(row, hy);
-      }
-      // h_t stores (generic proxy) -> CTA barrier -> one gpu-scope release on the step counter; the
-      // consumers pair it with ld.acquire + fence.proxy.async before their TMA reads of the image
-      named_bar_sync(1, 128);
-      if (et == 0) {
-        red_release_add(p.barrier, 1u);
-        if (p.dbg && cta == 0) p.dbg[t * 4 + 3] = gtimer();
       }
     }
     if (valid) {
