@@ -79,6 +79,8 @@ struct Gemm {
   const uint8_t* act;   // activation image (TR = Bpad8 tiles, [kb][part] contiguous)
   const uint8_t* w;     // this CTA's weight tiles ([kb][part] contiguous, NC rows each)
   int KB, NC, col;
+  int gated;            // 1: the activation image was written in the phase just before (wait for the grid counter);
+                        // 0: it is older (the recurrent state h of a predictor layer) and can stream immediately
 };
 
 __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p) {
@@ -135,19 +137,22 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
   auto phase_gemms = [&](int phase, int par, Gemm (&gm)[2]) -> int {
     if (phase == 0) {
       if (!in_A) return 0;
-      gm[0] = Gemm{p.g_img, wA, KBH, p.NC_A, 0};
+      gm[0] = Gemm{p.g_img, wA, KBH, p.NC_A, 0, 1};
       return 1;
     }
     if (phase == 1) {
       if (!in_B) return 0;
-      gm[0] = Gemm{p.z_img, wB, KBJ, p.NC_B, 0};
+      gm[0] = Gemm{p.z_img, wB, KBJ, p.NC_B, 0, 1};
       return 1;
     }
+    // predictor layer l: the recurrent product h_l * R_l only needs state written a whole predictor run ago, so it
+    // goes FIRST and ungated (it overlaps the previous phase's epilogue and barrier); the input product x * K_l
+    // (l > 0) needs BatchNorm(h_{l-1}) of this run.  TMEM columns: [0, 2NC) input product, [2NC, 4NC) recurrent.
     const int l = phase - 2;
-    int n = 0;
-    if (l > 0) gm[n++] = Gemm{p.x_img[(l - 1) & 1], p.k_img[l] + img_tile_offset(cta, 0, 0, KBH, p.NC_C), KBH, p.NC_C, 0};
-    gm[n] = Gemm{p.h_img[l][par], p.r_img[l] + img_tile_offset(cta, 0, 0, KBH, p.NC_C), KBH, p.NC_C, n * 2 * p.NC_C};
-    return n + 1;
+    gm[0] = Gemm{p.h_img[l][par], p.r_img[l] + img_tile_offset(cta, 0, 0, KBH, p.NC_C), KBH, p.NC_C, l > 0 ? 2 * p.NC_C : 0, 0};
+    if (l == 0) return 1;
+    gm[1] = Gemm{p.x_img[(l - 1) & 1], p.k_img[l] + img_tile_offset(cta, 0, 0, KBH, p.NC_C), KBH, p.NC_C, 0, 1};
+    return 2;
   };
 
   if (warp == 0 || warp == 6) {
@@ -161,12 +166,12 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     auto run_phase = [&](int phase, int par) {
       Gemm gm[2];
       const int ng = phase_gemms(phase, par, gm);
-      if (acts && ng > 0) {
-        while (ld_acquire_u32(p.barrier) < nbar * (unsigned)G) {
-        }
-        fence_proxy_async_global();
-      }
       for (int q = 0; q < ng; ++q) {
+        if (acts && gm[q].gated) {
+          while (ld_acquire_u32(p.barrier) < nbar * (unsigned)G) {
+          }
+          fence_proxy_async_global();
+        }
         const uint32_t wkb = (uint32_t)gm[q].NC * 256;
         for (int kb0 = 0; kb0 < gm[q].KB; kb0 += KPS, ++g) {
           const int s = g % S;
@@ -189,6 +194,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
       ++nbar;
     };
     int par = 0;
+    if (acts) {   // the initial operand images (written by every CTA's epilogue warps) precede even the ungated GEMMs
+      while (ld_acquire_u32(p.barrier) < (unsigned)G) {
+      }
+      fence_proxy_async_global();
+    }
     if (!p.use_state_in) {
       for (int l = 0; l < Lp; ++l) run_phase(2 + l, par);
       par ^= 1;
@@ -216,9 +226,12 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
       Gemm gm[2];
       const int ng = phase_gemms(phase, par, gm);
       if (ng == 0) return;
-      if (nacc > 0) mbar_wait(tempty, (nacc - 1) & 1);
-      tc_fence_after();
+      // the previous phase's accumulators must be drained before they are overwritten; the ungated recurrent GEMM
+      // of predictor layer 1 targets columns [2NC, 4NC) that layer 0's drain never reads, so it may start early
+      const bool early = phase == 3 && ng == 2;
       for (int q = 0; q < ng; ++q) {
+        if (nacc > 0 && ((q == 0 && !early) || (q == 1 && early))) mbar_wait(tempty, (nacc - 1) & 1);
+        tc_fence_after();
         const uint32_t idesc = umma_idesc_f16(MM, 2 * gm[q].NC);
         const uint32_t wkb_u = ((uint32_t)gm[q].NC * 256) >> 4;
         const uint32_t dcol = tmem + (uint32_t)gm[q].col;
