@@ -673,6 +673,16 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
   if ((state_h == nullptr) != (state_c == nullptr)) return fail(h, RNNT_B200_ERR_INVALID, "encode: state_h and state_c must both be given");
   cudaStream_t st = (cudaStream_t)stream;
   const int H = c.hidden_sz, X = c.n_mels * c.n_stack, Bp = bp_of(B);
+  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->lstm_tc_ok && B > 128 && !state_h) {
+    // independent utterances: stateless batches beyond the persistent LSTM kernel's capacity run as sub-batches of 128
+    for (int b0 = 0; b0 < B; b0 += 128) {
+      const int nb = std::min(128, B - b0);
+      const int r = rnnt_b200_encode(h, feats + (size_t)b0 * T * X, lens_T ? lens_T + b0 : nullptr, nb, T, nullptr, nullptr, 0,
+                                     enc_out + (size_t)b0 * T * H, stream);
+      if (r) return r;
+    }
+    return RNNT_B200_OK;
+  }
   const int64_t M = (int64_t)B * T;
   if (int r = ensure_encode_ws(h, B, T)) return r;
   if (h->ev) cudaEventRecord(h->ev[0], st);
@@ -815,8 +825,26 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
   const rnnt_b200_config& c = h->cfg;
   if (!enc || !tokens_out || !ntok_out || B < 1 || T < 1 || max_iters < 1 || max_iters > 255)
     return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: bad arguments");
-  if (B > kDecodeMaxBatch) return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: B > 256 (split the batch)");
   if ((int64_t)U_cap < (int64_t)max_iters * T) return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: U_cap < max_iters*T");
+  {
+    // Utterances are independent: larger batches run as consecutive sub-batches of the kernel's capacity
+    // (64 for the tcgen05 kernel, 256 for the fp32 one).  State tensors are [Lp, B, H], i.e. not sliceable
+    // per sub-batch, so stateful (streaming) calls must fit one launch.
+    const int cap = (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok) ? 64 : kDecodeMaxBatch;
+    if (B > cap) {
+      if (pred_state_h || pred_out || use_state_in)
+        return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: stateful calls are limited to " + std::to_string(cap) + " streams per call");
+      for (int b0 = 0; b0 < B; b0 += cap) {
+        const int nb = std::min(cap, B - b0);
+        const int r = rnnt_b200_decode_greedy(h, enc + (size_t)b0 * T * c.hidden_sz, lens_T ? lens_T + b0 : nullptr, nb, T, max_iters,
+                                              nullptr, nullptr, 0, tokens_out + (size_t)b0 * U_cap, U_cap, ntok_out + b0,
+                                              neg_logp_out ? neg_logp_out + b0 : nullptr, iters_out ? iters_out + (size_t)b0 * T : nullptr,
+                                              trace_logp ? trace_logp + (size_t)b0 * trace_cap * c.vocab_sz : nullptr, trace_cap, stream);
+        if (r) return r;
+      }
+      return RNNT_B200_OK;
+    }
+  }
   if (use_state_in && (!pred_state_h || !pred_out)) return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: use_state_in needs pred_state_h and pred_out");
   if (trace_logp && trace_cap < 1) return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: trace_cap < 1");
   cudaStream_t st = (cudaStream_t)stream;

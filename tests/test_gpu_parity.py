@@ -256,3 +256,44 @@ def test_error_behaviour():
         eng.features(torch.zeros(1, 300, device="cuda"))  # shorter than the reflect padding
     with pytest.raises(NotImplementedError):
         m(None)
+
+
+# ---------------- batch-size dependent kernel paths ----------------
+@pytest.mark.parametrize("name,B,seconds", [("tiny", 48, 1.5), ("tiny", 100, 1.2), ("tiny", 150, 1.0), ("cfg2", 40, 1.5), ("cfg2", 72, 1.2)])
+def test_large_batches_match_single_utterance_runs(name, B, seconds):
+    """B in (32, 64]: M = 128 stacked tiles; B in (64, 128]: unfused LSTM tiles + decode sub-batches of 64;
+    B > 128: encoder sub-batches.  Every utterance must decode exactly as it does alone."""
+    from libreasr_b200.engine import tokens_to_lists
+
+    cfg, sd, m, orc = model_for(name)
+    eng = m.engine()
+    n = int(seconds * 16000)
+    audio = torch.from_numpy(weights.make_audio(B, n, seed=200 + B)).cuda()
+    r = eng.transcribe(audio, max_iters=3)
+    toks = tokens_to_lists(r["tokens"], r["ntok"])
+    assert sum(map(len, toks)) > 0
+    for b in list(range(0, B, max(1, B // 7))) + [B - 1]:
+        r1 = eng.transcribe(audio[b:b + 1].contiguous(), max_iters=3)
+        assert tokens_to_lists(r1["tokens"], r1["ntok"])[0] == toks[b], b
+        assert r1["iters"][0].cpu().tolist() == r["iters"][b].cpu().tolist()
+    # and two of them against the CPU oracle
+    for b in (1, B - 2):
+        want = O.transcribe_batch(orc, audio[b:b + 1].cpu().numpy(), max_iters=3, impl="aten")[0]
+        assert toks[b] == want, b
+
+
+def test_gemm_arithmetic_modes_against_fp64():
+    """The library GEMM behind the gate / joint projections: both arithmetic modes stay at fp32-grade error."""
+    cfg, sd, m, _ = model_for("tiny")
+    eng = m.engine()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (M_, N_, K_) in [(130, 260, 160), (777, 1024, 800)]:
+        A = torch.randn(M_, K_, device="cuda", generator=g)
+        W = (torch.rand(N_, K_, device="cuda", generator=g) * 2 - 1) * 0.1
+        b = torch.randn(N_, device="cuda", generator=g)
+        ref = A.double() @ W.double().t() + b.double()
+        scale = float(ref.abs().mean())
+        for mode in (0, 1):
+            C = eng.selftest_gemm(A, W, b, gemm_mode=mode)
+            rel = float((C.double() - ref).pow(2).mean().sqrt()) / scale
+            assert rel < 4e-6, (mode, M_, N_, K_, rel)
