@@ -128,7 +128,7 @@ def run_product(args):
     U = MAX_ITERS * T
 
     # synthetic input: N_ROTATE distinct batches per rank, in pinned host memory and in HBM
-    base = synth.make_audio(BATCH, n, seed=rank)  # seed 0 on rank 0
+    base = synth.make_audio(BATCH, n, seed=synth.BENCH_AUDIO_SEED + 1000 * rank)  # see synth.BENCH_AUDIO_SEED
     host = [torch.from_numpy(np.roll(base, 997 * r, axis=1).copy()).pin_memory() for r in range(N_ROTATE)]
     devb = [h.to(dev) for h in host]
     out_host = Engine.alloc_host_outputs(BATCH, U)

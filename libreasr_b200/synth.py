@@ -76,6 +76,12 @@ CONFIGS = {
 }
 
 
+# Audio seed of the headline workload (bench.py, BASELINE.json configs[1]): chosen among the first seeds so that the
+# fp32 CPU path's own greedy decisions all have a top-1/top-2 log-probability margin >= 1e-3 (seed 0 contains a
+# 1.5e-5 near-tie that two fp32 implementations may legitimately resolve differently); 77 % blank evaluations.
+BENCH_AUDIO_SEED = 4
+
+
 def _rng(seed: int, name: str) -> np.random.Generator:
     return np.random.Generator(np.random.PCG64([seed & 0xFFFFFFFF, zlib.crc32(name.encode())]))
 

@@ -258,6 +258,27 @@ def test_error_behaviour():
         m(None)
 
 
+def test_bench_workload_tokens_identical_to_oracle():
+    """The headline workload itself (bench.py: 32 x 10 s, cfg2, synth.BENCH_AUDIO_SEED): every utterance's greedy
+    token sequence and per-frame evaluation counts equal the CPU oracle's."""
+    from libreasr_b200.engine import tokens_to_lists
+
+    cfg, sd, m, orc = model_for("cfg2")
+    eng = m.engine()
+    audio = weights.make_audio(32, 160000, seed=weights.BENCH_AUDIO_SEED)
+    r = eng.transcribe(torch.from_numpy(audio).cuda(), max_iters=3)
+    got = tokens_to_lists(r["tokens"], r["ntok"])
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    n_tok = 0
+    for b in range(32):
+        ro = orc.decode_greedy(O.features_offline(torch.from_numpy(audio[b:b + 1]), cfg)[0], max_iters=3, impl="aten")
+        assert got[b] == ro["tokens"], f"utt {b}: oracle min margin {min(ro['margins']):.2e}"
+        assert r["iters"][b].cpu().tolist() == ro["iters"]
+        assert abs(float(r["neg_logp"][b]) - ro["neg_log_p"]) < 5e-3
+        n_tok += len(got[b])
+    assert n_tok > 500
+
+
 # ---------------- batch-size dependent kernel paths ----------------
 @pytest.mark.parametrize("name,B,seconds", [("tiny", 48, 1.5), ("tiny", 100, 1.2), ("tiny", 150, 1.0), ("cfg2", 40, 1.5), ("cfg2", 72, 1.2)])
 def test_large_batches_match_single_utterance_runs(name, B, seconds):
