@@ -172,6 +172,31 @@ def modules_fixture(name="tiny", T=12, N=3):
     }
 
 
+def demo_fixture(name="ref"):
+    """BASELINE.json configs[0]: the reference's demo utterance (api-client.py:13; 16 kHz mono 16-bit FLAC, 330,400
+    samples) through the reference-shape model, greedy (max_iters 3).  No pretrained weights exist offline, so this is
+    plumbing parity on real speech with the seeded synthetic weights.  The PCM is stored (int16) because the
+    reference tree does not exist on the GPU box."""
+    from . import flac
+
+    cfg = weights.CONFIGS[name]
+    ref = build_reference(cfg)
+    pcm, sr, bps = flac.decode(os.path.join(ref_shim.REFERENCE_ROOT, "demo", "3729-6852-0035.flac"))
+    assert (sr, bps, pcm.shape) == (16000, 16, (1, 330400))
+    audio = torch.from_numpy(pcm.astype(np.float32) / 32768.0)          # torchaudio.load normalisation
+    feats = ref_features_offline(audio, cfg)[0]
+    with torch.no_grad():
+        toks, nlp, metrics, extra = ref.decode_greedy(feats, max_iters=3)
+    logp = torch.stack([o.reshape(-1) for o in extra["outs"]])
+    top2 = torch.topk(logp, 2, dim=-1).values
+    margins = (top2[:, 0] - top2[:, 1]).numpy()
+    print(f"[demo/{name}] T={feats.shape[0]} evals={logp.shape[0]} tokens={len(toks)} min margin={margins.min():.2e}")
+    return {"config": name, "weight_seed": WEIGHT_SEED, "pcm16": pcm[0].astype(np.int16), "max_iters": 3,
+            "tokens": np.asarray(toks, dtype=np.int32), "iters": np.asarray(extra["iters"], dtype=np.int32),
+            "neg_log_p": np.float64(nlp), "alignment_score": np.float64(metrics["alignment_score"]),
+            "maxlogp": logp.max(-1).values.numpy().astype(np.float32), "margins": margins.astype(np.float32)}
+
+
 def main():
     if not ref_shim.reference_available():
         sys.exit("reference tree missing; fixtures can only be generated in the authoring container")
@@ -186,6 +211,7 @@ def main():
         "cfg2_stream": lambda: stream_fixture("cfg2", n_chunks=50, audio_seed=47),
         "ref_offline": lambda: offline_fixture("ref", n_utt=1, n_samples=48000, audio_seed=25),
         "cfg4_offline": lambda: offline_fixture("cfg4", n_utt=1, n_samples=32000, audio_seed=26),
+        "cfg1_demo": lambda: demo_fixture("ref"),
     }
     only = sys.argv[1:]
     for k, fn in jobs.items():

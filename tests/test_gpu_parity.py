@@ -105,6 +105,23 @@ def test_transcribe_stream_matches_reference_fixture(name):
     assert yields[-1][0] == g["tokens_all"].tolist()
 
 
+def test_config1_demo_utterance_through_libreasr_facade():
+    """BASELINE.json configs[0]: the reference's demo utterance through ``LibreASR.transcribe()`` with the
+    reference-shape model -- token ids identical to the imported reference's ``decode_greedy``."""
+    from libreasr_b200 import LibreASR
+
+    g = load_golden("cfg1_demo")
+    cfg, sd, m, _ = model_for(str(g["config"]))
+    audio = g["pcm16"].astype(np.float32) / 32768.0
+    asr = LibreASR(m)
+    assert asr.transcribe(audio) == g["tokens"].tolist()
+    # and the reference entry point (api-server.py:75-78): features [T, X, 1] -> model.transcribe
+    feats = m.engine().features(torch.from_numpy(audio)[None].cuda())[0].unsqueeze(-1)
+    toks, metrics = m.transcribe(feats)
+    assert toks == g["tokens"].tolist()
+    assert abs(metrics["alignment_score"] - float(g["alignment_score"])) < 1e-9
+
+
 def test_modules_match_reference_fixture():
     """Encoder / Predictor / Joint forward with explicit state."""
     g = load_golden("tiny_modules")

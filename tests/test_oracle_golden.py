@@ -92,3 +92,17 @@ def test_mel_filterbank_properties():
     assert int(nz.min()) >= 1  # every filter has taps at n_fft=1024
     # triangular: each bin contributes to at most two adjacent filters
     assert int((fb > 0).sum(1).max()) <= 2
+
+
+def test_demo_utterance_config1_matches_reference():
+    """BASELINE.json configs[0]: the reference's demo utterance (decoded FLAC PCM stored in the fixture)."""
+    g = load_golden("cfg1_demo")
+    cfg, orc = _model(g)
+    audio = torch.from_numpy(g["pcm16"].astype(np.float32) / 32768.0)[None]
+    assert audio.shape == (1, 330400)
+    feats = O.features_offline(audio, cfg)[0]
+    r = orc.decode_greedy(feats, max_iters=int(g["max_iters"]), impl="aten", keep_logits=True)
+    assert r["tokens"] == g["tokens"].tolist()
+    assert r["iters"] == g["iters"].tolist()
+    assert abs(r["neg_log_p"] - float(g["neg_log_p"])) < 5e-3
+    np.testing.assert_allclose(r["logp"].max(-1).values.numpy(), g["maxlogp"], atol=5e-4)
