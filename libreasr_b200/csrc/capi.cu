@@ -709,8 +709,8 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
       const size_t ximg = img_bytes(128, H, 128);
       CK(h->x_img[0].ensure(ximg));
       CK(h->x_img[1].ensure(ximg));
-      CK(h->gbar.ensure(64));
-      CK(cudaMemsetAsync(h->gbar.p, 0, 4, st));
+      CK(h->gbar.ensure(1024));
+      CK(cudaMemsetAsync(h->gbar.p, 0, (size_t)(H / 64) * 4, st));
       LstmTcArgs a;
       memset(&a, 0, sizeof(a));
       a.w_img = h->Whh_img[l];
@@ -872,7 +872,7 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     CK(h->dkeys.ensure((size_t)max_steps * dpl.Bq * 8 + (size_t)B * 4 + 64));
     CK(cudaMemsetAsync(h->dkeys.p, 0, (size_t)max_steps * dpl.Bq * 8, st));
     CK(h->dlse.ensure(std::max<size_t>((size_t)B * (trace_logp ? trace_cap : 1), 1) * 4));
-    CK(h->gbar.ensure(64));
+    CK(h->gbar.ensure(1024));
     CK(cudaMemsetAsync(h->gbar.p, 0, 4, st));
     if (trace_logp) {
       CK(cudaMemsetAsync(h->dlse.p, 0, (size_t)B * trace_cap * 4, st));

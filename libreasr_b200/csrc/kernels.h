@@ -67,7 +67,7 @@ struct LstmTcArgs {
   const float* h_init_vec; const float* c_init_vec;   // [H] learnable initial state
   const float* state_h_in; const float* state_c_in;   // [B][H] or nullptr
   float* state_h_out; float* state_c_out;             // [B][H] or nullptr
-  unsigned int* barrier;     // grid step counter, zero at launch
+  unsigned int* barrier;     // [H/64] per-k-block readiness counters, zero at launch
   unsigned long long* dbg;   // optional [T][4] globaltimer stamps of CTA 0 (tuning aid), or nullptr
   int T, B, H;
   // filled from the plan by the launcher

@@ -22,8 +22,8 @@
 //              c (and h) kept in REGISTERS across steps, writes h_t straight into the next
 //              step's operand image (fp16 hi/lo, swizzled) and BatchNorm(h_t) both as fp32
 //              and as the operand image of the next layer's input GEMM; then arrives on the
-//              grid counter (release) that the producers of all CTAs poll (acquire).
-// The only grid-wide synchronisation is that one counter per step.
+//              readiness counter of its 64-unit k-block (release) that the producers poll (acquire).
+// There is no grid-wide rendezvous: a k-block of h_t is consumable as soon as its 64/U owner CTAs published it.
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -128,13 +128,19 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
     }
     uint32_t g = 0;
     for (int t = 0; t < p.T; ++t) {
-      const unsigned target = (unsigned)(t + 1) * (unsigned)G;
-      while (ld_acquire_u32(p.barrier) < target) {
-      }
-      fence_proxy_async_global();
-      if (p.dbg && cta == 0 && lane == 0) p.dbg[t * 4 + 0] = gtimer();
+      // h_{t-1} is published per 64-unit k-block: p.barrier[kb] counts the (64 / U) CTAs that own its units, so the
+      // first k-blocks stream in while slower CTAs are still in their epilogue (no single grid-wide rendezvous)
+      const unsigned target = (unsigned)(t + 1) * (unsigned)(64 / U);
       const uint8_t* ximg = p.x_img[t & 1];
+      uint32_t ready = 0;   // k-blocks of h_{t-1} known to be published (lane i polls counter i: one L2 round trip per poll)
       for (int gi = 0; gi < n_groups; ++gi, ++g) {
+        const uint32_t need = ((KPS >= 32 ? 0u : (1u << KPS)) - 1u) << (gi * KPS);
+        while ((ready & need) != need) {
+          const bool ok = lane < KB ? (ld_acquire_u32(p.barrier + lane) >= target) : true;
+          ready = __ballot_sync(0xffffffffu, ok);
+        }
+        fence_proxy_async_global();
+        if (gi == 0 && p.dbg && cta == 0 && lane == 0) p.dbg[t * 4 + 0] = gtimer();
         const int s = g % S;
         const uint32_t ph = (g / S) & 1;
         mbar_wait(&sm.empty[s], ph ^ 1);
@@ -239,9 +245,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
         }
       }
     };
+    unsigned* my_flag = p.barrier + (cta * U) / 64;   // readiness counter of the k-block holding this CTA's units
     if (valid) store_h(p.x_img[0], h);
     named_bar_sync(1, 128);
-    if (et == 0) red_release_add(p.barrier, 1u);
+    if (et == 0) red_release_add(my_flag, 1u);
 
     const int prs = NC + 1;  // row stride of the exchange buffers
     for (int t = 0; t < p.T; ++t) {
@@ -337,7 +344,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
       if (valid) store_h(p.x_img[(t + 1) & 1], h);
       named_bar_sync(1, 128);
       if (et == 0) {
-        red_release_add(p.barrier, 1u);
+        red_release_add(my_flag, 1u);
         if (p.dbg && cta == 0) p.dbg[t * 4 + 3] = gtimer();
       }
       if (valid) {
@@ -381,7 +388,7 @@ cudaError_t configure_lstm_tc() {
 
 // Chooses the decomposition for hidden size H, batch B on a device with `sms` SMs; false if none fits.
 bool lstm_tc_plan(int H, int B, int sms, LstmTcPlan* pl) {
-  if (B < 1 || B > 128 || H % 64) return false;
+  if (B < 1 || B > 128 || H % 64 || H > 2048) return false;   // H / 64 <= 32: one polling lane per k-block counter
   int U = 0;
   for (int u : {4, 8, 16})
     if (H % u == 0 && H / u <= sms) { U = u; break; }
