@@ -292,18 +292,18 @@ def pick_cpu_threads(orc, cfg, probe_audio):
     return best
 
 
-def cpu_baseline(cfg, n, budget_s=12.0, max_utts=16, seed=100):
+def cpu_baseline(cfg, n, budget_s=12.0, max_utts=512, pool=16, seed=100):
     """The reference's CPU path (oracle port: torch fp32, utterance by utterance as the
     reference serves them) on this host's cores, on a bounded sample of the workload."""
     from oracle import rnnt_oracle as O
     from libreasr_b200 import synth
 
     orc = O.OracleTransducer(cfg, synth.make_state_dict(cfg, 1234))
-    audio = synth.make_audio(max_utts, n, seed=seed)
+    audio = synth.make_audio(pool, n, seed=seed)   # the sample cycles over a pool of distinct utterances
     threads = pick_cpu_threads(orc, cfg, audio[:1, : n // 5])
     done, t0 = 0, time.perf_counter()
     while done < max_utts and (done < 1 or time.perf_counter() - t0 < budget_s):
-        O.transcribe_batch(orc, audio[done:done + 1], max_iters=MAX_ITERS)
+        O.transcribe_batch(orc, audio[done % pool:done % pool + 1], max_iters=MAX_ITERS)
         done += 1
     dt = time.perf_counter() - t0
     return {"value": round(done * n / cfg.sample_rate / dt, 2), "unit": "x real-time", "cores": threads,
