@@ -862,7 +862,7 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
   }
   if (h->ev) cudaEventRecord(h->ev[3], st);
   DecodeTcPlan dpl;
-  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && decode_tc_plan(H, J, c.vocab_sz, B, h->sm_count, &dpl)) {
+  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && decode_tc_plan(H, J, c.vocab_sz, c.pred_layers, B, h->sm_count, &dpl)) {
     const size_t one = (size_t)(std::max(H, J) / 64) * 2 * dpl.Bpad8 * 128;
     const int nimg = 4 + 2 * c.pred_layers;
     CK(h->dimg.ensure(one * nimg));

@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
   uint64_t* tfull = empty + S;
   uint64_t* tempty = tfull + 1;
   uint64_t* ctlbar = tempty + 1;
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(ctlbar + 1);
+  uint64_t* tfull_r = ctlbar + 1;    // speculative recurrent products (all predictor layers) complete
+  uint64_t* tempty_r = tfull_r + 1;  // ... and drained by the predictor phases that consumed them
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(tempty_r + 1);
   const int nB = (V + p.NC_B - 1) / p.NC_B;                     // CTAs that produce a softmax partial
 
   if (threadIdx.x == 0) {
@@ -118,6 +120,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     mbar_init(tfull, 1);
     mbar_init(tempty, 128);
     mbar_init(ctlbar, 1);
+    mbar_init(tfull_r, 1);
+    mbar_init(tempty_r, 128);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tptr, p.tmem_cols);
@@ -145,14 +149,19 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
       gm[0] = Gemm{p.z_img, wB, KBJ, p.NC_B, 0, 1};
       return 1;
     }
-    // predictor layer l: the recurrent product h_l * R_l only needs state written a whole predictor run ago, so it
-    // goes FIRST and ungated (it overlaps the previous phase's epilogue and barrier); the input product x * K_l
-    // (l > 0) needs BatchNorm(h_{l-1}) of this run.  TMEM columns: [0, 2NC) input product, [2NC, 4NC) recurrent.
+    // predictor layer l: only the input product x * K_l (l > 0), which needs BatchNorm(h_{l-1}) of this run; layer 0's
+    // input is a table row.  The recurrent products are speculative (rec_gemm below).
     const int l = phase - 2;
-    gm[0] = Gemm{p.h_img[l][par], p.r_img[l] + img_tile_offset(cta, 0, 0, KBH, p.NC_C), KBH, p.NC_C, l > 0 ? 2 * p.NC_C : 0, 0};
-    if (l == 0) return 1;
-    gm[1] = Gemm{p.x_img[(l - 1) & 1], p.k_img[l] + img_tile_offset(cta, 0, 0, KBH, p.NC_C), KBH, p.NC_C, 0, 1};
-    return 2;
+    if (l == 0) return 0;
+    gm[0] = Gemm{p.x_img[(l - 1) & 1], p.k_img[l] + img_tile_offset(cta, 0, 0, KBH, p.NC_C), KBH, p.NC_C, 0, 1};
+    return 1;
+  };
+  // The recurrent product h_l * R_l of every predictor layer depends only on state written by the PREVIOUS predictor
+  // run, so it is issued speculatively right after phase B's operands -- before the greedy rule of this step is known --
+  // into its own TMEM columns.  It overlaps B's epilogue, the barrier and the rule; when no utterance emits, the
+  // products stay valid (h unchanged) and are consumed by the next predictor run.
+  auto rec_gemm = [&](int l, int par) -> Gemm {
+    return Gemm{p.h_img[l][par], p.r_img[l] + img_tile_offset(cta, 0, 0, KBH, p.NC_C), KBH, p.NC_C, p.rec_col0 + l * p.rec_cols, 0};
   };
 
   if (warp == 0 || warp == 6) {
@@ -163,55 +172,69 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     const bool acts = warp == 0;
     uint32_t g = 0;
     unsigned nbar = 1;   // grid barriers to wait for before a phase reads activations (1 = initial images)
+    unsigned seen = 0;   // highest grid-barrier count this warp has observed
+    auto gate = [&](unsigned n) {
+      if (acts && seen < n) {
+        while (ld_acquire_u32(p.barrier) < n * (unsigned)G) {
+        }
+        fence_proxy_async_global();
+        seen = n;
+      }
+    };
+    auto run_gemm = [&](const Gemm& gq) {
+      const uint32_t wkb = (uint32_t)gq.NC * 256;
+      for (int kb0 = 0; kb0 < gq.KB; kb0 += KPS, ++g) {
+        const int s = g % S;
+        const uint32_t ph = (g / S) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one()) {
+          const int nkb = min(KPS, gq.KB - kb0);
+          uint8_t* dst = ring + (size_t)s * stage_bytes;
+          if (acts) {
+            mbar_arrive_expect_tx(&full[s], (uint32_t)nkb * xkb);
+            tma_bulk_g2s(dst, gq.act + (size_t)kb0 * xkb, (uint32_t)nkb * xkb, &full[s]);
+          } else {
+            mbar_arrive_expect_tx(&fullw[s], (uint32_t)nkb * wkb);
+            tma_bulk_g2s(dst + KPS * xkb, gq.w + (size_t)kb0 * wkb, (uint32_t)nkb * wkb, &fullw[s]);
+          }
+        }
+        __syncwarp();
+      }
+    };
     auto run_phase = [&](int phase, int par) {
       Gemm gm[2];
       const int ng = phase_gemms(phase, par, gm);
       for (int q = 0; q < ng; ++q) {
-        if (acts && gm[q].gated) {
-          while (ld_acquire_u32(p.barrier) < nbar * (unsigned)G) {
-          }
-          fence_proxy_async_global();
-        }
-        const uint32_t wkb = (uint32_t)gm[q].NC * 256;
-        for (int kb0 = 0; kb0 < gm[q].KB; kb0 += KPS, ++g) {
-          const int s = g % S;
-          const uint32_t ph = (g / S) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          if (elect_one()) {
-            const int nkb = min(KPS, gm[q].KB - kb0);
-            uint8_t* dst = ring + (size_t)s * stage_bytes;
-            if (acts) {
-              mbar_arrive_expect_tx(&full[s], (uint32_t)nkb * xkb);
-              tma_bulk_g2s(dst, gm[q].act + (size_t)kb0 * xkb, (uint32_t)nkb * xkb, &full[s]);
-            } else {
-              mbar_arrive_expect_tx(&fullw[s], (uint32_t)nkb * wkb);
-              tma_bulk_g2s(dst + KPS * xkb, gm[q].w + (size_t)kb0 * wkb, (uint32_t)nkb * wkb, &fullw[s]);
-            }
-          }
-          __syncwarp();
-        }
+        if (gm[q].gated) gate(nbar);
+        run_gemm(gm[q]);
       }
       ++nbar;
     };
+    unsigned hgate = 1;   // barrier count after which the current h images are complete
+    auto run_spec = [&](int par) {
+      gate(hgate);
+      for (int l = 0; l < Lp; ++l) run_gemm(rec_gemm(l, par));
+    };
     int par = 0;
-    if (acts) {   // the initial operand images (written by every CTA's epilogue warps) precede even the ungated GEMMs
-      while (ld_acquire_u32(p.barrier) < (unsigned)G) {
-      }
-      fence_proxy_async_global();
-    }
+    gate(1);   // the initial operand images (written by every CTA's epilogue warps) precede even the ungated GEMMs
     if (!p.use_state_in) {
+      run_spec(par);
       for (int l = 0; l < Lp; ++l) run_phase(2 + l, par);
       par ^= 1;
+      hgate = nbar;
     }
-    bool any_upd = true;
+    bool any_upd = true, spec_valid = false;
     for (int step = 0;; ++step) {
       if (any_upd) run_phase(0, par); else ++nbar;
       run_phase(1, par);
+      if (!spec_valid) { run_spec(par); spec_valid = true; }
       mbar_wait(ctlbar, step & 1);
       const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
       if (any_emit) {
         for (int l = 0; l < Lp; ++l) run_phase(2 + l, par);
         par ^= 1;
+        hgate = nbar;
+        spec_valid = false;
       }
       any_upd = any_emit;
       if (!any_active) break;
@@ -221,62 +244,71 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     const uint64_t a_desc0 = umma_desc_sw128(smem_u32(ring));
     const uint64_t b_desc0 = umma_desc_sw128(smem_u32(ring) + KPS * xkb);
     const uint32_t stage_u = stage_bytes >> 4, xkb_u = xkb >> 4;
-    uint32_t g = 0, nacc = 0;
+    uint32_t g = 0, nacc = 0, nspec = 0;
+    // issue one GEMM into its TMEM columns; `done` (nullable) is committed with the last stage
+    auto run_gemm = [&](const Gemm& gq, uint64_t* done) {
+      const uint32_t idesc = umma_idesc_f16(MM, 2 * gq.NC);
+      const uint32_t wkb_u = ((uint32_t)gq.NC * 256) >> 4;
+      const uint32_t dcol = tmem + (uint32_t)gq.col;
+      for (int kb0 = 0; kb0 < gq.KB; kb0 += KPS, ++g) {
+        const int s = g % S;
+        const uint32_t ph = (g / S) & 1;
+        mbar_wait(&fullw[s], ph);
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const int nkb = min(KPS, gq.KB - kb0);
+          uint64_t ad = a_desc0 + (uint64_t)(s * stage_u);
+          uint64_t bd = b_desc0 + (uint64_t)(s * stage_u);
+          uint32_t accumulate = kb0 == 0 ? 0u : 1u;
+          for (int i = 0; i < nkb; ++i) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              tc_mma_f16(dcol, ad + 2 * k4, bd + 2 * k4, idesc, accumulate);
+              accumulate = 1u;
+            }
+            ad += xkb_u;
+            bd += wkb_u;
+          }
+          tc_commit(&empty[s]);
+          if (done && kb0 + KPS >= gq.KB) tc_commit(done);
+        }
+        __syncwarp();
+      }
+    };
     auto run_phase = [&](int phase, int par) {
       Gemm gm[2];
       const int ng = phase_gemms(phase, par, gm);
       if (ng == 0) return;
-      // the previous phase's accumulators must be drained before they are overwritten; the ungated recurrent GEMM
-      // of predictor layer 1 targets columns [2NC, 4NC) that layer 0's drain never reads, so it may start early
-      const bool early = phase == 3 && ng == 2;
-      for (int q = 0; q < ng; ++q) {
-        if (nacc > 0 && ((q == 0 && !early) || (q == 1 && early))) mbar_wait(tempty, (nacc - 1) & 1);
-        tc_fence_after();
-        const uint32_t idesc = umma_idesc_f16(MM, 2 * gm[q].NC);
-        const uint32_t wkb_u = ((uint32_t)gm[q].NC * 256) >> 4;
-        const uint32_t dcol = tmem + (uint32_t)gm[q].col;
-        for (int kb0 = 0; kb0 < gm[q].KB; kb0 += KPS, ++g) {
-          const int s = g % S;
-          const uint32_t ph = (g / S) & 1;
-          mbar_wait(&fullw[s], ph);
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          if (elect_one()) {
-            const int nkb = min(KPS, gm[q].KB - kb0);
-            uint64_t ad = a_desc0 + (uint64_t)(s * stage_u);
-            uint64_t bd = b_desc0 + (uint64_t)(s * stage_u);
-            uint32_t accumulate = kb0 == 0 ? 0u : 1u;
-            for (int i = 0; i < nkb; ++i) {
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                tc_mma_f16(dcol, ad + 2 * k4, bd + 2 * k4, idesc, accumulate);
-                accumulate = 1u;
-              }
-              ad += xkb_u;
-              bd += wkb_u;
-            }
-            tc_commit(&empty[s]);
-            if (q == ng - 1 && kb0 + KPS >= gm[q].KB) tc_commit(tfull);
-          }
-          __syncwarp();
-        }
-      }
+      // the previous phase's accumulators must be drained before they are overwritten
+      if (nacc > 0) mbar_wait(tempty, (nacc - 1) & 1);
+      tc_fence_after();
+      for (int q = 0; q < ng; ++q) run_gemm(gm[q], q == ng - 1 ? tfull : nullptr);
       ++nacc;
+    };
+    auto run_spec = [&](int par) {   // the recurrent columns are free once the predictor run that read them has drained
+      if (nspec > 0) mbar_wait(tempty_r, (nspec - 1) & 1);
+      tc_fence_after();
+      for (int l = 0; l < Lp; ++l) run_gemm(rec_gemm(l, par), l == Lp - 1 ? tfull_r : nullptr);
+      ++nspec;
     };
     int par = 0;
     if (!p.use_state_in) {
+      run_spec(par);
       for (int l = 0; l < Lp; ++l) run_phase(2 + l, par);
       par ^= 1;
     }
-    bool any_upd = true;
+    bool any_upd = true, spec_valid = false;
     for (int step = 0;; ++step) {
       if (any_upd) run_phase(0, par);
       run_phase(1, par);
+      if (!spec_valid) { run_spec(par); spec_valid = true; }
       mbar_wait(ctlbar, step & 1);
       const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
       if (any_emit) {
         for (int l = 0; l < Lp; ++l) run_phase(2 + l, par);
         par ^= 1;
+        spec_valid = false;
       }
       any_upd = any_emit;
       if (!any_active) break;
@@ -299,20 +331,18 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
       c.tok[i] = w.bos; c.active[i] = len > 0; c.emit[i] = i < B;
     }
 
-    // TMEM accumulator rows -> exchange buffers (row r < Bpad8: hi row of batch r, else lo row of batch r - Bpad8)
-    auto drain = [&](int ncols /*multiple of 8*/) {
-      mbar_wait(tfull, nacc & 1);
-      tc_fence_after();
+    // TMEM accumulator rows -> exchange buffers (row r < Bpad8: hi row of batch r, else lo row of batch r - Bpad8).
+    // A GEMM with NC rows occupies 2*NC columns: [0,NC) x*hi, [NC,2NC) x*lo.
+    auto copy_cols = [&](int tcol, int ncols /*multiple of 8*/, int dstoff) {
       const int r = q * rows_per_warp + lane;
       if (q * rows_per_warp < 2 * p.Bpad8) {
         const bool mine = lane < rows_per_warp && r < 2 * p.Bpad8;
         const bool is_lo = r >= p.Bpad8;
-        float* dstrow = is_lo ? pre_lo + (r - p.Bpad8) * prs : pre_hi + r * prs;
+        float* dstrow = (is_lo ? pre_lo + (r - p.Bpad8) * prs : pre_hi + r * prs) + dstoff;
         const float sc = is_lo ? kLoInv : 1.0f;
-        // a GEMM with NC rows occupies 2*NC columns: [0,NC) x*hi, [NC,2NC) x*lo
         for (int c0 = 0; c0 < ncols; c0 += 16) {
           float d[16];
-          tmem_ld16(tlane + c0, d);
+          tmem_ld16(tlane + (uint32_t)(tcol + c0), d);
           tmem_ld_wait();
           if (mine) {
 #pragma unroll
@@ -321,9 +351,29 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
           }
         }
       }
+    };
+    auto drain = [&](int ncols) {   // the phase GEMM at column 0
+      mbar_wait(tfull, nacc & 1);
+      tc_fence_after();
+      copy_cols(0, ncols, 0);
       tc_fence_before();
       mbar_arrive(tempty);
       ++nacc;
+      named_bar_sync(1, 128);
+    };
+    uint32_t nspec = 0;
+    // predictor layer l: input product (l > 0, column 0 -> exchange [0, 2NC)) and the speculative recurrent product
+    // (its own columns -> exchange [2NC, 4NC))
+    auto drain_pred = [&](int l) {
+      const int NC = p.NC_C;
+      if (l == 0) mbar_wait(tfull_r, nspec & 1);
+      if (l > 0) mbar_wait(tfull, nacc & 1);
+      tc_fence_after();
+      if (l > 0) copy_cols(0, 2 * NC, 0);
+      copy_cols(p.rec_col0 + l * p.rec_cols, 2 * NC, 2 * NC);
+      tc_fence_before();
+      if (l > 0) { mbar_arrive(tempty); ++nacc; }
+      if (l == Lp - 1) { mbar_arrive(tempty_r); ++nspec; }
       named_bar_sync(1, 128);
     };
     // value of GEMM `gi` (NC rows at TMEM column base gi*2*NC), row `rr`, batch b:  hi-row and lo-row pieces summed
@@ -410,8 +460,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
           }
         }
       }
-      drain((l > 0 ? 4 : 2) * NC);
-      const int gh = (l > 0) ? 2 * NC : 0;   // column base of the recurrent GEMM (after the input GEMM for l > 0)
+      drain_pred(l);
+      const int gh = 2 * NC;   // exchange column base of the recurrent product
       float xo[DT_MAX_RPT];
       if (bvalid) {
 #pragma unroll
@@ -669,7 +719,7 @@ bool decode_tc_wplan(int H, int J, int V, int sms, DecodeTcPlan* pl) {
   return 2 * pl->NC_max <= 256;
 }
 
-bool decode_tc_plan(int H, int J, int V, int B, int sms, DecodeTcPlan* pl) {
+bool decode_tc_plan(int H, int J, int V, int Lp, int B, int sms, DecodeTcPlan* pl) {
   if (B < 1 || B > DT_MAXB) return false;
   if (!decode_tc_wplan(H, J, V, sms, pl)) return false;
   pl->Bpad8 = (int)round_up(B, 8);
@@ -680,9 +730,13 @@ bool decode_tc_plan(int H, int J, int V, int B, int sms, DecodeTcPlan* pl) {
     if ((n * pl->Bq) % 128) return false;
     if (n * pl->Bq / 128 > DT_MAX_RPT) return false;
   }
+  // TMEM columns: [0, rec_col0) the phase GEMM (A, B or a predictor layer's input product), then one block of
+  // rec_cols per predictor layer for the speculative recurrent products
+  pl->rec_col0 = (int)round_up(2 * pl->NC_max, 16);
+  pl->rec_cols = (int)round_up(2 * pl->NC_C, 16);
   int cols = 32;
-  while (cols < 4 * pl->NC_max) cols *= 2;
-  if (cols > 512) return false;
+  while (cols < pl->rec_col0 + Lp * pl->rec_cols) cols *= 2;
+  if (Lp < 1 || Lp > kMaxPredLayers || cols > 512) return false;
   pl->tmem_cols = cols;
   const size_t xkb = (size_t)2 * pl->Bpad8 * 128, wmax = (size_t)pl->NC_max * 256;
   const size_t guard = (size_t)pl->mma_m * 128;
@@ -711,6 +765,7 @@ cudaError_t launch_decode_tc(const DecodeTcArgs& a, const DecodeTcPlan& pl, cuda
   args.Uc = pl.Uc; args.NC_A = pl.NC_A; args.NC_B = pl.NC_B; args.NC_C = pl.NC_C; args.NC_max = pl.NC_max;
   args.Bpad8 = pl.Bpad8; args.Bq = pl.Bq; args.mma_m = pl.mma_m; args.kps = pl.kps; args.stages = pl.stages;
   args.pre_offset = pl.pre_offset; args.ctl_offset = pl.ctl_offset; args.bar_offset = pl.bar_offset; args.tmem_cols = pl.tmem_cols;
+  args.rec_col0 = pl.rec_col0; args.rec_cols = pl.rec_cols;
   void* kargs[] = {&args};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)decode_tc_kernel, dim3(pl.G), dim3(DT_THREADS), kargs, pl.smem_bytes, st);
   if (e != cudaSuccess) return e;

@@ -144,7 +144,7 @@ cudaError_t launch_decode(const DecodeArgs& a, int grid_blocks, cudaStream_t st)
 // ---------------- decode_tc.cu (tcgen05 greedy decode) ----------------
 struct DecodeTcPlan {
   int G, Uc, NC_A, NC_B, NC_C, NC_max;                 // weight-side plan (batch independent)
-  int Bpad8, Bq, mma_m, kps, stages, pre_offset, ctl_offset, bar_offset, smem_bytes, tmem_cols;
+  int Bpad8, Bq, mma_m, kps, stages, pre_offset, ctl_offset, bar_offset, smem_bytes, tmem_cols, rec_col0, rec_cols;
 };
 struct DecodeTcArgs {
   DecodeWeights w;                 // fp32 vectors / tables (table0, biases, h0, BatchNorm, b2)
@@ -166,11 +166,11 @@ struct DecodeTcArgs {
   unsigned int* barrier;           // grid phase counter, zero at launch
   unsigned long long* dbg; int dbg_cap;   // optional (time, tag) trail of CTA 0 (tuning aid)
   // filled from the plan by the launcher
-  int Uc, NC_A, NC_B, NC_C, NC_max, Bpad8, Bq, mma_m, kps, stages, pre_offset, ctl_offset, bar_offset, tmem_cols;
+  int Uc, NC_A, NC_B, NC_C, NC_max, Bpad8, Bq, mma_m, kps, stages, pre_offset, ctl_offset, bar_offset, tmem_cols, rec_col0, rec_cols;
 };
 cudaError_t configure_decode_tc();
 bool decode_tc_wplan(int H, int J, int V, int sms, DecodeTcPlan* pl);
-bool decode_tc_plan(int H, int J, int V, int B, int sms, DecodeTcPlan* pl);
+bool decode_tc_plan(int H, int J, int V, int Lp, int B, int sms, DecodeTcPlan* pl);
 cudaError_t launch_decode_tc(const DecodeTcArgs& a, const DecodeTcPlan& pl, cudaStream_t st);
 
 // standalone predictor step / joint (same phase code, one launch per phase)

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_layer_tc_kernel(LstmTcArgs
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cta = blockIdx.x, G = gridDim.x;
+  const int cta = blockIdx.x;
   const int NC = p.NC, U = p.U, KB = p.KB, S = p.stages, KPS = p.kps, MM = p.mma_m;
   constexpr bool fused = FUSED;                          // hi and lo rows of the batch share one A tile
   const uint32_t xr = (uint32_t)p.Bpad8 * 128;          // valid rows of one part of an h tile
