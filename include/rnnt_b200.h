@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RNNT_B200_ABI_VERSION 1
+#define RNNT_B200_ABI_VERSION 2
 
 typedef struct rnnt_b200_handle_s* rnnt_b200_handle;
 
@@ -73,9 +73,14 @@ typedef struct rnnt_b200_config {
   int32_t bos;           /* models.py:226-227 -> 2 */
   int32_t device;        /* CUDA device ordinal */
   int32_t gemm_mode;     /* rnnt_b200_gemm_mode */
+  int32_t lm_layers;     /* lm.num_layers (config/testing.yaml:293-299,306-313); 0 = no fused LM (m.lm is None) */
+  int32_t lm_hidden_sz;  /* lm.hidden_sz */
+  int32_t lm_embed_sz;   /* lm.embed_sz (== lm_hidden_sz ties the output projection to the embedding, lm.py:27-29) */
   float log_offset;      /* transforms.py:312 -> 1e-6 */
   float ln_eps;          /* nn.LayerNorm default 1e-5 (models.py:84) */
   float bn_eps;          /* nn.BatchNorm1d default 1e-5 (custom_rnn.py:124) */
+  float lm_alpha;        /* lm.py:13 ALPHA = 0.1 (the decode loops call fuse() with its defaults, models.py:431,558) */
+  float lm_theta;        /* lm.py:14 THETA = 1.0 */
 } rnnt_b200_config;
 
 /* ---- lifecycle ---------------------------------------------------------------- */
@@ -100,8 +105,11 @@ const char* rnnt_b200_last_error(rnnt_b200_handle h);
  * "encoder.rnn_stack.rnns.0.weight_ih_l0", "predictor.rnn_stack.rnns.1.recurrent_kernel",
  * "joint.joint.2.bias", ...) plus two front-end tensors that the reference builds inside
  * torchaudio (transforms.py:290-296): "frontend.window" [win_length] and
- * "frontend.mel_fb" [n_fft/2+1, n_mels].  `data` is HOST fp32, copied before return.
- * Unknown names and wrong element counts return ERR_INVALID. */
+ * "frontend.mel_fb" [n_fft/2+1, n_mels].  With cfg.lm_layers > 0 the fused language model's
+ * state_dict (lm.py:20-29, loaded by load_lm, lm.py:86-101) is passed under the prefix "lm.":
+ * "lm.embed.weight", "lm.rnn.weight_ih_l{k}", "lm.rnn.weight_hh_l{k}", "lm.rnn.bias_ih_l{k}",
+ * "lm.rnn.bias_hh_l{k}", "lm.linear.weight", "lm.linear.bias".  `data` is HOST fp32, copied
+ * before return.  Unknown names and wrong element counts return ERR_INVALID. */
 int32_t rnnt_b200_set_weight(rnnt_b200_handle h, const char* name, const float* data_host, int64_t numel);
 
 /* Repacks the weights into kernel layouts (gate interleave, transposes, BatchNorm
@@ -167,6 +175,22 @@ int32_t rnnt_b200_predict(rnnt_b200_handle h, const int32_t* tokens_dev, int32_t
  * no softmax.  h_pred_dev, h_enc_dev [B, H]; logits_dev [B, V]. */
 int32_t rnnt_b200_joint(rnnt_b200_handle h, const float* h_pred_dev, const float* h_enc_dev,
                         int32_t B, float* logits_dev, void* stream);
+
+/* ---- LM shallow fusion: a16 (LMFuser, lm.py:43-83) ---------------------------------------- */
+
+/* With cfg.lm_layers > 0 every greedy decode (decode_greedy / transcribe*) fuses the language
+ * model exactly where the reference does: after the blank test, the joint's log_softmax row is
+ * standardised ((x - mean) / (std + 1e-5), utils.py:162-164), its blank entry pinned to -10, and
+ * the emitted token is arg max(lm_alpha * lm_row + lm_theta * joint_row) (lm.py:56-79); after each
+ * emitted token the LM advances one step and its standardised row replaces lm_row (lm.py:50-54);
+ * until the first emission there is no lm_row and the joint's arg max stands (lm.py:58,79).
+ * By default each call starts from a fresh fuser (models.py:401).  A streaming caller
+ * (transcribe_stream keeps one fuser for the whole stream, models.py:478) registers a
+ * caller-owned DEVICE blob that carries (h, c) of every LM layer, lm_row and its validity for
+ * B streams between calls; a zero-filled blob is a fresh fuser (LMFuser.reset, lm.py:81-83).
+ * The blob layout is private; size it with rnnt_b200_lm_state_bytes.  NULL unregisters. */
+int32_t rnnt_b200_lm_state_bytes(rnnt_b200_handle h, int32_t B, int64_t* bytes_out);
+int32_t rnnt_b200_set_lm_state(rnnt_b200_handle h, void* blob_dev, int32_t B);
 
 /* ---- greedy decode: a13 / a14 inner loop ---------------------------------------------- */
 

@@ -22,7 +22,9 @@ class Config(C.Structure):
         ("enc_layers", C.c_int32), ("pred_layers", C.c_int32),
         ("hidden_sz", C.c_int32), ("embed_sz", C.c_int32), ("joint_sz", C.c_int32), ("vocab_sz", C.c_int32),
         ("blank", C.c_int32), ("bos", C.c_int32), ("device", C.c_int32), ("gemm_mode", C.c_int32),
+        ("lm_layers", C.c_int32), ("lm_hidden_sz", C.c_int32), ("lm_embed_sz", C.c_int32),
         ("log_offset", C.c_float), ("ln_eps", C.c_float), ("bn_eps", C.c_float),
+        ("lm_alpha", C.c_float), ("lm_theta", C.c_float),
     ]
 
 
@@ -48,6 +50,8 @@ SIGNATURES = {
     "rnnt_b200_encode": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "rnnt_b200_predict": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "rnnt_b200_joint": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
+    "rnnt_b200_lm_state_bytes": (_i32, [_vp, _i32, C.POINTER(_i64)]),
+    "rnnt_b200_set_lm_state": (_i32, [_vp, _vp, _i32]),
     "rnnt_b200_decode_greedy": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "rnnt_b200_transcribe": (_i32, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "rnnt_b200_transcribe_host": (_i32, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),

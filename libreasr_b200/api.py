@@ -76,10 +76,14 @@ class StreamBatch:
         self.rows = []
         self.enc_state = None
         self.pred_state = None
+        # one LM fuser per stream (models.py:478), resident on the device like the other stream state
+        self.lm_state = engine.new_lm_state(n_streams) if cfg.lm_layers > 0 else None
         self.tokens = [[] for _ in range(n_streams)]
 
     def reset(self):
         self.enc_state, self.pred_state = None, None
+        if self.lm_state is not None:
+            self.lm_state.zero_()  # LMFuser.reset (lm.py:81-83)
 
     def push(self, chunks):
         """chunks [B, chunk] CUDA tensor.  Returns the list of new token lists when the
@@ -96,7 +100,7 @@ class StreamBatch:
         feats = torch.stack(self.rows, dim=1)  # [B, n_buffer, X]
         self.rows.clear()
         enc, self.enc_state = self.engine.encode(feats, state=self.enc_state, want_state=True)
-        r = self.engine.decode_greedy(enc, max_iters=self.max_iters, state=self.pred_state, want_state=True)
+        r = self.engine.decode_greedy(enc, max_iters=self.max_iters, state=self.pred_state, want_state=True, lm_state=self.lm_state)
         self.pred_state = r["state"]
         new = tokens_to_lists(r["tokens"], r["ntok"])
         for b in range(self.B):

@@ -81,6 +81,11 @@ struct rnnt_b200_handle_s {
   // workspaces
   DevBuf feats, lnx, xp, ya, yb, ep, ehT[2], ecT, dhT, dxT, dgT, deT, dppT, dzT, dpart, dlse;
   DevBuf t_audio, t_lens, t_tokens, t_ntok, t_nlp, t_iters, t_enc;
+  // fused language model (lm.py): fp32 layouts + per-call fuser workspace / registered stream blob
+  LmWeights lmw;
+  DevBuf lm_ws, lm_logitT, lm_part, lm_jpart, lm_fpart;
+  float* lm_blob = nullptr;   // caller-owned fuser state (rnnt_b200_set_lm_state); nullptr = fresh fuser per call
+  int lm_blob_B = 0;
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t*> evsets;  // one set of events per profiled transcribe() call: 6 stage marks + 2 per encoder layer
@@ -152,6 +157,25 @@ int64_t expected_numel(const rnnt_b200_config& c, const std::string& name, bool*
   if (name == "joint.joint.0.bias") return J;
   if (name == "joint.joint.2.weight") return V * J;
   if (name == "joint.joint.2.bias") return V;
+  if (c.lm_layers > 0 && name.compare(0, 3, "lm.") == 0) {   // LM.state_dict() keys (lm.py:20-29)
+    const int64_t Hl = c.lm_hidden_sz, El = c.lm_embed_sz;
+    const std::string rest = name.substr(3);
+    if (rest == "embed.weight") return V * El;
+    if (rest == "linear.weight") return V * Hl;
+    if (rest == "linear.bias") return V;
+    const size_t pos = rest.rfind("_l");
+    if (rest.compare(0, 4, "rnn.") == 0 && pos != std::string::npos && pos > 4 && pos + 2 < rest.size()) {
+      const std::string f = rest.substr(4, pos - 4), num = rest.substr(pos + 2);
+      int idx = 0;
+      bool digits = true;
+      for (char ch : num) { digits = digits && ch >= '0' && ch <= '9'; idx = idx * 10 + (ch - '0'); }
+      if (digits && num.size() <= 2 && idx < c.lm_layers) {
+        if (f == "weight_ih") return 4 * Hl * (idx == 0 ? El : Hl);
+        if (f == "weight_hh") return 4 * Hl * Hl;
+        if (f == "bias_ih" || f == "bias_hh") return 4 * Hl;
+      }
+    }
+  }
   for (int side = 0; side < 2; ++side) {
     const std::string pre = side == 0 ? "encoder.rnn_stack." : "predictor.rnn_stack.";
     if (name.compare(0, pre.size(), pre) != 0) continue;
@@ -198,6 +222,11 @@ int validate_config(const rnnt_b200_config& c, std::string* why) {
   if (c.enc_layers < 1 || c.enc_layers > 16) return bad("enc_layers must be in [1, 16]");
   if (c.pred_layers < 1 || c.pred_layers > kMaxPredLayers) return bad("pred_layers must be in [1, 4]");
   if (c.blank < 0 || c.blank >= c.vocab_sz || c.bos < 0 || c.bos >= c.vocab_sz) return bad("blank/bos out of range");
+  if (c.lm_layers < 0 || c.lm_layers > kMaxLmLayers) return bad("lm_layers must be in [0, 8]");
+  if (c.lm_layers > 0) {
+    if (c.lm_hidden_sz < 64 || c.lm_hidden_sz % 64) return bad("lm_hidden_sz must be a positive multiple of 64");
+    if (c.lm_embed_sz < 4 || c.lm_embed_sz % 4) return bad("lm_embed_sz must be a positive multiple of 4");
+  }
   if (c.gemm_mode != RNNT_B200_GEMM_FP32_SIMT && c.gemm_mode != RNNT_B200_GEMM_TC_FP16X3)
     return bad("gemm_mode not available in this build (0 = fp32 CUDA cores, 1 = tcgen05 3xFP16)");
   return 0;
@@ -219,6 +248,8 @@ int32_t rnnt_b200_default_config(rnnt_b200_config* c) {
   c->enc_layers = 6; c->pred_layers = 2; c->hidden_sz = 1024; c->embed_sz = 512; c->joint_sz = 1024; c->vocab_sz = 2048;
   c->blank = 0; c->bos = 2; c->device = 0; c->gemm_mode = RNNT_B200_GEMM_TC_FP16X3;
   c->log_offset = 1e-6f; c->ln_eps = 1e-5f; c->bn_eps = 1e-5f;
+  c->lm_layers = 0; c->lm_hidden_sz = 768; c->lm_embed_sz = 768;   // LM off; shapes of the shipped override (testing.yaml:306-313)
+  c->lm_alpha = 0.1f; c->lm_theta = 1.0f;                           // lm.py:13-14
   return RNNT_B200_OK;
 }
 
@@ -261,7 +292,8 @@ int32_t rnnt_b200_destroy(rnnt_b200_handle h) {
   for (void* p : h->weight_allocs) cudaFree(p);
   DevBuf* bufs[] = {&h->feats, &h->lnx, &h->xp, &h->ya, &h->yb, &h->ep, &h->ehT[0], &h->ehT[1], &h->ecT, &h->dhT, &h->dxT,
                     &h->dgT, &h->deT, &h->dppT, &h->dzT, &h->dpart, &h->dlse, &h->t_audio, &h->t_lens, &h->t_tokens,
-                    &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc, &h->a_img, &h->x_img[0], &h->x_img[1], &h->gbar, &h->dimg, &h->dkeys};
+                    &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc, &h->a_img, &h->x_img[0], &h->x_img[1], &h->gbar, &h->dimg, &h->dkeys,
+                    &h->lm_ws, &h->lm_logitT, &h->lm_part, &h->lm_jpart, &h->lm_fpart};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t* set : h->evsets) {
     for (int i = 0; i < kEvPerSet; ++i) cudaEventDestroy(set[i]);
@@ -554,6 +586,67 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
       }
     }
   }
+  // ---- fused language model (lm.py:20-41): fp32 k-major layouts for the decode loop's tile GEMMs ----
+  memset(&h->lmw, 0, sizeof(h->lmw));
+  if (c.lm_layers > 0) {
+    const int Hl = c.lm_hidden_sz, El = c.lm_embed_sz, Ll = c.lm_layers;
+    LmWeights& lw = h->lmw;
+    lw.L = Ll; lw.Hl = Hl; lw.alpha = c.lm_alpha; lw.theta = c.lm_theta;
+    int* lperm4 = nullptr;
+    {
+      std::vector<int> p4(4 * Hl);
+      for (int u = 0; u < Hl; ++u)
+        for (int g = 0; g < 4; ++g) p4[u * 4 + g] = g * Hl + u;
+      CK(upload(h, p4, &lperm4));
+    }
+    NEED(lemb, "lm.embed.weight");
+    NEED(lwo, "lm.linear.weight");
+    NEED(lbo, "lm.linear.bias");
+    for (int l = 0; l < Ll; ++l) {
+      const std::string sl = std::to_string(l);
+      NEED(wih, "lm.rnn.weight_ih_l" + sl);
+      NEED(whh, "lm.rnn.weight_hh_l" + sl);
+      NEED(bih, "lm.rnn.bias_ih_l" + sl);
+      NEED(bhh, "lm.rnn.bias_hh_l" + sl);
+      std::vector<float> bsum(4 * Hl);
+      for (int i = 0; i < 4 * Hl; ++i) bsum[i] = (*bih)[i] + (*bhh)[i];
+      float *d_whh, *d_r, *Rt;
+      CK(tmp_upload(*whh, &d_whh));
+      CK(tmp_alloc((size_t)4 * Hl * Hl, &d_r));
+      CK(dalloc(h, (size_t)4 * Hl * Hl, &Rt));
+      LAUNCH(1, launch_gather_rows(d_whh, d_r, lperm4, 4 * Hl, Hl, st));   // rows unit*4+gate
+      LAUNCH(1, launch_transpose(d_r, Hl, Rt, 4 * Hl, Hl, st));            // [Hl][4Hl interleaved]
+      lw.Rt[l] = Rt;
+      float* d_wih;
+      CK(tmp_upload(*wih, &d_wih));
+      if (l == 0) {
+        // table0 = embed * W_ih0^T + (b_ih0 + b_hh0)  -> [V][4Hl] gate-major (i|f|g|o)
+        float *d_emb, *d_b, *table;
+        CK(tmp_upload(*lemb, &d_emb));
+        CK(tmp_upload(bsum, &d_b));
+        CK(dalloc(h, (size_t)V * 4 * Hl, &table));
+        LAUNCH(1, launch_gemm_nt_f32(d_emb, El, d_wih, El, d_b, table, 4 * Hl, V, 4 * Hl, El, st));
+        lw.table0 = table;
+      } else {
+        float *d_a, *Wt, *t_b;
+        CK(tmp_alloc((size_t)4 * Hl * Hl, &d_a));
+        CK(dalloc(h, (size_t)4 * Hl * Hl, &Wt));
+        LAUNCH(1, launch_gather_rows(d_wih, d_a, lperm4, 4 * Hl, Hl, st));
+        LAUNCH(1, launch_transpose(d_a, Hl, Wt, 4 * Hl, Hl, st));
+        std::vector<float> bi(4 * Hl);
+        for (int u = 0; u < Hl; ++u)
+          for (int g = 0; g < 4; ++g) bi[u * 4 + g] = bsum[g * Hl + u];
+        CK(upload(h, bi, &t_b));
+        lw.Wt[l] = Wt; lw.bias[l] = t_b;
+      }
+    }
+    float *d_wo, *Wo_t, *t_bo;
+    CK(tmp_upload(*lwo, &d_wo));
+    CK(dalloc(h, (size_t)Hl * V, &Wo_t));
+    LAUNCH(1, launch_transpose(d_wo, Hl, Wo_t, V, Hl, st));   // [V][Hl] -> [Hl][V]
+    CK(upload(h, *lbo, &t_bo));
+    lw.Wo_t = Wo_t; lw.bo = t_bo;
+  }
 #undef NEED
   CK(cudaStreamSynchronize(st));
   for (void* p : tmp) cudaFree(p);
@@ -830,9 +923,10 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     // Utterances are independent: larger batches run as consecutive sub-batches of the kernel's capacity
     // (64 for the tcgen05 kernel, 256 for the fp32 one).  State tensors are [Lp, B, H], i.e. not sliceable
     // per sub-batch, so stateful (streaming) calls must fit one launch.
-    const int cap = (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok) ? 64 : kDecodeMaxBatch;
+    // With a fused language model the loop runs in the fp32 cooperative kernel (decode.cu), whatever gemm_mode says.
+    const int cap = (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && c.lm_layers == 0) ? 64 : kDecodeMaxBatch;
     if (B > cap) {
-      if (pred_state_h || pred_out || use_state_in)
+      if (pred_state_h || pred_out || use_state_in || h->lm_blob)
         return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: stateful calls are limited to " + std::to_string(cap) + " streams per call");
       for (int b0 = 0; b0 < B; b0 += cap) {
         const int nb = std::min(cap, B - b0);
@@ -862,7 +956,8 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
   }
   if (h->ev) cudaEventRecord(h->ev[3], st);
   DecodeTcPlan dpl;
-  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && decode_tc_plan(H, J, c.vocab_sz, c.pred_layers, B, h->sm_count, &dpl)) {
+  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && c.lm_layers == 0 &&
+      decode_tc_plan(H, J, c.vocab_sz, c.pred_layers, B, h->sm_count, &dpl)) {
     const size_t one = (size_t)(std::max(H, J) / 64) * 2 * dpl.Bpad8 * 128;
     const int nimg = 4 + 2 * c.pred_layers;
     CK(h->dimg.ensure(one * nimg));
@@ -942,12 +1037,55 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
   a.part = h->dpart.as<float>(); a.trace_lse = h->dlse.as<float>();
   a.tokens = tokens_out; a.U_cap = U_cap; a.ntok = ntok_out; a.neg_logp = neg_logp_out; a.iters = iters_out;
   a.trace = trace_logp; a.trace_cap = trace_logp ? trace_cap : 0;
+  if (c.lm_layers > 0) {   // LMFuser (lm.py:43-83): a fresh fuser per call unless the caller registered stream state
+    const int V = c.vocab_sz, Ll = c.lm_layers, Hl = c.lm_hidden_sz;
+    const size_t nfl = lm_state_floats(Ll, Hl, V, Bp);
+    float* blob = h->lm_blob;
+    if (blob) {
+      if (h->lm_blob_B != B) return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: the registered LM state was sized for " +
+                                                                      std::to_string(h->lm_blob_B) + " streams, call has " + std::to_string(B));
+    } else {
+      CK(h->lm_ws.ensure(nfl * 4));
+      CK(cudaMemsetAsync(h->lm_ws.p, 0, nfl * 4, st));
+      blob = h->lm_ws.as<float>();
+    }
+    const size_t ntile = (size_t)(V / 32) * Bp;
+    CK(h->lm_logitT.ensure((size_t)V * Bp * 4));
+    CK(h->lm_part.ensure(ntile * 2 * 8));
+    CK(h->lm_jpart.ensure(ntile * 2 * 8));
+    CK(h->lm_fpart.ensure(ntile * 2 * 4));
+    a.lm = h->lmw;
+    a.lms = lm_state_view(blob, Ll, Hl, V, Bp);
+    a.logitT = h->lm_logitT.as<float>();
+    a.lmpart = h->lm_part.as<double>();
+    a.jpart = h->lm_jpart.as<double>();
+    a.fpart = h->lm_fpart.as<float>();
+  }
   LAUNCH(1, launch_decode(a, h->coop_blocks, st));
   if (pred_state_h)
     for (int l = 0; l < c.pred_layers; ++l)
       LAUNCH(1, launch_state_from_T(a.hT[l][0], pred_state_h + (size_t)l * B * H, B, Bp, H, st));
   if (pred_out) LAUNCH(1, launch_state_from_T(h->dgT.as<float>(), pred_out, B, Bp, H, st));
   if (h->ev) cudaEventRecord(h->ev[4], st);
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_lm_state_bytes(rnnt_b200_handle h, int32_t B, int64_t* bytes_out) {
+  if (!h || !bytes_out) return fail(h, RNNT_B200_ERR_INVALID, "lm_state_bytes: null argument");
+  const rnnt_b200_config& c = h->cfg;
+  if (c.lm_layers < 1) return fail(h, RNNT_B200_ERR_STATE, "lm_state_bytes: the handle has no language model (cfg.lm_layers == 0)");
+  if (B < 1 || B > kDecodeMaxBatch) return fail(h, RNNT_B200_ERR_INVALID, "lm_state_bytes: B must be in [1, 256]");
+  *bytes_out = (int64_t)lm_state_floats(c.lm_layers, c.lm_hidden_sz, c.vocab_sz, bp_of(B)) * 4;
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_set_lm_state(rnnt_b200_handle h, void* blob_dev, int32_t B) {
+  if (!h) return RNNT_B200_ERR_INVALID;
+  if (!blob_dev) { h->lm_blob = nullptr; h->lm_blob_B = 0; return RNNT_B200_OK; }
+  if (h->cfg.lm_layers < 1) return fail(h, RNNT_B200_ERR_STATE, "set_lm_state: the handle has no language model (cfg.lm_layers == 0)");
+  if (B < 1 || B > kDecodeMaxBatch) return fail(h, RNNT_B200_ERR_INVALID, "set_lm_state: B must be in [1, 256]");
+  h->lm_blob = static_cast<float*>(blob_dev);
+  h->lm_blob_B = B;
   return RNNT_B200_OK;
 }
 

@@ -121,8 +121,43 @@ struct DecodeWeights {
   const float* b2;              // [V]
 };
 
+// Fused language model (reference libreasr/lib/lm.py:20-83); L == 0 means no LM.
+constexpr int kMaxLmLayers = 8;
+struct LmWeights {
+  int L, Hl;
+  float alpha, theta;
+  const float* table0;              // [V][4Hl] gate-major (i|f|g|o): embed * W_ih0^T + b_ih0 + b_hh0
+  const float* Wt[kMaxLmLayers];    // layers >= 1: [Hl][4Hl] k-major, columns unit*4 + gate
+  const float* Rt[kMaxLmLayers];    // [Hl][4Hl] k-major interleaved
+  const float* bias[kMaxLmLayers];  // layers >= 1: [4Hl] interleaved (b_ih + b_hh)
+  const float* rbias0;              // unused (layer 0's biases live in table0)
+  const float* Wo_t;                // [Hl][V] k-major output projection
+  const float* bo;                  // [V]
+};
+// Per-stream fuser state, feature-major like the predictor state; all zero = fresh fuser (lm.py:81-83).
+// Layout of the blob (floats): h [L][2][Hl][Bp] | c [L][Hl][Bp] | logits [V][Bp] | stats [2][Bp] | valid [Bp]
+struct LmState {
+  float* h; float* c; float* logits; float* stats; float* valid;
+};
+inline size_t lm_state_floats(int L, int Hl, int V, int Bp) { return ((size_t)3 * L * Hl + V + 3) * Bp; }
+inline LmState lm_state_view(float* blob, int L, int Hl, int V, int Bp) {
+  LmState s;
+  s.h = blob;
+  s.c = s.h + (size_t)2 * L * Hl * Bp;
+  s.logits = s.c + (size_t)L * Hl * Bp;
+  s.stats = s.logits + (size_t)V * Bp;
+  s.valid = s.stats + (size_t)2 * Bp;
+  return s;
+}
+
 struct DecodeArgs {
   DecodeWeights w;
+  LmWeights lm;
+  LmState lms;            // fuser state (workspace zeroed by the caller, or the registered stream blob)
+  float* logitT;          // [V][Bp] joint logits of the current evaluation (LM fusion only)
+  double* lmpart;         // [V/32][Bp][2] per-tile (sum, sum of squares) of the LM logits
+  double* jpart;          // [V/32][Bp][2] ... of the joint logits of the current evaluation
+  float* fpart;           // [V/32][Bp][2] per-tile (max, argmax) of the fused scores
   const float* ep;        // [B][T][J] enc half projection incl. b1
   const int32_t* lens_T;  // [B] or nullptr
   int B, Bp, T, max_iters, use_state_in;

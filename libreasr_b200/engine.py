@@ -37,6 +37,12 @@ class EngineConfig:
     log_offset: float = 1e-6
     ln_eps: float = 1e-5
     bn_eps: float = 1e-5
+    # fused language model (config/testing.yaml:293-313, lm.py); lm_layers == 0: no LM (``m.lm is None``)
+    lm_layers: int = 0
+    lm_hidden_sz: int = 768
+    lm_embed_sz: int = 768
+    lm_alpha: float = 0.1
+    lm_theta: float = 1.0
 
     @property
     def feature_sz(self):
@@ -55,6 +61,9 @@ class EngineConfig:
             enc_layers=m["encoder"]["num_layers"], pred_layers=m["predictor"]["num_layers"],
             hidden_sz=m["hidden_sz"], embed_sz=m["embed_sz"], joint_sz=m["joint_sz"], vocab_sz=m["vocab_sz"],
         )
+        lm = conf.get("lm") or {}
+        if lm.get("enable"):  # config/testing.yaml:293-299 (+ the per-language override :306-313)
+            kw.update(lm_layers=lm["num_layers"], lm_hidden_sz=lm["hidden_sz"], lm_embed_sz=lm["embed_sz"])
         kw.update(over)
         return EngineConfig(**kw)
 
@@ -100,7 +109,7 @@ class Engine:
         self.lib.rnnt_b200_default_config(C.byref(c))
         for k in ("n_mels", "n_stack", "downsample", "enc_layers", "pred_layers", "hidden_sz", "embed_sz", "joint_sz",
                   "vocab_sz", "blank", "bos", "sample_rate", "n_fft", "win_length", "hop_length", "gemm_mode",
-                  "log_offset", "ln_eps", "bn_eps"):
+                  "log_offset", "ln_eps", "bn_eps", "lm_layers", "lm_hidden_sz", "lm_embed_sz", "lm_alpha", "lm_theta"):
             setattr(c, k, getattr(cfg, k))
         c.device = self.device.index or 0
         self._h = C.c_void_p(0)
@@ -127,11 +136,16 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def load_state_dict(self, sd):
+    def load_state_dict(self, sd, lm_state_dict=None):
         """``sd``: reference ``state_dict`` (name -> tensor / ndarray).  Adds the two
-        front-end tensors (hann window, mel filterbank) and finalizes."""
+        front-end tensors (hann window, mel filterbank) and finalizes.  ``lm_state_dict``: the
+        ``LM.state_dict()`` of the fused language model (lm.py:20-29), required iff ``cfg.lm_layers > 0``."""
         cfg = self.cfg
         items = dict(sd)
+        if (lm_state_dict is not None) != (cfg.lm_layers > 0):
+            raise ValueError("lm_state_dict must be given exactly when cfg.lm_layers > 0")
+        for k, v in (lm_state_dict or {}).items():
+            items["lm." + k] = v
         items["frontend.window"] = torch.hann_window(cfg.win_length, periodic=True)
         items["frontend.mel_fb"] = melscale_fbanks_htk(cfg.n_fft // 2 + 1, cfg.n_mels, cfg.sample_rate)
         for name, v in items.items():
@@ -147,6 +161,18 @@ class Engine:
 
     def reserve(self, max_batch, max_samples):
         self._ck(self.lib.rnnt_b200_reserve(self._h, max_batch, max_samples))
+
+    # ---- LM fuser state (streaming; lm.py:43-48,81-83) ------------------------------------
+    def new_lm_state(self, B):
+        """A zero-filled (= fresh fuser) device blob carrying the LM state of B streams between decode calls."""
+        n = C.c_int64(0)
+        self._ck(self.lib.rnnt_b200_lm_state_bytes(self._h, B, C.byref(n)))
+        return torch.zeros(n.value // 4, dtype=torch.float32, device=self.device)
+
+    def set_lm_state(self, blob, B=0):
+        """Registers ``blob`` (from ``new_lm_state``) for the following decode calls; ``None`` = fresh fuser per call."""
+        self._ck(self.lib.rnnt_b200_set_lm_state(self._h, _ptr(blob), B))
+        self._lm_blob = blob  # keep it alive while registered
 
     # ---- shapes ------------------------------------------------------------------------
     def num_frames(self, n):
@@ -240,10 +266,11 @@ class Engine:
         return out
 
     # ---- decode ----------------------------------------------------------------------------------
-    def decode_greedy(self, enc, lens_T=None, max_iters=3, state=None, want_state=False, trace_cap=0):
+    def decode_greedy(self, enc, lens_T=None, max_iters=3, state=None, want_state=False, trace_cap=0, lm_state=None):
         """enc [B,T,H].  state = (pred_h [Lp,B,H], pred_out [B,H]) or None (-> BOS from the
-        learnable state).  Returns dict of device tensors: tokens [B,U], ntok [B],
-        neg_logp [B] (f64), iters [B,T] (u8), trace [B,trace_cap,V] | None, state | None."""
+        learnable state).  lm_state: blob from ``new_lm_state(B)`` carrying the LM fuser of B streams
+        across calls (updated in place); None = fresh fuser (offline decode).  Returns dict of device tensors:
+        tokens [B,U], ntok [B], neg_logp [B] (f64), iters [B,T] (u8), trace [B,trace_cap,V] | None, state | None."""
         enc = self._f32(enc)
         B, T, H = enc.shape
         Lp, V = self.cfg.pred_layers, self.cfg.vocab_sz
@@ -262,9 +289,15 @@ class Engine:
         elif want_state:
             ph = torch.empty(Lp, B, H, device=self.device)
             po = torch.empty(B, H, device=self.device)
-        self._ck(self.lib.rnnt_b200_decode_greedy(
-            self._h, _ptr(enc), _ptr(lens_T), B, T, max_iters, _ptr(ph), _ptr(po), use_in, _ptr(tokens), U,
-            _ptr(ntok), _ptr(nlp), _ptr(iters), _ptr(trace), trace_cap, self._stream()))
+        if lm_state is not None:
+            self.set_lm_state(lm_state, B)
+        try:
+            self._ck(self.lib.rnnt_b200_decode_greedy(
+                self._h, _ptr(enc), _ptr(lens_T), B, T, max_iters, _ptr(ph), _ptr(po), use_in, _ptr(tokens), U,
+                _ptr(ntok), _ptr(nlp), _ptr(iters), _ptr(trace), trace_cap, self._stream()))
+        finally:
+            if lm_state is not None:
+                self.set_lm_state(None)
         return {"tokens": tokens, "ntok": ntok, "neg_logp": nlp, "iters": iters, "trace": trace,
                 "state": (ph, po) if ph is not None else None}
 

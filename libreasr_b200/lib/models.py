@@ -217,10 +217,24 @@ class Transducer(nn.Module):
             if dev.type != "cuda":
                 raise RuntimeError("Transducer parameters are on %s; move the model to a CUDA device "
                                    "(libreasr_b200 has no CPU path)" % dev)
-            eng = Engine(self._ecfg, device=dev)
-            eng.load_state_dict({k: v for k, v in self.state_dict().items()})
+            import dataclasses
+
+            ecfg, lm_sd = self._ecfg, None
+            sd = {k: v for k, v in self.state_dict().items() if not k.startswith("lm.")}
+            if self.lm is not None:  # fused LM (models.py:234, api-server.py:158-161): weights go to the engine as "lm.*"
+                lm = self.lm
+                ecfg = dataclasses.replace(ecfg, lm_layers=lm.num_layers, lm_hidden_sz=lm.hidden_sz, lm_embed_sz=lm.embed_sz)
+                lm_sd = {k: v for k, v in lm.state_dict().items()}
+            eng = Engine(ecfg, device=dev)
+            eng.load_state_dict(sd, lm_state_dict=lm_sd)
             self._engine = eng
+            object.__setattr__(self, "_engine_lm", self.lm)
         return self._engine
+
+    def __setattr__(self, name, value):
+        super().__setattr__(name, value)
+        if name == "lm" and getattr(self, "_engine", None) is not None and value is not getattr(self, "_engine_lm", None):
+            self._drop_engine()  # the engine bakes the LM in at finalize
 
     def forward(self, tpl):
         raise NotImplementedError("training forward (models.py:308-359) is outside the built inference path")
@@ -236,9 +250,9 @@ class Transducer(nn.Module):
 
     def decode_greedy(self, x, max_iters=3, alpha=0.005, theta=1.0, return_logp=False):
         """x [T,X,1] (what the inference transform pipeline yields, api-server.py:75-78) or
-        [T,X]: features of one utterance (models.py:369-455)."""
-        if self.lm is not None:
-            raise NotImplementedError("LM shallow fusion (lm.py:43-83) is a 'next' row, not part of this path")
+        [T,X]: features of one utterance (models.py:369-455).  With ``self.lm`` set the LM is fused inside the
+        decode loop with the fuser's constants (lm.py:13-14; like the reference, the ``alpha``/``theta`` arguments are
+        not forwarded to ``fuse``, models.py:431)."""
         eng = self.engine()
         x = x.to(eng.device, torch.float32)
         if x.dim() == 2:
@@ -261,14 +275,15 @@ class Transducer(nn.Module):
 
     def transcribe_stream(self, stream, denumericalizer, max_iters=10, alpha=0.3, theta=1.0):
         """Generator over chunks of shape [T_c, X(,1)] or None (models.py:457-577): yields
-        (all tokens so far, denumericalizer(tokens of this chunk), reset_fn)."""
-        if self.lm is not None:
-            raise NotImplementedError("LM shallow fusion (lm.py:43-83) is a 'next' row, not part of this path")
+        (all tokens so far, denumericalizer(tokens of this chunk), reset_fn).  One LM fuser lives for the whole
+        stream (models.py:478) until ``reset_fn`` is called (models.py:491-500)."""
         eng = self.engine()
-        st = {"enc": None, "pred": None}
+        st = {"enc": None, "pred": None, "lm": eng.new_lm_state(1) if self.lm is not None else None}
 
         def reset():  # models.py:480-500
             st["enc"], st["pred"] = None, None
+            if st["lm"] is not None:
+                st["lm"].zero_()  # LMFuser.reset (lm.py:81-83)
 
         y = []
         for chunk in stream:
@@ -277,7 +292,7 @@ class Transducer(nn.Module):
             x = chunk.to(eng.device, torch.float32)
             x = x.reshape(1, x.size(0), -1)
             enc, st["enc"] = eng.encode(x, state=st["enc"], want_state=True)
-            r = eng.decode_greedy(enc, max_iters=max_iters, state=st["pred"], want_state=True)
+            r = eng.decode_greedy(enc, max_iters=max_iters, state=st["pred"], want_state=True, lm_state=st["lm"])
             st["pred"] = r["state"]
             y_seq = tokens_to_lists(r["tokens"], r["ntok"])[0]
             y = y + y_seq

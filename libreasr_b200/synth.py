@@ -150,6 +150,49 @@ def make_state_dict(cfg: ModelConfig, seed: int = 1234) -> dict:
     return sd
 
 
+@dataclass(frozen=True)
+class LMConfig:
+    """Shape of the fused language model (reference libreasr/lib/lm.py:20-29, config/testing.yaml:293-313)."""
+
+    vocab_sz: int = 2048
+    embed_sz: int = 768
+    hidden_sz: int = 768
+    num_layers: int = 4
+    alpha: float = 0.1  # lm.py:13 (the decode loops call fuse() with its defaults, models.py:431,558)
+    theta: float = 1.0  # lm.py:14
+    rnn_gain: float = 3.0
+
+    @property
+    def tied(self) -> bool:  # lm.py:27-29
+        return self.embed_sz == self.hidden_sz
+
+
+LM_CONFIGS = {
+    "tiny": LMConfig(vocab_sz=64, embed_sz=64, hidden_sz=64, num_layers=2),  # tied embedding / output weights
+    "tiny_untied": LMConfig(vocab_sz=64, embed_sz=32, hidden_sz=64, num_layers=3),
+    "en": LMConfig(),  # the shipped inference override (testing.yaml:306-313): 4 x 768, tied
+    "default": LMConfig(embed_sz=1024, hidden_sz=1024, num_layers=6),  # testing.yaml:293-299
+}
+
+
+def make_lm_state_dict(lm: LMConfig, seed: int = 4321) -> dict:
+    """name -> np.ndarray with the reference ``LM.state_dict()`` keys (lm.py:20-29)."""
+    V, E, H = lm.vocab_sz, lm.embed_sz, lm.hidden_sz
+    sd = {}
+    sd["embed.weight"] = _normal(seed, "lm.embed.weight", (V, E), 1.0)
+    sd["embed.weight"][0] = 0.0  # padding_idx=0
+    k = 1.0 / np.sqrt(H)
+    for i in range(lm.num_layers):
+        inp = E if i == 0 else H
+        sd[f"rnn.weight_ih_l{i}"] = _uniform(seed, f"lm.rnn.weight_ih_l{i}", (4 * H, inp), k * lm.rnn_gain)
+        sd[f"rnn.weight_hh_l{i}"] = _uniform(seed, f"lm.rnn.weight_hh_l{i}", (4 * H, H), k * lm.rnn_gain)
+        sd[f"rnn.bias_ih_l{i}"] = _uniform(seed, f"lm.rnn.bias_ih_l{i}", (4 * H,), k)
+        sd[f"rnn.bias_hh_l{i}"] = _uniform(seed, f"lm.rnn.bias_hh_l{i}", (4 * H,), k)
+    sd["linear.weight"] = sd["embed.weight"] if lm.tied else _uniform(seed, "lm.linear.weight", (V, H), k * 4.0)
+    sd["linear.bias"] = _uniform(seed, "lm.linear.bias", (V,), k)
+    return sd
+
+
 def make_audio(batch: int, n_samples: int, seed: int = 0) -> np.ndarray:
     """[batch, n_samples] float32 synthetic 16 kHz audio.  Speech-like non-stationarity:
     a N(0, 0.02^2) noise floor plus back-to-back 40-300 ms segments, each a harmonic

@@ -197,6 +197,83 @@ def demo_fixture(name="ref"):
             "maxlogp": logp.max(-1).values.numpy().astype(np.float32), "margins": margins.astype(np.float32)}
 
 
+LM_WEIGHT_SEED = 4321
+
+
+def build_reference_lm(lm_cfg):
+    """The reference ``LM`` (lm.py:20-41) with the seeded synthetic weights; attached as ``Transducer.lm``
+    (models.py:234, api-server.py:158-161)."""
+    import importlib
+
+    ref_shim.import_reference_models()
+    L = importlib.import_module("libreasr.lib.lm")
+    lm = L.LM(lm_cfg.vocab_sz, lm_cfg.embed_sz, lm_cfg.hidden_sz, lm_cfg.num_layers)
+    sd = weights.make_lm_state_dict(lm_cfg, LM_WEIGHT_SEED)
+    lm.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=True)
+    lm.eval()
+    return lm
+
+
+def lm_fixture(name, lm_name, n_utt, n_samples, audio_seed, n_chunks, stream_seed, lm_rows=4):
+    """Shallow fusion: ``decode_greedy`` and ``transcribe_stream`` of the reference with
+    ``m.lm`` set.  Also stores the first standardised LM rows the fuser holds (lm.py:50-54) and the fused-score margins."""
+    from . import rnnt_oracle as O
+
+    cfg, lm_cfg = weights.CONFIGS[name], weights.LM_CONFIGS[lm_name]
+    ref = build_reference(cfg)
+    with torch.no_grad():
+        plain = []
+        audio = weights.make_audio(n_utt, n_samples, audio_seed)
+        feats_all = [ref_features_offline(torch.from_numpy(audio[b:b + 1]), cfg)[0] for b in range(n_utt)]
+        for f in feats_all:
+            plain.append(ref.decode_greedy(f, max_iters=3)[0])
+    ref.lm = build_reference_lm(lm_cfg)
+    orc = O.OracleTransducer(cfg, weights.make_state_dict(cfg, WEIGHT_SEED))
+    olm = O.OracleLM(lm_cfg, weights.make_lm_state_dict(lm_cfg, LM_WEIGHT_SEED))
+    out = {"config": name, "lm_config": lm_name, "weight_seed": WEIGHT_SEED, "lm_weight_seed": LM_WEIGHT_SEED,
+           "audio_seed": audio_seed, "n_utt": n_utt, "n_samples": n_samples, "max_iters": 3,
+           "n_chunks": n_chunks, "stream_seed": stream_seed}
+    for b, feats in enumerate(feats_all):
+        with torch.no_grad():
+            toks, nlp, metrics, extra = ref.decode_greedy(feats, max_iters=3)
+        toks = [int(t) for t in toks]
+        out[f"tokens_{b}"] = np.asarray(toks, dtype=np.int32)
+        out[f"tokens_nolm_{b}"] = np.asarray(plain[b], dtype=np.int32)
+        out[f"neg_log_p_{b}"] = np.float64(nlp)
+        out[f"iters_{b}"] = np.asarray(extra["iters"], dtype=np.int32)
+        # the rows the reference's fuser held after each of the first emitted tokens (reference LM + standardize)
+        fz = importlib_lm().LMFuser(ref.lm)
+        rows = []
+        with torch.no_grad():
+            for t in toks[:lm_rows]:
+                fz.advance(torch.LongTensor([[t]]))
+                rows.append(fz.lm_logits.reshape(-1).clone())
+        out[f"lm_rows_{b}"] = torch.stack(rows).numpy() if rows else np.zeros((0, lm_cfg.vocab_sz), np.float32)
+        # fused-score margins along the reference's own path (informational: tie risk of the fused arg max)
+        res = orc.decode_greedy(feats[..., 0], max_iters=3, impl="aten", lm=olm, keep_logits=True)
+        assert res["tokens"] == toks, "oracle restatement of the fusion differs from the reference"
+        n_flip = sum(1 for x, y in zip(toks, plain[b]) if x != y) + abs(len(toks) - len(plain[b]))
+        out[f"fused_margins_{b}"] = np.asarray(olm.fused_margins, dtype=np.float32)
+        out[f"margins_{b}"] = np.asarray(res["margins"], dtype=np.float32)
+        print(f"[{name}+lm:{lm_name}] utt {b}: tokens={len(toks)} (no-LM {len(plain[b])}), positions that differ from the no-LM decode: {n_flip}; "
+              f"min margin joint {min(res['margins']):.2e}, fused {min(olm.fused_margins) if olm.fused_margins else float('nan'):.2e}")
+    a = weights.make_audio(1, n_chunks * CHUNK, stream_seed)[0]
+    a[:CHUNK] = 0.0
+    rows = [c for c in ref_stream_chunks(torch.from_numpy(a), cfg)]
+    with torch.no_grad():
+        yields = [([int(t) for t in y], [int(t) for t in ys]) for (y, ys, _r) in ref.transcribe_stream(iter(rows), lambda t: list(t), max_iters=10)]
+    out["stream_tokens_all"] = np.asarray(yields[-1][0] if yields else [], dtype=np.int32)
+    out["stream_chunk_counts"] = np.asarray([len(ys) for _, ys in yields], dtype=np.int32)
+    print(f"[{name}+lm:{lm_name} stream] yields={len(yields)} tokens={len(out['stream_tokens_all'])}")
+    return out
+
+
+def importlib_lm():
+    import importlib
+
+    return importlib.import_module("libreasr.lib.lm")
+
+
 def main():
     if not ref_shim.reference_available():
         sys.exit("reference tree missing; fixtures can only be generated in the authoring container")
@@ -212,6 +289,9 @@ def main():
         "ref_offline": lambda: offline_fixture("ref", n_utt=1, n_samples=48000, audio_seed=25),
         "cfg4_offline": lambda: offline_fixture("cfg4", n_utt=1, n_samples=32000, audio_seed=26),
         "cfg1_demo": lambda: demo_fixture("ref"),
+        "tiny_lm": lambda: lm_fixture("tiny", "tiny", n_utt=3, n_samples=40000, audio_seed=21, n_chunks=40, stream_seed=22),
+        "tiny_lm_untied": lambda: lm_fixture("tiny", "tiny_untied", n_utt=2, n_samples=40000, audio_seed=31, n_chunks=30, stream_seed=32),
+        "cfg2_lm": lambda: lm_fixture("cfg2", "en", n_utt=2, n_samples=80000, audio_seed=105, n_chunks=50, stream_seed=47),
     }
     only = sys.argv[1:]
     for k, fn in jobs.items():

@@ -129,6 +129,67 @@ def _t(a):
     return a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
 
 
+class OracleLM:
+    """The fused language model and its fuser (reference libreasr/lib/lm.py:20-83).
+
+    ``LM.forward`` (lm.py:31-41): Embedding -> nn.LSTM (zero initial state when none is carried) -> Dropout (identity in
+    eval) -> Linear (weights tied to the embedding when embed_sz == hidden_sz, lm.py:27-29) -> log_softmax.
+    ``LMFuser.advance`` (lm.py:50-54) standardises that row in place ((t - mean) / (std + 1e-5), unbiased std,
+    utils.py:162-164) and pins the blank entry to -10; ``LMFuser.fuse`` (lm.py:56-79) does the same to the joint's
+    log_softmax row and takes arg max of ``alpha * lm + theta * joint``.  Before the first ``advance`` there is no LM row
+    and ``fuse`` returns its inputs (lm.py:58,79)."""
+
+    MIN_VAL = -10.0  # lm.py:15
+
+    def __init__(self, lm_cfg, state_dict: dict):
+        self.cfg = lm_cfg
+        self.sd = {k: _t(v) for k, v in state_dict.items()}
+        self.reset()
+
+    def reset(self):  # lm.py:81-83
+        self.logits = None
+        self.state = None
+        self.fused_margins = []  # top-1 minus top-2 of every fused row (tie-risk bookkeeping for the tests)
+
+    @staticmethod
+    def standardize(t: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:  # utils.py:162-164
+        t = t - t.mean()
+        return t / (t.std() + eps)
+
+    def forward(self, token: int):
+        """One LM step on one token: returns the log_softmax row [V] and updates the carried (h, c) per layer."""
+        sd, L, H = self.sd, self.cfg.num_layers, self.cfg.hidden_sz
+        x = sd["embed.weight"][token]
+        if self.state is None:
+            self.state = [(torch.zeros(H), torch.zeros(H)) for _ in range(L)]
+        new = []
+        for i in range(L):
+            h, c = self.state[i]
+            v = sd[f"rnn.weight_ih_l{i}"] @ x + sd[f"rnn.bias_ih_l{i}"] + sd[f"rnn.weight_hh_l{i}"] @ h + sd[f"rnn.bias_hh_l{i}"]
+            ig, fg, gg, og = v.chunk(4)  # torch.nn.LSTM gate order i, f, g, o
+            c = torch.sigmoid(fg) * c + torch.sigmoid(ig) * torch.tanh(gg)
+            h = torch.sigmoid(og) * torch.tanh(c)
+            new.append((h, c))
+            x = h
+        self.state = new
+        return F.log_softmax(sd["linear.weight"] @ x + sd["linear.bias"], dim=-1)
+
+    def advance(self, token: int):  # lm.py:50-54
+        row = self.standardize(self.forward(token))
+        row[0] = self.MIN_VAL
+        self.logits = row
+
+    def fuse(self, logp: torch.Tensor, pred: int) -> int:  # lm.py:56-79
+        if self.logits is None:
+            return pred
+        j = self.standardize(logp)
+        j[0] = self.MIN_VAL
+        fused = self.cfg.alpha * self.logits + self.cfg.theta * j
+        top2 = torch.topk(fused, 2).values
+        self.fused_margins.append(float(top2[0] - top2[1]))
+        return int(fused.argmax(-1))
+
+
 class OracleTransducer:
     """Restates ``Transducer`` inference (models.py:190-577) on a reference ``state_dict``."""
 
@@ -223,8 +284,8 @@ class OracleTransducer:
         return x @ sd["joint.joint.2.weight"].t() + sd["joint.joint.2.bias"]
 
     # -- decode loops ------------------------------------------------------------
-    def decode_greedy(self, x: torch.Tensor, max_iters: int = 3, impl: str = "explicit", keep_logits: bool = False):
-        """``Transducer.decode_greedy`` (models.py:369-455), no LM (``m.lm is None``).
+    def decode_greedy(self, x: torch.Tensor, max_iters: int = 3, impl: str = "explicit", keep_logits: bool = False, lm=None):
+        """``Transducer.decode_greedy`` (models.py:369-455); ``lm`` = an ``OracleLM`` for shallow fusion (models.py:401,431,440).
         x [T,X] features of ONE utterance.  Returns dict(tokens, neg_log_p, iters,
         alignment_score, margins[, logp])."""
         with torch.no_grad():
@@ -233,6 +294,8 @@ class OracleTransducer:
             tok = torch.tensor([self.bos])
             h_pred, pstate = self.predictor(tok)
             y_seq, log_p, iters_all, margins, outs = [], 0.0, [], [], []
+            if lm is not None:
+                lm.reset()  # a fresh LMFuser per call (models.py:401)
             for h_enc in enc:
                 iters = 0
                 while iters < max_iters:
@@ -247,8 +310,12 @@ class OracleTransducer:
                     log_p += float(prob)
                     if pred == self.blank:
                         break
+                    if lm is not None:
+                        pred = lm.fuse(logp, pred)  # only after the blank test (models.py:427-431)
                     y_seq.append(pred)
                     h_pred, pstate = self.predictor(torch.tensor([pred]), pstate)
+                    if lm is not None:
+                        lm.advance(pred)
                 iters_all.append(iters)
             align = np.array(iters_all)
             _sum = align.sum()
@@ -262,13 +329,15 @@ class OracleTransducer:
                 res["logp"] = torch.stack(outs)
             return res
 
-    def transcribe_stream(self, stream, max_iters: int = 10, impl: str = "explicit"):
-        """``Transducer.transcribe_stream`` (models.py:457-577), no LM: generator over
+    def transcribe_stream(self, stream, max_iters: int = 10, impl: str = "explicit", lm=None):
+        """``Transducer.transcribe_stream`` (models.py:457-577; LM fusion at :558,569): generator over
         chunks ([T_c, X] or None) yielding (all tokens so far, this chunk's tokens)."""
         with torch.no_grad():
             enc_state = None
             h_pred, pstate = self.predictor(torch.tensor([self.bos]))
             y = []
+            if lm is not None:
+                lm.reset()
             for chunk in stream:
                 if chunk is None:  # models.py:509
                     continue
@@ -283,18 +352,22 @@ class OracleTransducer:
                         pred = int(logp.argmax(-1))
                         if pred == self.blank:
                             break
+                        if lm is not None:
+                            pred = lm.fuse(logp, pred)
                         y_seq.append(pred)
                         h_pred, pstate = self.predictor(torch.tensor([pred]), pstate)
+                        if lm is not None:
+                            lm.advance(pred)
                 y = y + y_seq
                 yield list(y), list(y_seq)
 
 
-def transcribe_batch(model: OracleTransducer, audio: np.ndarray, max_iters: int = 3, impl: str = "aten"):
+def transcribe_batch(model: OracleTransducer, audio: np.ndarray, max_iters: int = 3, impl: str = "aten", lm=None):
     """The reference serving path applied utterance by utterance (api-server.py:64-80;
     the reference has no batched decode, config/testing.yaml:380 bs=1):
     audio [B, n] -> list of token lists."""
     out = []
     for b in range(audio.shape[0]):
         feats = features_offline(torch.from_numpy(audio[b : b + 1]), model.cfg)[0]
-        out.append(model.decode_greedy(feats, max_iters=max_iters, impl=impl)["tokens"])
+        out.append(model.decode_greedy(feats, max_iters=max_iters, impl=impl, lm=lm)["tokens"])
     return out

@@ -32,17 +32,19 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_abi_version_and_default_config():
     lib = _capi.load_library()
-    assert lib.rnnt_b200_abi_version() == 1
+    assert lib.rnnt_b200_abi_version() == 2
     c = _capi.Config()
     assert lib.rnnt_b200_default_config(C.byref(c)) == 0
     # reference's shipped shape (config/testing.yaml:133-135,202-229)
     assert (c.n_mels, c.n_stack, c.downsample, c.enc_layers, c.pred_layers) == (128, 10, 8, 6, 2)
     assert (c.hidden_sz, c.embed_sz, c.joint_sz, c.vocab_sz, c.blank, c.bos) == (1024, 512, 1024, 2048, 0, 2)
     assert (c.sample_rate, c.n_fft, c.win_length, c.hop_length) == (16000, 1024, 400, 160)
+    # no fused LM by default (m.lm is None, models.py:234); fuser constants of lm.py:13-14
+    assert c.lm_layers == 0 and abs(c.lm_alpha - 0.1) < 1e-7 and c.lm_theta == 1.0
 
 
 @pytest.mark.parametrize("field,value", [("n_fft", 512), ("hidden_sz", 100), ("vocab_sz", 33), ("pred_layers", 9),
-                                         ("joint_sz", 0), ("gemm_mode", 7), ("bos", 5000)])
+                                         ("joint_sz", 0), ("gemm_mode", 7), ("bos", 5000), ("lm_layers", 9)])
 def test_create_rejects_bad_config(field, value):
     lib = _capi.load_library()
     c = _capi.Config()

@@ -335,3 +335,116 @@ def test_gemm_arithmetic_modes_against_fp64():
             C = eng.selftest_gemm(A, W, b, gemm_mode=mode)
             rel = float((C.double() - ref).pow(2).mean().sqrt()) / scale
             assert rel < 4e-6, (mode, M_, N_, K_, rel)
+
+
+# ---------------- LM shallow fusion (lm.py:43-83) ----------------
+_lm_models = {}
+
+
+def lm_model_for(name, lm_name):
+    """Transducer with the reference-named ``LM`` attached (``m.lm = lm``, api-server.py:158-161)."""
+    from libreasr_b200.lib.lm import LM
+    from libreasr_b200.lib.models import Transducer
+
+    key = (name, lm_name)
+    if key not in _lm_models:
+        cfg, lc = weights.CONFIGS[name], weights.LM_CONFIGS[lm_name]
+        sd, lsd = weights.make_state_dict(cfg, 1234), weights.make_lm_state_dict(lc, 4321)
+        m = Transducer(cfg.feature_sz, cfg.embed_sz, cfg.vocab_sz, cfg.hidden_sz, cfg.out_sz, cfg.joint_sz, Lang(),
+                       encoder_kwargs={"num_layers": cfg.enc_layers}, predictor_kwargs={"num_layers": cfg.pred_layers},
+                       gemm_mode=GEMM_MODE)
+        m.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()}, strict=True)
+        lm = LM(lc.vocab_sz, lc.embed_sz, lc.hidden_sz, lc.num_layers)
+        lm.load_state_dict({k: torch.as_tensor(v) for k, v in lsd.items()}, strict=True)
+        m.lm = lm
+        m = m.to("cuda:0")
+        _lm_models[key] = (cfg, lc, m, O.OracleTransducer(cfg, sd), O.OracleLM(lc, lsd))
+    return _lm_models[key]
+
+
+@pytest.mark.parametrize("name", ["tiny_lm", "tiny_lm_untied", "cfg2_lm"])
+def test_lm_fusion_matches_reference_fixture(name):
+    """decode_greedy and transcribe_stream with ``m.lm`` set: token ids identical to the imported reference's."""
+    from libreasr_b200.lib.transforms import FusedStreamFeatures
+
+    g = load_golden(name)
+    cfg, lc, m, _, _ = lm_model_for(str(g["config"]), str(g["lm_config"]))
+    eng = m.engine()
+    audio = weights.make_audio(int(g["n_utt"]), int(g["n_samples"]), int(g["audio_seed"]))
+    for b in range(int(g["n_utt"])):
+        feats = eng.features(torch.from_numpy(audio[b:b + 1]).cuda())[0]
+        toks, nlp, metrics, extra = m.decode_greedy(feats.unsqueeze(-1), max_iters=int(g["max_iters"]))
+        assert toks == g[f"tokens_{b}"].tolist()
+        assert extra["iters"] == g[f"iters_{b}"].tolist()
+        assert abs(nlp - float(g[f"neg_log_p_{b}"])) < 2e-3   # accumulates the PRE-fusion log-probs (models.py:422)
+    n_chunks = int(g["n_chunks"])
+    a = weights.make_audio(1, n_chunks * CHUNK, int(g["stream_seed"]))[0]
+    a[:CHUNK] = 0.0
+    tfm = FusedStreamFeatures(eng, n_buffer=2)
+    frames, rows = [], []
+    for j in range(n_chunks):
+        frames.append(torch.from_numpy(a[None, j * CHUNK:(j + 1) * CHUNK]))
+        if len(frames) < 3:
+            rows.append(None)
+            continue
+        rows.append(tfm(torch.cat(frames, dim=1)))
+        frames.pop(0)
+    yields = [(list(y), list(ys)) for y, ys, _ in m.transcribe_stream(iter(rows), lambda t: list(t), max_iters=10)]
+    assert [len(ys) for _, ys in yields] == g["stream_chunk_counts"].tolist()
+    assert (yields[-1][0] if yields else []) == g["stream_tokens_all"].tolist()
+
+
+def test_lm_fusion_batched_ragged_matches_oracle():
+    """A ragged batch through Engine.transcribe with the LM on: every utterance has its own fuser."""
+    cfg, lc, m, orc, olm = lm_model_for("tiny", "tiny")
+    eng = m.engine()
+    n = 48000
+    audio = weights.make_audio(7, n, seed=91)
+    lens = np.array([n, 30000, 41000, n, 17000, 25000, 36000], dtype=np.int32)
+    r = eng.transcribe(torch.from_numpy(audio).cuda(), lens=torch.from_numpy(lens))
+    got = [r["tokens"][b, : int(r["ntok"][b])].tolist() for b in range(7)]
+    plain = []
+    for b in range(7):
+        feats = O.features_offline(torch.from_numpy(audio[b:b + 1, : lens[b]]), cfg)[0]
+        want = orc.decode_greedy(feats, max_iters=3, impl="aten", lm=olm)
+        assert got[b] == want["tokens"], f"utterance {b}"
+        plain.append(orc.decode_greedy(feats, max_iters=3, impl="aten")["tokens"])
+    assert got != plain
+
+
+def test_lm_fuser_state_carries_across_calls_and_resets():
+    """Streaming: chunked decode with a registered fuser blob == one decode over the whole sequence (bit-equal tokens),
+    a zeroed blob == a fresh fuser, and two streams in one batch keep separate fusers."""
+    cfg, lc, m, _, _ = lm_model_for("tiny", "tiny")
+    eng = m.engine()
+    audio = torch.from_numpy(weights.make_audio(2, 64000, seed=93)).cuda()
+    feats = eng.features(audio)
+    enc, _ = eng.encode(feats)
+    T = enc.shape[1]
+    full = eng.decode_greedy(enc, max_iters=10)
+    want = [full["tokens"][b, : int(full["ntok"][b])].tolist() for b in range(2)]
+    blob = eng.new_lm_state(2)
+    state, got = None, [[], []]
+    for t0 in range(0, T, 7):
+        r = eng.decode_greedy(enc[:, t0:t0 + 7].contiguous(), max_iters=10, state=state, want_state=True, lm_state=blob)
+        state = r["state"]
+        for b in range(2):
+            got[b] += r["tokens"][b, : int(r["ntok"][b])].tolist()
+    assert got == want
+    blob.zero_()
+    again = eng.decode_greedy(enc, max_iters=10, lm_state=blob)
+    assert [again["tokens"][b, : int(again["ntok"][b])].tolist() for b in range(2)] == want
+    # per-stream fusers: decoding stream 1 alone gives the same tokens as inside the batch
+    solo = eng.decode_greedy(enc[1:2].contiguous(), max_iters=10)
+    assert solo["tokens"][0, : int(solo["ntok"][0])].tolist() == want[1]
+
+
+def test_lm_errors():
+    cfg, lc, m, _, _ = lm_model_for("tiny", "tiny")
+    eng = m.engine()
+    enc = torch.zeros(3, 4, cfg.hidden_sz, device="cuda")
+    with pytest.raises(ValueError):
+        eng.decode_greedy(enc, lm_state=eng.new_lm_state(2))     # blob sized for another stream count
+    _, _, plain, _ = model_for("tiny")
+    with pytest.raises(Exception):
+        plain.engine().new_lm_state(1)                            # handle without a language model

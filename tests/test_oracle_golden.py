@@ -106,3 +106,36 @@ def test_demo_utterance_config1_matches_reference():
     assert r["iters"] == g["iters"].tolist()
     assert abs(r["neg_log_p"] - float(g["neg_log_p"])) < 5e-3
     np.testing.assert_allclose(r["logp"].max(-1).values.numpy(), g["maxlogp"], atol=5e-4)
+
+
+@pytest.mark.parametrize("name", ["tiny_lm", "tiny_lm_untied", "cfg2_lm"])
+def test_lm_fusion_matches_reference(name):
+    """``LMFuser`` inside ``decode_greedy`` / ``transcribe_stream`` (lm.py:43-83) -- the oracle's
+    restatement against the imported reference run with ``m.lm`` set (tokens exact; the fuser's rows 2e-4)."""
+    g = load_golden(name)
+    cfg = weights.CONFIGS[str(g["config"])]
+    lm_cfg = weights.LM_CONFIGS[str(g["lm_config"])]
+    orc = O.OracleTransducer(cfg, weights.make_state_dict(cfg, int(g["weight_seed"])))
+    lm = O.OracleLM(lm_cfg, weights.make_lm_state_dict(lm_cfg, int(g["lm_weight_seed"])))
+    audio = weights.make_audio(int(g["n_utt"]), int(g["n_samples"]), int(g["audio_seed"]))
+    differs = 0
+    for b in range(int(g["n_utt"])):
+        feats = O.features_offline(torch.from_numpy(audio[b:b + 1]), cfg)[0]
+        r = orc.decode_greedy(feats, max_iters=int(g["max_iters"]), impl="aten", lm=lm)
+        assert r["tokens"] == g[f"tokens_{b}"].tolist()
+        assert r["iters"] == g[f"iters_{b}"].tolist()
+        assert abs(r["neg_log_p"] - float(g[f"neg_log_p_{b}"])) < 2e-3
+        differs += r["tokens"] != g[f"tokens_nolm_{b}"].tolist()
+        lm.reset()
+        for j, t in enumerate(g[f"tokens_{b}"].tolist()[: g[f"lm_rows_{b}"].shape[0]]):
+            lm.advance(t)
+            np.testing.assert_allclose(lm.logits.numpy(), g[f"lm_rows_{b}"][j], atol=2e-4)
+    assert differs > 0, "the fixture must exercise the fusion (some decode changes with the LM)"
+    n_chunks = int(g["n_chunks"])
+    a = weights.make_audio(1, n_chunks * CHUNK, int(g["stream_seed"]))[0]
+    a[:CHUNK] = 0.0
+    fe = O.StreamFrontend(cfg)
+    rows = [fe.push(torch.from_numpy(a[None, j * CHUNK:(j + 1) * CHUNK])) for j in range(n_chunks)]
+    yields = list(orc.transcribe_stream(iter(rows), max_iters=10, lm=lm))
+    assert [len(ys) for _, ys in yields] == g["stream_chunk_counts"].tolist()
+    assert (yields[-1][0] if yields else []) == g["stream_tokens_all"].tolist()
