@@ -167,11 +167,13 @@ class Engine:
         """A zero-filled (= fresh fuser) device blob carrying the LM state of B streams between decode calls."""
         n = C.c_int64(0)
         self._ck(self.lib.rnnt_b200_lm_state_bytes(self._h, B, C.byref(n)))
-        return torch.zeros(n.value // 4, dtype=torch.float32, device=self.device)
+        blob = torch.zeros(n.value // 4, dtype=torch.float32, device=self.device)
+        blob._rnnt_streams = B  # the library checks the stream count of every call against the registration
+        return blob
 
     def set_lm_state(self, blob, B=0):
         """Registers ``blob`` (from ``new_lm_state``) for the following decode calls; ``None`` = fresh fuser per call."""
-        self._ck(self.lib.rnnt_b200_set_lm_state(self._h, _ptr(blob), B))
+        self._ck(self.lib.rnnt_b200_set_lm_state(self._h, _ptr(blob), getattr(blob, "_rnnt_streams", B) if blob is not None else 0))
         self._lm_blob = blob  # keep it alive while registered
 
     # ---- shapes ------------------------------------------------------------------------
