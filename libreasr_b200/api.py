@@ -49,10 +49,12 @@ class LibreASR:
         """``chunks``: iterable of 80 ms float32 PCM chunks (arrays or raw bytes).  Yields
         (all token ids so far, denumericalized tokens of this step) each time the model
         advanced (every second chunk once three are buffered)."""
-        sb = StreamBatch(self.engine, 1, max_iters=max_iters)
+        sb = None
         for ch in chunks:
             a = _as_audio(ch)
-            new = sb.push(a.to(self.engine.device))
+            if sb is None:  # the first chunk fixes the chunk size of the stream (80 ms in the reference client)
+                sb = StreamBatch(self.engine, 1, chunk=a.shape[1], max_iters=max_iters)
+            new = sb.push(a)
             if new is not None:
                 yield list(sb.tokens[0]), self.denumericalize(new[0])
 
@@ -63,46 +65,58 @@ class StreamBatch:
     Reproduces, per stream, the reference serving loop: 3-chunk sliding window
     (api-server.py:26,95-102) -> stream transforms incl. ``Buffer(n_buffer=2)``
     (config/testing.yaml:356-374) -> ``Transducer.transcribe_stream`` with carried encoder /
-    predictor state (models.py:457-577).  All state (audio window, pending feature row,
-    LSTM (h, c), GRU h, last predictor output) stays resident in HBM."""
+    predictor / LM-fuser state (models.py:457-577).  A thin veneer over the C ABI's streaming session
+    (``rnnt_b200_stream_open/push/reset/close``): one library call per chunk tick; all state (audio window,
+    pending feature rows, LSTM (h, c), GRU h, last predictor output, LM fuser) stays resident in HBM."""
 
     def __init__(self, engine: Engine, n_streams: int, chunk: int = None, max_iters: int = 10, n_buffer: int = 2):
+        import ctypes as C
+
         cfg = engine.cfg
         self.engine, self.B, self.max_iters, self.n_buffer = engine, n_streams, max_iters, n_buffer
         self.chunk = chunk or cfg.sample_rate * CHUNK_MS // 1000
-        dev = engine.device
-        self.window = torch.zeros(n_streams, BUFFER_N_FRAMES * self.chunk, device=dev)
-        self.n_chunks = 0
-        self.rows = []
-        self.enc_state = None
-        self.pred_state = None
-        # one LM fuser per stream (models.py:478), resident on the device like the other stream state
-        self.lm_state = engine.new_lm_state(n_streams) if cfg.lm_layers > 0 else None
+        self._s = C.c_void_p(0)
+        with torch.cuda.device(engine.device):
+            engine._ck(engine.lib.rnnt_b200_stream_open(engine._h, n_streams, self.chunk, BUFFER_N_FRAMES, n_buffer, max_iters,
+                                                        C.byref(self._s)))
+        self.U = max_iters * n_buffer
+        self._tok = torch.zeros(n_streams, self.U, dtype=torch.int32).pin_memory()
+        self._ntok = torch.zeros(n_streams, dtype=torch.int32).pin_memory()
+        self._adv = C.c_int32(0)
         self.tokens = [[] for _ in range(n_streams)]
 
+    def close(self):
+        if getattr(self, "_s", None) is not None and self._s.value:
+            self.engine.lib.rnnt_b200_stream_close(self._s)
+            self._s.value = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def reset(self):
-        self.enc_state, self.pred_state = None, None
-        if self.lm_state is not None:
-            self.lm_state.zero_()  # LMFuser.reset (lm.py:81-83)
+        self.engine._ck(self.engine.lib.rnnt_b200_stream_reset(self._s))
 
     def push(self, chunks):
-        """chunks [B, chunk] CUDA tensor.  Returns the list of new token lists when the
-        encoder advanced on this call, else None."""
-        c = self.chunk
-        # slide by one chunk (api-server.py:99-102)
-        self.window = torch.cat([self.window[:, c:], chunks.to(self.window.dtype)], dim=1)
-        self.n_chunks += 1
-        if self.n_chunks < BUFFER_N_FRAMES:
+        """chunks [B, chunk] float32, CUDA or (ideally pinned) CPU tensor.  Returns the list of new token lists
+        when the encoder advanced on this call, else None."""
+        import ctypes as C
+
+        eng = self.engine
+        if chunks.dtype != torch.float32 or not chunks.is_contiguous():
+            chunks = chunks.to(torch.float32).contiguous()
+        if tuple(chunks.shape) != (self.B, self.chunk):
+            raise ValueError(f"expected chunks of shape {(self.B, self.chunk)}, got {tuple(chunks.shape)}")
+        with torch.cuda.device(eng.device):
+            eng._ck(eng.lib.rnnt_b200_stream_push(self._s, C.c_void_p(chunks.data_ptr()), 0 if chunks.is_cuda else 1,
+                                                  C.c_void_p(self._tok.data_ptr()), self.U, C.c_void_p(self._ntok.data_ptr()),
+                                                  C.byref(self._adv), eng._stream()))
+        if not self._adv.value:
             return None
-        self.rows.append(self.engine.features_stream(self.window))  # [B, X]
-        if len(self.rows) < self.n_buffer:
-            return None
-        feats = torch.stack(self.rows, dim=1)  # [B, n_buffer, X]
-        self.rows.clear()
-        enc, self.enc_state = self.engine.encode(feats, state=self.enc_state, want_state=True)
-        r = self.engine.decode_greedy(enc, max_iters=self.max_iters, state=self.pred_state, want_state=True, lm_state=self.lm_state)
-        self.pred_state = r["state"]
-        new = tokens_to_lists(r["tokens"], r["ntok"])
+        t, n = self._tok.numpy(), self._ntok.numpy()
+        new = [t[b, : int(n[b])].tolist() for b in range(self.B)]
         for b in range(self.B):
             self.tokens[b].extend(new[b])
         return new

@@ -1151,6 +1151,121 @@ int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, c
   return RNNT_B200_OK;
 }
 
+// ---------------- streaming sessions ----------------
+struct rnnt_b200_stream_s {
+  rnnt_b200_handle h = nullptr;
+  int B = 0, chunk = 0, n_window = 0, n_buffer = 0, max_iters = 0;
+  int64_t n_chunks = 0;   // pushes since open / reset
+  int n_rows = 0;         // feature rows waiting in the Buffer
+  bool fresh = true;      // no encoder / decode step yet: start from the learnable states and BOS
+  int cur = 0;            // which window buffer is current
+  DevBuf win[2], stage, row, rows, enc_h, enc_c, pred_h, pred_out, enc_out, tokens, ntok, lm;
+};
+
+int32_t rnnt_b200_stream_open(rnnt_b200_handle h, int32_t B, int32_t chunk, int32_t n_window, int32_t n_buffer,
+                              int32_t max_iters, rnnt_b200_stream* out) {
+  if (int r = check_ready(h)) return r;
+  if (!out) return fail(h, RNNT_B200_ERR_INVALID, "stream_open: null argument");
+  *out = nullptr;
+  const rnnt_b200_config& c = h->cfg;
+  const int cap = (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && c.lm_layers == 0) ? 64 : kDecodeMaxBatch;
+  if (B < 1 || B > cap) return fail(h, RNNT_B200_ERR_INVALID, "stream_open: n_streams must be in [1, " + std::to_string(cap) + "]");
+  if (chunk < 1 || n_window < 1 || n_buffer < 1 || n_buffer > 64 || max_iters < 1 || max_iters > 255)
+    return fail(h, RNNT_B200_ERR_INVALID, "stream_open: bad arguments");
+  const int64_t W = (int64_t)n_window * chunk, F = num_frames(c, W);
+  if (W <= c.n_fft / 2 || F / 3 + 1 + c.n_stack > F)
+    return fail(h, RNNT_B200_ERR_INVALID, "stream_open: window too short for n_stack frames after the middle-third crop");
+  CK(cudaSetDevice(c.device));
+  rnnt_b200_stream s = new rnnt_b200_stream_s();
+  s->h = h; s->B = B; s->chunk = chunk; s->n_window = n_window; s->n_buffer = n_buffer; s->max_iters = max_iters;
+  const size_t X = (size_t)c.n_mels * c.n_stack, H = c.hidden_sz;
+  cudaError_t e = cudaSuccess;
+  auto need = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.ensure(bytes); };
+  need(s->win[0], (size_t)B * W * 4); need(s->win[1], (size_t)B * W * 4);
+  need(s->stage, (size_t)B * chunk * 4);
+  need(s->row, (size_t)B * X * 4); need(s->rows, (size_t)B * n_buffer * X * 4);
+  need(s->enc_h, (size_t)c.enc_layers * B * H * 4); need(s->enc_c, (size_t)c.enc_layers * B * H * 4);
+  need(s->pred_h, (size_t)c.pred_layers * B * H * 4); need(s->pred_out, (size_t)B * H * 4);
+  need(s->enc_out, (size_t)B * n_buffer * H * 4);
+  need(s->tokens, (size_t)B * max_iters * n_buffer * 4); need(s->ntok, (size_t)B * 4);
+  if (c.lm_layers > 0) need(s->lm, lm_state_floats(c.lm_layers, c.lm_hidden_sz, c.vocab_sz, bp_of(B)) * 4);
+  if (e != cudaSuccess) { rnnt_b200_stream_close(s); return fail_cuda(h, e, "stream_open: allocation"); }
+  *out = s;
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_stream_reset(rnnt_b200_stream s) {
+  if (!s) return RNNT_B200_ERR_INVALID;
+  rnnt_b200_handle h = s->h;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  for (DevBuf* b : {&s->win[0], &s->win[1], &s->lm})
+    if (b->p) CK(cudaMemset(b->p, 0, b->bytes));
+  s->n_chunks = 0; s->n_rows = 0; s->fresh = true; s->cur = 0;
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_stream_close(rnnt_b200_stream s) {
+  if (!s) return RNNT_B200_OK;
+  cudaSetDevice(s->h->cfg.device);
+  cudaDeviceSynchronize();
+  if (s->h->lm_blob == s->lm.p) { s->h->lm_blob = nullptr; s->h->lm_blob_B = 0; }
+  for (DevBuf* b : {&s->win[0], &s->win[1], &s->stage, &s->row, &s->rows, &s->enc_h, &s->enc_c, &s->pred_h, &s->pred_out,
+                    &s->enc_out, &s->tokens, &s->ntok, &s->lm})
+    b->release();
+  delete s;
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_stream_push(rnnt_b200_stream s, const float* chunks, int32_t on_host, int32_t* tokens_host, int32_t U_cap,
+                              int32_t* ntok_host, int32_t* advanced, void* stream) {
+  if (!s) return RNNT_B200_ERR_INVALID;
+  rnnt_b200_handle h = s->h;
+  const rnnt_b200_config& c = h->cfg;
+  if (!chunks || !advanced) return fail(h, RNNT_B200_ERR_INVALID, "stream_push: null argument");
+  *advanced = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = s->B, ck = s->chunk;
+  const size_t W = (size_t)s->n_window * ck, X = (size_t)c.n_mels * c.n_stack;
+  const int U = s->max_iters * s->n_buffer;
+  // slide every stream's window by one chunk (api-server.py:99-102): new = [old[chunk:], chunk]
+  float* wold = s->win[s->cur].as<float>();
+  float* wnew = s->win[s->cur ^ 1].as<float>();
+  if (s->n_window > 1)
+    CK(cudaMemcpy2DAsync(wnew, W * 4, wold + ck, W * 4, (W - ck) * 4, B, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpy2DAsync(wnew + (W - ck), W * 4, chunks, (size_t)ck * 4, (size_t)ck * 4, B,
+                       on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+  s->cur ^= 1;
+  s->n_chunks += 1;
+  if (s->n_chunks < s->n_window) return RNNT_B200_OK;
+  // stream transforms -> one stacked row per stream, appended to the Buffer (transforms.py:326-342,463-471)
+  if (int r = rnnt_b200_features_stream(h, wnew, B, (int64_t)W, s->row.as<float>(), stream)) return r;
+  CK(cudaMemcpy2DAsync(s->rows.as<float>() + (size_t)s->n_rows * X, (size_t)s->n_buffer * X * 4, s->row.p, X * 4, X * 4, B,
+                       cudaMemcpyDeviceToDevice, st));
+  if (++s->n_rows < s->n_buffer) return RNNT_B200_OK;
+  s->n_rows = 0;
+  if (!tokens_host || !ntok_host || U_cap < U) return fail(h, RNNT_B200_ERR_INVALID, "stream_push: token outputs missing or U_cap < max_iters * n_buffer");
+  // Transducer.transcribe_stream, one chunk of n_buffer encoder steps (models.py:503-571)
+  const int use_in = s->fresh ? 0 : 1;
+  if (int r = rnnt_b200_encode(h, s->rows.as<float>(), nullptr, B, s->n_buffer, s->enc_h.as<float>(), s->enc_c.as<float>(), use_in,
+                               s->enc_out.as<float>(), stream))
+    return r;
+  void* prev_blob = h->lm_blob;
+  const int prev_B = h->lm_blob_B;
+  if (c.lm_layers > 0) { h->lm_blob = s->lm.as<float>(); h->lm_blob_B = B; }
+  const int r = rnnt_b200_decode_greedy(h, s->enc_out.as<float>(), nullptr, B, s->n_buffer, s->max_iters, s->pred_h.as<float>(),
+                                        s->pred_out.as<float>(), use_in, s->tokens.as<int32_t>(), U, s->ntok.as<int32_t>(), nullptr,
+                                        nullptr, nullptr, 0, stream);
+  h->lm_blob = static_cast<float*>(prev_blob); h->lm_blob_B = prev_B;
+  if (r) return r;
+  s->fresh = false;
+  CK(cudaMemcpy2DAsync(tokens_host, (size_t)U_cap * 4, s->tokens.p, (size_t)U * 4, (size_t)U * 4, B, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ntok_host, s->ntok.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *advanced = 1;
+  return RNNT_B200_OK;
+}
+
 int32_t rnnt_b200_selftest_gemm(rnnt_b200_handle h, const float* A, const float* W, const float* bias, float* C, int64_t M,
                                 int32_t N, int32_t K, int32_t gemm_mode, void* stream) {
   if (!h || !A || !W || !C || M < 1 || N < 1 || K < 1 || (K & 3) || (N & 3)) return fail(h, RNNT_B200_ERR_INVALID, "selftest_gemm: bad arguments");

@@ -448,3 +448,40 @@ def test_lm_errors():
     _, _, plain, _ = model_for("tiny")
     with pytest.raises(Exception):
         plain.engine().new_lm_state(1)                            # handle without a language model
+
+
+# ---------------- streaming sessions (rnnt_b200_stream_*) ----------------
+def _oracle_stream_tokens(orc, cfg, audio_1d, n_chunks, lm=None):
+    fe = O.StreamFrontend(cfg)
+    rows = [fe.push(torch.from_numpy(audio_1d[None, j * CHUNK:(j + 1) * CHUNK])) for j in range(n_chunks)]
+    ys = list(orc.transcribe_stream(iter(rows), max_iters=10, lm=lm))
+    return [list(y) for _, y in ys]
+
+
+@pytest.mark.parametrize("with_lm", [False, True])
+def test_stream_session_many_streams_match_oracle_and_reset(with_lm):
+    """5 concurrent streams through the C streaming session (host chunks in, host tokens out): every stream's per-tick
+    tokens equal the oracle's transcribe_stream run on that stream alone; reset() starts all streams over."""
+    from libreasr_b200.api import StreamBatch
+
+    if with_lm:
+        cfg, lc, m, orc, olm = lm_model_for("tiny", "tiny")
+    else:
+        cfg, sd, m, orc = model_for("tiny")
+        olm = None
+    eng = m.engine()
+    S, n_chunks = 5, 24
+    audio = weights.make_audio(S, n_chunks * CHUNK, seed=71)
+    want = [_oracle_stream_tokens(orc, cfg, audio[b], n_chunks, olm) for b in range(S)]
+    sb = StreamBatch(eng, S, max_iters=10)
+    for rep in range(2):
+        ticks = [[] for _ in range(S)]
+        for j in range(n_chunks):
+            slab = torch.from_numpy(np.ascontiguousarray(audio[:, j * CHUNK:(j + 1) * CHUNK]))
+            new = sb.push(slab if j % 2 else slab.cuda())   # host and device chunk sources
+            if new is not None:
+                for b in range(S):
+                    ticks[b].append(new[b])
+        assert ticks == want, f"pass {rep}"
+        sb.reset()
+    sb.close()

@@ -17,8 +17,9 @@ def main():
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--gemm-mode", type=int, default=1)
+    ap.add_argument("--config", default="cfg2", help="cfg2 (BASELINE configs[1]) or cfg4 (configs[3] shape: 6x1536, 15 s)")
     a = ap.parse_args()
-    cfg = synth.CONFIGS["cfg2"]
+    cfg = synth.CONFIGS[a.config]
     ec = EngineConfig(n_mels=cfg.n_mels, n_stack=cfg.n_stack, downsample=cfg.downsample, enc_layers=cfg.enc_layers,
                       pred_layers=cfg.pred_layers, hidden_sz=cfg.hidden_sz, embed_sz=cfg.embed_sz, joint_sz=cfg.joint_sz,
                       vocab_sz=cfg.vocab_sz, gemm_mode=a.gemm_mode)
@@ -41,7 +42,7 @@ def main():
         ms = e0.elapsed_time(e1) / a.steps
         rows.append({"batch": B, "ms_per_step": round(ms, 3), "rtfx": round(B * a.seconds / (ms * 1e-3), 1),
                      "tokens": int(out["ntok"].sum().item())})
-    print(json.dumps({"metric": "offline RTFx vs utterance batch (cfg2, 10 s utterances, 1 GPU, device-resident inputs)",
+    print(json.dumps({"metric": "offline greedy RTFx vs utterance batch (%s, %.0f s utterances, 1 GPU, device-resident inputs)" % (a.config, a.seconds),
                       "gemm_mode": a.gemm_mode, "rows": rows}))
 
 
