@@ -924,7 +924,17 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     // (64 for the tcgen05 kernel, 256 for the fp32 one).  State tensors are [Lp, B, H], i.e. not sliceable
     // per sub-batch, so stateful (streaming) calls must fit one launch.
     // With a fused language model the loop runs in the fp32 cooperative kernel (decode.cu), whatever gemm_mode says.
-    const int cap = (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && c.lm_layers == 0) ? 64 : kDecodeMaxBatch;
+    int cap = kDecodeMaxBatch;
+    if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && c.lm_layers == 0) {
+      // the tcgen05 kernel takes up to 64 utterances; some shapes (e.g. H = 1536: 12 vocabulary rows per epilogue
+      // thread at 64) only plan for 32, which still beats falling back to the fp32 kernel
+      DecodeTcPlan probe;
+      cap = 64;
+      if (B > 32 && !(pred_state_h || pred_out || use_state_in) &&
+          !decode_tc_plan(c.hidden_sz, c.joint_sz, c.vocab_sz, c.pred_layers, std::min(B, 64), h->sm_count, &probe) &&
+          decode_tc_plan(c.hidden_sz, c.joint_sz, c.vocab_sz, c.pred_layers, 32, h->sm_count, &probe))
+        cap = 32;
+    }
     if (B > cap) {
       if (pred_state_h || pred_out || use_state_in || h->lm_blob)
         return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: stateful calls are limited to " + std::to_string(cap) + " streams per call");
