@@ -84,6 +84,11 @@ struct rnnt_b200_handle_s {
   // fused language model (lm.py): fp32 layouts + per-call fuser workspace / registered stream blob
   LmWeights lmw;
   DevBuf lm_ws, lm_logitT, lm_part, lm_jpart, lm_fpart;
+  bool lm_tc_ok = false;      // LM phases available in the tcgen05 decode kernel for this shape
+  uint8_t* lmR_img[kTcLmLayers] = {};   // operand images of the LM weight slices (TR = NC_L / NC_B)
+  uint8_t* lmW_img[kTcLmLayers] = {};
+  uint8_t* lmWo_img = nullptr;
+  DevBuf lm_himg, lm_stat;
   float* lm_blob = nullptr;   // caller-owned fuser state (rnnt_b200_set_lm_state); nullptr = fresh fuser per call
   int lm_blob_B = 0;
   // profiling
@@ -293,7 +298,7 @@ int32_t rnnt_b200_destroy(rnnt_b200_handle h) {
   DevBuf* bufs[] = {&h->feats, &h->lnx, &h->xp, &h->ya, &h->yb, &h->ep, &h->ehT[0], &h->ehT[1], &h->ecT, &h->dhT, &h->dxT,
                     &h->dgT, &h->deT, &h->dppT, &h->dzT, &h->dpart, &h->dlse, &h->t_audio, &h->t_lens, &h->t_tokens,
                     &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc, &h->a_img, &h->x_img[0], &h->x_img[1], &h->gbar, &h->dimg, &h->dkeys,
-                    &h->lm_ws, &h->lm_logitT, &h->lm_part, &h->lm_jpart, &h->lm_fpart};
+                    &h->lm_ws, &h->lm_logitT, &h->lm_part, &h->lm_jpart, &h->lm_fpart, &h->lm_himg, &h->lm_stat};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t* set : h->evsets) {
     for (int i = 0; i < kEvPerSet; ++i) cudaEventDestroy(set[i]);
@@ -592,6 +597,9 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
     const int Hl = c.lm_hidden_sz, El = c.lm_embed_sz, Ll = c.lm_layers;
     LmWeights& lw = h->lmw;
     lw.L = Ll; lw.Hl = Hl; lw.alpha = c.lm_alpha; lw.theta = c.lm_theta;
+    DecodeTcPlan lpl;
+    const bool lm_tc = h->dec_tc_ok && decode_tc_wplan(H, J, V, h->sm_count, &lpl, Ll, Hl);
+    h->lm_tc_ok = lm_tc;
     int* lperm4 = nullptr;
     {
       std::vector<int> p4(4 * Hl);
@@ -617,6 +625,13 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
       LAUNCH(1, launch_gather_rows(d_whh, d_r, lperm4, 4 * Hl, Hl, st));   // rows unit*4+gate
       LAUNCH(1, launch_transpose(d_r, Hl, Rt, 4 * Hl, Hl, st));            // [Hl][4Hl interleaved]
       lw.Rt[l] = Rt;
+      if (lm_tc) {
+        void* img = nullptr;
+        CK(cudaMalloc(&img, img_bytes((int64_t)lpl.G_l * lpl.NC_L, Hl, lpl.NC_L)));
+        h->weight_allocs.push_back(img);
+        h->lmR_img[l] = (uint8_t*)img;
+        LAUNCH(1, launch_to_image(d_r, Hl, 4 * Hl, Hl, lpl.NC_L, (uint8_t*)img, st));   // d_r: [4Hl interleaved][Hl]
+      }
       float* d_wih;
       CK(tmp_upload(*wih, &d_wih));
       if (l == 0) {
@@ -633,6 +648,13 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
         CK(dalloc(h, (size_t)4 * Hl * Hl, &Wt));
         LAUNCH(1, launch_gather_rows(d_wih, d_a, lperm4, 4 * Hl, Hl, st));
         LAUNCH(1, launch_transpose(d_a, Hl, Wt, 4 * Hl, Hl, st));
+        if (lm_tc) {
+          void* img = nullptr;
+          CK(cudaMalloc(&img, img_bytes((int64_t)lpl.G_l * lpl.NC_L, Hl, lpl.NC_L)));
+          h->weight_allocs.push_back(img);
+          h->lmW_img[l] = (uint8_t*)img;
+          LAUNCH(1, launch_to_image(d_a, Hl, 4 * Hl, Hl, lpl.NC_L, (uint8_t*)img, st));
+        }
         std::vector<float> bi(4 * Hl);
         for (int u = 0; u < Hl; ++u)
           for (int g = 0; g < 4; ++g) bi[u * 4 + g] = bsum[g * Hl + u];
@@ -644,6 +666,13 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
     CK(tmp_upload(*lwo, &d_wo));
     CK(dalloc(h, (size_t)Hl * V, &Wo_t));
     LAUNCH(1, launch_transpose(d_wo, Hl, Wo_t, V, Hl, st));   // [V][Hl] -> [Hl][V]
+    if (lm_tc) {
+      void* img = nullptr;
+      CK(cudaMalloc(&img, img_bytes((int64_t)lpl.G * lpl.NC_B, Hl, lpl.NC_B)));
+      h->weight_allocs.push_back(img);
+      h->lmWo_img = (uint8_t*)img;
+      LAUNCH(1, launch_to_image(d_wo, Hl, V, Hl, lpl.NC_B, (uint8_t*)img, st));
+    }
     CK(upload(h, *lbo, &t_bo));
     lw.Wo_t = Wo_t; lw.bo = t_bo;
   }
@@ -925,19 +954,21 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     // per sub-batch, so stateful (streaming) calls must fit one launch.
     // With a fused language model the loop runs in the fp32 cooperative kernel (decode.cu), whatever gemm_mode says.
     int cap = kDecodeMaxBatch;
-    if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && c.lm_layers == 0) {
+    if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && (c.lm_layers == 0 || h->lm_tc_ok)) {
       // the tcgen05 kernel takes up to 64 utterances; some shapes (e.g. H = 1536: 12 vocabulary rows per epilogue
       // thread at 64) only plan for 32, which still beats falling back to the fp32 kernel
       DecodeTcPlan probe;
       cap = 64;
       if (B > 32 && !(pred_state_h || pred_out || use_state_in) &&
-          !decode_tc_plan(c.hidden_sz, c.joint_sz, c.vocab_sz, c.pred_layers, std::min(B, 64), h->sm_count, &probe) &&
-          decode_tc_plan(c.hidden_sz, c.joint_sz, c.vocab_sz, c.pred_layers, 32, h->sm_count, &probe))
+          !decode_tc_plan(c.hidden_sz, c.joint_sz, c.vocab_sz, c.pred_layers, std::min(B, 64), h->sm_count, &probe, c.lm_layers, c.lm_hidden_sz) &&
+          decode_tc_plan(c.hidden_sz, c.joint_sz, c.vocab_sz, c.pred_layers, 32, h->sm_count, &probe, c.lm_layers, c.lm_hidden_sz))
         cap = 32;
     }
-    if (B > cap) {
-      if (pred_state_h || pred_out || use_state_in || h->lm_blob)
-        return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: stateful calls are limited to " + std::to_string(cap) + " streams per call");
+    const bool stateful = pred_state_h || pred_out || use_state_in || h->lm_blob;
+    if (stateful && B > kDecodeMaxBatch)
+      return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: stateful calls are limited to " + std::to_string(kDecodeMaxBatch) + " streams per call");
+    // (a stateful call beyond the tcgen05 kernel's capacity falls through to the fp32 cooperative kernel below)
+    if (B > cap && !stateful) {
       for (int b0 = 0; b0 < B; b0 += cap) {
         const int nb = std::min(cap, B - b0);
         const int r = rnnt_b200_decode_greedy(h, enc + (size_t)b0 * T * c.hidden_sz, lens_T ? lens_T + b0 : nullptr, nb, T, max_iters,
@@ -966,8 +997,8 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
   }
   if (h->ev) cudaEventRecord(h->ev[3], st);
   DecodeTcPlan dpl;
-  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && c.lm_layers == 0 &&
-      decode_tc_plan(H, J, c.vocab_sz, c.pred_layers, B, h->sm_count, &dpl)) {
+  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && (c.lm_layers == 0 || h->lm_tc_ok) &&
+      decode_tc_plan(H, J, c.vocab_sz, c.pred_layers, B, h->sm_count, &dpl, c.lm_layers, c.lm_hidden_sz)) {
     const size_t one = (size_t)(std::max(H, J) / 64) * 2 * dpl.Bpad8 * 128;
     const int nimg = 4 + 2 * c.pred_layers;
     CK(h->dimg.ensure(one * nimg));
@@ -1003,6 +1034,39 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     t.tokens = tokens_out; t.U_cap = U_cap; t.ntok = ntok_out; t.neg_logp = neg_logp_out; t.iters = iters_out;
     t.trace = trace_logp; t.trace_cap = trace_logp ? trace_cap : 0;
     t.barrier = h->gbar.as<unsigned int>();
+    if (c.lm_layers > 0) {   // LMFuser (lm.py:43-83) inside the tcgen05 loop
+      const int V = c.vocab_sz, Ll = c.lm_layers, Hl = c.lm_hidden_sz;
+      const size_t nfl = lm_state_floats(Ll, Hl, V, Bp);
+      float* blob = h->lm_blob;
+      if (blob) {
+        if (h->lm_blob_B != B) return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: the registered LM state was sized for " +
+                                                                        std::to_string(h->lm_blob_B) + " streams, call has " + std::to_string(B));
+      } else {
+        CK(h->lm_ws.ensure(nfl * 4));
+        CK(cudaMemsetAsync(h->lm_ws.p, 0, nfl * 4, st));
+        blob = h->lm_ws.as<float>();
+      }
+      const size_t lone = (size_t)(Hl / 64) * 2 * dpl.Bpad8 * 128;
+      CK(h->lm_himg.ensure(lone * 2 * Ll));
+      const size_t stat_bytes = (size_t)max_steps * dpl.Bq * 16;   // jstat | lmstat | fkeys (8 B each)
+      CK(h->lm_stat.ensure(stat_bytes * 2 + (size_t)max_steps * dpl.Bq * 8));
+      CK(cudaMemsetAsync(h->lm_stat.p, 0, stat_bytes * 2 + (size_t)max_steps * dpl.Bq * 8, st));
+      DecodeTcLm& L = t.lm;
+      L.L = Ll; L.Hl = Hl; L.alpha = c.lm_alpha; L.theta = c.lm_theta;
+      L.table0 = h->lmw.table0; L.bo = h->lmw.bo;
+      for (int l = 0; l < Ll; ++l) {
+        L.bias[l] = h->lmw.bias[l];
+        L.r_img[l] = h->lmR_img[l]; L.w_img[l] = h->lmW_img[l];
+        L.h_img[l][0] = h->lm_himg.as<uint8_t>() + (size_t)(2 * l) * lone;
+        L.h_img[l][1] = h->lm_himg.as<uint8_t>() + (size_t)(2 * l + 1) * lone;
+      }
+      L.wo_img = h->lmWo_img;
+      L.st = lm_state_view(blob, Ll, Hl, V, Bp);
+      L.Bp = Bp;
+      L.jstat = h->lm_stat.as<double>();
+      L.lmstat = reinterpret_cast<double*>(h->lm_stat.as<uint8_t>() + stat_bytes);
+      L.fkeys = reinterpret_cast<unsigned long long*>(h->lm_stat.as<uint8_t>() + 2 * stat_bytes);
+    }
     static const bool ddbg = getenv("RNNT_DEC_DBG") != nullptr;
     unsigned long long* dbg = nullptr;
     const int dcap = 8192;
@@ -1178,7 +1242,7 @@ int32_t rnnt_b200_stream_open(rnnt_b200_handle h, int32_t B, int32_t chunk, int3
   if (!out) return fail(h, RNNT_B200_ERR_INVALID, "stream_open: null argument");
   *out = nullptr;
   const rnnt_b200_config& c = h->cfg;
-  const int cap = (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && c.lm_layers == 0) ? 64 : kDecodeMaxBatch;
+  const int cap = kDecodeMaxBatch;   // beyond the tcgen05 kernel's 64 streams the fp32 kernel takes over
   if (B < 1 || B > cap) return fail(h, RNNT_B200_ERR_INVALID, "stream_open: n_streams must be in [1, " + std::to_string(cap) + "]");
   if (chunk < 1 || n_window < 1 || n_buffer < 1 || n_buffer > 64 || max_iters < 1 || max_iters > 255)
     return fail(h, RNNT_B200_ERR_INVALID, "stream_open: bad arguments");

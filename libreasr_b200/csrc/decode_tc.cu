@@ -51,8 +51,27 @@ struct Ctrl {
   int t[DT_MAXB], it[DT_MAXB], ntok[DT_MAXB], tok[DT_MAXB], n_eval[DT_MAXB], len[DT_MAXB];
   float red[4][DT_MAXB][4];   // partial (max, argmax, sumexp) exchange between the threads of one batch row
   unsigned char active[DT_MAXB], emit[DT_MAXB];
-  int flags[2];               // any_emit, any_active of the current step
+  int flags[3];               // any_emit, any_active of the current step; any pending fused arg max
+  // LM fusion
+  float j_mean[DT_MAXB], j_rstd[DT_MAXB], lm_mean[DT_MAXB], lm_rstd[DT_MAXB];   // standardisation constants (utils.py:162-164)
+  int am[DT_MAXB];
+  unsigned char pend[DT_MAXB], lm_valid[DT_MAXB];
 };
+constexpr float kLmMinVal = -10.0f;  // lm.py:15
+constexpr float kLmStdEps = 1e-5f;   // utils.py:162
+constexpr int DT_LM_UPT = 4;         // LM units per epilogue thread
+__device__ __forceinline__ void standardize_consts(double s, double q, int n, float* mean, float* rstd) {
+  const double m = s / n;
+  double var = (q - s * m) / (n - 1);   // unbiased, torch.Tensor.std
+  if (var < 0.0) var = 0.0;
+  *mean = (float)m;
+  *rstd = 1.0f / ((float)sqrt(var) + kLmStdEps);
+}
+__device__ __forceinline__ unsigned long long pack_key(float m, int idx) {   // orderable (value, lowest index wins ties)
+  unsigned u = __float_as_uint(m);
+  u ^= (u & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u;
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx);
+}
 
 // n (1, 2 or 4) consecutive k of one image row as hi / lo halves
 __device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, int r, int k, int n, const float* v) {
@@ -83,6 +102,9 @@ struct Gemm {
                         // 0: it is older (the recurrent state h of a predictor layer) and can stream immediately
 };
 
+// LM = true instantiates the LM shallow-fusion phases (LMFuser, reference libreasr/lib/lm.py:43-83): see the block
+// comment at `lm_phase` below.  The LM = false instantiation is the plain greedy loop.
+template <bool LM>
 __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -108,7 +130,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
   uint64_t* ctlbar = tempty + 1;
   uint64_t* tfull_r = ctlbar + 1;    // speculative recurrent products (all predictor layers) complete
   uint64_t* tempty_r = tfull_r + 1;  // ... and drained by the predictor phases that consumed them
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(tempty_r + 1);
+  uint64_t* tfull_l = tempty_r + 1;  // LM accumulators (layer products / output projection) complete
+  uint64_t* tempty_l = tfull_l + 1;  // ... and drained
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(tempty_l + 1);
   const int nB = (V + p.NC_B - 1) / p.NC_B;                     // CTAs that produce a softmax partial
 
   if (threadIdx.x == 0) {
@@ -122,6 +146,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     mbar_init(ctlbar, 1);
     mbar_init(tfull_r, 1);
     mbar_init(tempty_r, 128);
+    mbar_init(tfull_l, 1);
+    mbar_init(tempty_l, 128);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tptr, p.tmem_cols);
@@ -162,6 +188,21 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
   // products stay valid (h unchanged) and are consumed by the next predictor run.
   auto rec_gemm = [&](int l, int par) -> Gemm {
     return Gemm{p.h_img[l][par], p.r_img[l] + img_tile_offset(cta, 0, 0, KBH, p.NC_C), KBH, p.NC_C, p.rec_col0 + l * p.rec_cols, 0};
+  };
+  // ---- LM (lm.py:20-41): G_l CTAs own Ul units (NC_L = 4 Ul gate rows) of every LSTM layer; the output projection is
+  // sliced over the vocabulary exactly like phase B.  LM accumulators live in their own TMEM block [lm_col0, ...):
+  // input product at +0, recurrent product at +2 NC_L; the output projection reuses +0.
+  const DecodeTcLm& lm = p.lm;
+  const int Ll = LM ? lm.L : 0, KBL = LM ? lm.Hl / 64 : 0;
+  const bool in_L = LM && cta < p.G_l;
+  auto lm_rec_gemm = [&](int l, int lpar) -> Gemm {   // h_l of the previous LM run: not gated
+    return Gemm{lm.h_img[l][lpar], lm.r_img[l] + img_tile_offset(cta, 0, 0, KBL, p.NC_L), KBL, p.NC_L, p.lm_col0 + 2 * p.NC_L, 0};
+  };
+  auto lm_in_gemm = [&](int l, int lpar) -> Gemm {    // h_{l-1} of THIS run (written one phase ago): gated
+    return Gemm{lm.h_img[l - 1][lpar ^ 1], lm.w_img[l] + img_tile_offset(cta, 0, 0, KBL, p.NC_L), KBL, p.NC_L, p.lm_col0, 1};
+  };
+  auto lm_out_gemm = [&](int lpar) -> Gemm {          // top layer's h of the run just finished: gated
+    return Gemm{lm.h_img[Ll - 1][lpar], lm.wo_img + img_tile_offset(cta, 0, 0, KBL, p.NC_B), KBL, p.NC_B, p.lm_col0, 1};
   };
 
   if (warp == 0 || warp == 6) {
@@ -215,29 +256,58 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
       gate(hgate);
       for (int l = 0; l < Lp; ++l) run_gemm(rec_gemm(l, par));
     };
-    int par = 0;
+    int par = 0, lpar = 0;
+    bool lm_pending = false;   // an LM run finished; its output projection rides on the next phase A
     gate(1);   // the initial operand images (written by every CTA's epilogue warps) precede even the ungated GEMMs
+    // one grid phase of a predictor (+ LM) run: layer i of both
+    auto run_layer_phase = [&](int i, bool with_lm) {
+      Gemm gm[2];
+      if (i < Lp) {
+        const int ng = phase_gemms(2 + i, par, gm);
+        for (int q = 0; q < ng; ++q) { gate(nbar); run_gemm(gm[q]); }
+      }
+      if (LM && with_lm && i < Ll && in_L) {
+        gate(hgate);
+        run_gemm(lm_rec_gemm(i, lpar));
+        if (i > 0) { gate(nbar); run_gemm(lm_in_gemm(i, lpar)); }
+      }
+      ++nbar;
+    };
     if (!p.use_state_in) {
       run_spec(par);
-      for (int l = 0; l < Lp; ++l) run_phase(2 + l, par);
+      for (int l = 0; l < Lp; ++l) run_layer_phase(l, false);
       par ^= 1;
       hgate = nbar;
     }
     bool any_upd = true, spec_valid = false;
     for (int step = 0;; ++step) {
-      if (any_upd) run_phase(0, par); else ++nbar;
+      if (any_upd) {
+        Gemm gm[2];
+        const int ng = phase_gemms(0, par, gm);
+        for (int q = 0; q < ng; ++q) { gate(nbar); run_gemm(gm[q]); }
+        if (LM && lm_pending && in_B) { gate(nbar); run_gemm(lm_out_gemm(lpar)); }
+        lm_pending = false;
+      }
+      ++nbar;
       run_phase(1, par);
       if (!spec_valid) { run_spec(par); spec_valid = true; }
       mbar_wait(ctlbar, step & 1);
       const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
+      if (LM && c.flags[2]) ++nbar;   // the fused-arg-max barrier of this step (no GEMM)
       if (any_emit) {
-        for (int l = 0; l < Lp; ++l) run_phase(2 + l, par);
+        const int nph = (LM && Ll > Lp) ? Ll : Lp;
+        for (int i = 0; i < nph; ++i) run_layer_phase(i, true);
         par ^= 1;
         hgate = nbar;
         spec_valid = false;
+        if (LM) { lpar ^= 1; lm_pending = true; }
       }
       any_upd = any_emit;
       if (!any_active) break;
+    }
+    if (LM && lm_pending) {   // the fuser must hold the row of the last emitted token (lm.py:50-54)
+      if (in_B) { gate(nbar); run_gemm(lm_out_gemm(lpar)); }
+      ++nbar;
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
@@ -292,27 +362,50 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
       for (int l = 0; l < Lp; ++l) run_gemm(rec_gemm(l, par), l == Lp - 1 ? tfull_r : nullptr);
       ++nspec;
     };
-    int par = 0;
+    uint32_t nacc_l = 0;
+    // LM accumulators: one (tfull_l, tempty_l) hand-over per LM layer phase / output projection
+    auto lm_begin = [&]() {
+      if (nacc_l > 0) mbar_wait(tempty_l, (nacc_l - 1) & 1);
+      tc_fence_after();
+      ++nacc_l;
+    };
+    int par = 0, lpar = 0;
+    bool lm_pending = false;
+    auto run_layer_phase = [&](int i, bool with_lm) {
+      if (i < Lp) run_phase(2 + i, par);
+      if (LM && with_lm && i < Ll && in_L) {
+        lm_begin();
+        run_gemm(lm_rec_gemm(i, lpar), i == 0 ? tfull_l : nullptr);
+        if (i > 0) run_gemm(lm_in_gemm(i, lpar), tfull_l);
+      }
+    };
     if (!p.use_state_in) {
       run_spec(par);
-      for (int l = 0; l < Lp; ++l) run_phase(2 + l, par);
+      for (int l = 0; l < Lp; ++l) run_layer_phase(l, false);
       par ^= 1;
     }
     bool any_upd = true, spec_valid = false;
     for (int step = 0;; ++step) {
-      if (any_upd) run_phase(0, par);
+      if (any_upd) {
+        run_phase(0, par);
+        if (LM && lm_pending && in_B) { lm_begin(); run_gemm(lm_out_gemm(lpar), tfull_l); }
+        lm_pending = false;
+      }
       run_phase(1, par);
       if (!spec_valid) { run_spec(par); spec_valid = true; }
       mbar_wait(ctlbar, step & 1);
       const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
       if (any_emit) {
-        for (int l = 0; l < Lp; ++l) run_phase(2 + l, par);
+        const int nph = (LM && Ll > Lp) ? Ll : Lp;
+        for (int i = 0; i < nph; ++i) run_layer_phase(i, true);
         par ^= 1;
         spec_valid = false;
+        if (LM) { lpar ^= 1; lm_pending = true; }
       }
       any_upd = any_emit;
       if (!any_active) break;
     }
+    if (LM && lm_pending && in_B) { lm_begin(); run_gemm(lm_out_gemm(lpar), tfull_l); }
   } else {
     // =========================== epilogue ===========================
     const int q = warp & 3;
@@ -435,6 +528,48 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
         store_act(p.g_img, unit0, upt, gval);
       }
     }
+    // ---- LM fuser state (lm.py:43-48): per-thread slices kept in shared memory, column et of each array ----
+    //   lmh / lmc [Ll][upt_l][128]   hidden / cell state of this thread's (b, units)
+    //   lmv / lvj [rptB][128]        LM logits / joint logits of this thread's (b, vocabulary rows)
+    //   dred [4][DT_MAXB][2]         double exchange between the threads of one batch row
+    const int upt_l = LM ? p.Ul * Bq / 128 : 0;
+    const int lunit0 = cta * p.Ul + sub * upt_l;
+    float* lmh = reinterpret_cast<float*>(base + p.lm_offset);
+    float* lmc = lmh + Ll * upt_l * 128;
+    float* lmv = lmc + Ll * upt_l * 128;
+    float* lvj = lmv + rptB * 128;
+    double* dred = reinterpret_cast<double*>(lvj + rptB * 128);
+    uint32_t nacc_l = 0;
+    int lpar = 0, lm_runs = 0;   // LM runs whose output projection has been folded into lmv / lmstat
+    bool lm_pending = false;
+    if constexpr (LM) {
+      const int Bp = lm.Bp, Hl = lm.Hl;
+      for (int i = et; i < DT_MAXB; i += 128) {
+        const bool v = i < B && lm.st.valid[i] != 0.f;
+        c.lm_valid[i] = v;
+        c.lm_mean[i] = v ? lm.st.stats[i] : 0.f;
+        c.lm_rstd[i] = v ? lm.st.stats[Bp + i] : 0.f;
+        c.pend[i] = 0;
+      }
+      if (in_L) {
+        for (int l = 0; l < Ll; ++l) {
+          float hv[DT_LM_UPT];
+#pragma unroll
+          for (int i = 0; i < DT_LM_UPT; ++i) {
+            if (i < upt_l) {
+              const size_t si = (size_t)(lunit0 + i) * Bp + b;
+              hv[i] = bvalid ? lm.st.h[(size_t)l * 2 * Hl * Bp + si] : 0.f;
+              lmh[(l * upt_l + i) * 128 + et] = hv[i];
+              lmc[(l * upt_l + i) * 128 + et] = bvalid ? lm.st.c[(size_t)l * Hl * Bp + si] : 0.f;
+            }
+          }
+          if (bvalid) store_act(lm.h_img[l][0], lunit0, upt_l, hv);
+        }
+      }
+      if (in_B)
+        for (int i = 0; i < rptB; ++i)
+          lmv[i * 128 + et] = (bvalid && vB0 + i < V) ? lm.st.logits[(size_t)(vB0 + i) * Bp + b] : 0.f;
+    }
     grid_arrive();
 
     // ---- predictor layer l (GRU cell + BatchNorm), haste/nbrc.py:46-56 ----
@@ -490,11 +625,103 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
           store_act(p.x_img[l & 1], unit0, upt, xo);
         }
       }
+    };
+    // ---- LM layer l (torch.nn.LSTM cell, gate order i,f,g,o; lm.py:23,33-36), sharing a grid phase with predictor
+    // layer l.  Only streams that emitted a token this step advance (LMFuser.advance, lm.py:50-54); layer 0's input
+    // projection is a row of the Embedding * W_ih0 table. ----
+    auto lm_phase = [&](int l, bool after_pred) {
+      if (!in_L) return;
+      const int NC = p.NC_L, Hl = lm.Hl;
+      const bool em = bvalid && c.emit[b] != 0;
+      float vxin[DT_LM_UPT][4];
+      if (em) {
+#pragma unroll
+        for (int i = 0; i < DT_LM_UPT; ++i) {
+          if (i < upt_l) {
+            const int unit = lunit0 + i;
+            if (l == 0) {
+              const float* row = lm.table0 + (size_t)c.tok[b] * (4 * Hl);
+#pragma unroll
+              for (int gg = 0; gg < 4; ++gg) vxin[i][gg] = row[gg * Hl + unit];
+            } else {
+#pragma unroll
+              for (int gg = 0; gg < 4; ++gg) vxin[i][gg] = lm.bias[l][unit * 4 + gg];
+            }
+          }
+        }
+      }
+      if (after_pred) named_bar_sync(1, 128);   // the predictor part has finished reading the exchange buffers
+      mbar_wait(tfull_l, nacc_l & 1);
+      tc_fence_after();
+      if (l > 0) copy_cols(p.lm_col0, 2 * NC, 0);
+      copy_cols(p.lm_col0 + 2 * NC, 2 * NC, 2 * NC);
+      tc_fence_before();
+      mbar_arrive(tempty_l);
+      ++nacc_l;
+      named_bar_sync(1, 128);
+      if (bvalid) {
+        float hv[DT_LM_UPT];
+#pragma unroll
+        for (int i = 0; i < DT_LM_UPT; ++i) {
+          if (i < upt_l) {
+            const int lr = (sub * upt_l + i) * 4, si = (l * upt_l + i) * 128 + et;
+            float h = lmh[si];
+            if (em) {
+              float v[4];
+#pragma unroll
+              for (int gg = 0; gg < 4; ++gg)
+                v[gg] = ((l == 0) ? vxin[i][gg] : pre_val(0, NC, lr + gg) + vxin[i][gg]) + pre_val(2 * NC, NC, lr + gg);
+              const float ig = sigmoidf_acc(v[0]), fg = sigmoidf_acc(v[1]), gg_ = tanhf(v[2]), og = sigmoidf_acc(v[3]);
+              const float cn = fg * lmc[si] + ig * gg_;
+              lmc[si] = cn;
+              h = og * tanhf(cn);
+              lmh[si] = h;
+            }
+            hv[i] = h;
+          }
+        }
+        store_act(lm.h_img[l][lpar ^ 1], lunit0, upt_l, hv);
+      }
+    };
+    // LM output projection (lm.py:37-40) for this CTA's vocabulary rows: raw logits (log_softmax is a per-row shift
+    // that standardisation removes) + the (sum, sum of squares) the fuser standardises with (utils.py:162-164)
+    auto lm_out_epilogue = [&](bool after_other) {
+      if (!in_B) return;
+      if (after_other) named_bar_sync(1, 128);
+      mbar_wait(tfull_l, nacc_l & 1);
+      tc_fence_after();
+      copy_cols(p.lm_col0, 2 * p.NC_B, 0);
+      tc_fence_before();
+      mbar_arrive(tempty_l);
+      ++nacc_l;
+      named_bar_sync(1, 128);
+      double sd = 0.0, qd = 0.0;
+      if (bvalid) {
+        for (int i = 0; i < rptB; ++i) {
+          const int v = vB0 + i;
+          if (v < V) {
+            const float x = pre_val(0, p.NC_B, sub * rptB + i) + lm.bo[v];
+            lmv[i * 128 + et] = x;
+            sd += (double)x; qd += (double)x * (double)x;
+          }
+        }
+        dred[(sub * DT_MAXB + b) * 2] = sd; dred[(sub * DT_MAXB + b) * 2 + 1] = qd;
+      }
+      named_bar_sync(1, 128);
+      if (bvalid && sub == 0) {
+        for (int k = 1; k < tpr; ++k) { sd += dred[(k * DT_MAXB + b) * 2]; qd += dred[(k * DT_MAXB + b) * 2 + 1]; }
+        atomicAdd(lm.lmstat + ((size_t)lm_runs * Bq + b) * 2, sd);
+        atomicAdd(lm.lmstat + ((size_t)lm_runs * Bq + b) * 2 + 1, qd);
+      }
+    };
+    auto layer_phase = [&](int i, bool with_lm) {
+      if (i < Lp) predictor_phase(i);
+      if (LM && with_lm && i < Ll) lm_phase(i, i < Lp);
       grid_arrive();
     };
 
-    if (!p.use_state_in) {   // feed BOS from the learnable initial state (models.py:397-398)
-      for (int l = 0; l < Lp; ++l) predictor_phase(l);
+    if (!p.use_state_in) {   // feed BOS from the learnable initial state (models.py:397-398); the LM only sees emitted tokens
+      for (int l = 0; l < Lp; ++l) layer_phase(l, false);
       par ^= 1;
     }
 
@@ -521,6 +748,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
           }
         }
         if (act) store_act(p.z_img, jA0, rptA, zv);
+      }
+      if (LM && lm_pending) {   // rides on phase A: the row the fuser holds for the tokens emitted last step
+        lm_out_epilogue(any_upd && in_A);
+        ++lm_runs;
+        lm_pending = false;
       }
       grid_arrive();
       stamp(0);
@@ -550,8 +782,24 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
               if (i < rptB && vB0 + i < V) tr[i] = lv[i];
           }
           c.red[sub][b][0] = m; c.red[sub][b][1] = __int_as_float(am); c.red[sub][b][2] = s;
+          if constexpr (LM) {   // the fuser standardises the joint row too (lm.py:59-61)
+            double sd = 0.0, qd = 0.0;
+            for (int i = 0; i < rptB; ++i) {
+              if (vB0 + i < V) {
+                lvj[i * 128 + et] = lv[i];
+                sd += (double)lv[i]; qd += (double)lv[i] * (double)lv[i];
+              }
+            }
+            dred[(sub * DT_MAXB + b) * 2] = sd; dred[(sub * DT_MAXB + b) * 2 + 1] = qd;
+          }
         }
         named_bar_sync(1, 128);
+        if (LM && bvalid && sub == 0 && c.active[b] && step < p.max_steps) {
+          double sd = 0.0, qd = 0.0;
+          for (int k = 0; k < tpr; ++k) { sd += dred[(k * DT_MAXB + b) * 2]; qd += dred[(k * DT_MAXB + b) * 2 + 1]; }
+          atomicAdd(lm.jstat + ((size_t)step * Bq + b) * 2, sd);
+          atomicAdd(lm.jstat + ((size_t)step * Bq + b) * 2 + 1, qd);
+        }
         if (bvalid && sub == 0) {
           for (int k = 1; k < tpr; ++k) {   // ascending vocabulary order, strict > keeps the first maximum
             const float m2 = c.red[k][b][0], s2 = c.red[k][b][2];
@@ -576,17 +824,84 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
 
       // ---------------- R: greedy rule (models.py:408-437), identical in every CTA ----------------
       {
+        const int kstep = min(step, p.max_steps - 1);
+        if (et < B) {
+          const int bb = et;
+          c.pend[bb] = 0;
+          if (c.active[bb]) {
+            const unsigned long long key = __ldcg(p.keys + (size_t)kstep * Bq + bb);
+            const int am2 = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+            c.am[bb] = am2;
+            if constexpr (LM) {
+              // LMFuser.fuse applies to a non-blank decision once the fuser holds an LM row (models.py:427-431, lm.py:58)
+              if (am2 != w.blank && c.lm_valid[bb]) {
+                const double* js = lm.jstat + ((size_t)kstep * Bq + bb) * 2;
+                standardize_consts(__ldcg(js), __ldcg(js + 1), V, &c.j_mean[bb], &c.j_rstd[bb]);
+                if (lm_runs > 0) {   // else: the row carried in by the stream state, constants already in c.lm_mean / c.lm_rstd
+                  const double* ls = lm.lmstat + ((size_t)(lm_runs - 1) * Bq + bb) * 2;
+                  standardize_consts(__ldcg(ls), __ldcg(ls + 1), V, &c.lm_mean[bb], &c.lm_rstd[bb]);
+                }
+                c.pend[bb] = 1;
+              }
+            }
+          }
+        }
+        if constexpr (LM) {
+          named_bar_sync(1, 128);
+          if (et == 0) {
+            int ap = 0;
+            for (int i = 0; i < B; ++i) ap |= c.pend[i];
+            c.flags[2] = ap;
+          }
+          named_bar_sync(1, 128);
+          if (c.flags[2]) {
+            // ---- F: arg max of alpha * std(lm row) + theta * std(joint row), entry 0 of both rows pinned to -10
+            //      (lm.py:54,59-77); this thread's vocabulary rows, then one packed atomicMax per stream ----
+            if (in_B) {
+              const bool on = bvalid && c.pend[b];
+              float m = -INFINITY;
+              int am = 0;
+              if (on) {
+                const float lmean = c.lm_mean[b], lrstd = c.lm_rstd[b], jmean = c.j_mean[b], jrstd = c.j_rstd[b];
+                for (int i = 0; i < rptB; ++i) {
+                  const int v = vB0 + i;
+                  if (v < V) {
+                    float a = (lmv[i * 128 + et] - lmean) * lrstd;
+                    float j = (lvj[i * 128 + et] - jmean) * jrstd;
+                    if (v == 0) { a = kLmMinVal; j = kLmMinVal; }
+                    const float f = __fadd_rn(__fmul_rn(lm.alpha, a), __fmul_rn(lm.theta, j));
+                    if (f > m) { m = f; am = v; }
+                  }
+                }
+                c.red[sub][b][0] = m; c.red[sub][b][1] = __int_as_float(am);
+              }
+              named_bar_sync(1, 128);
+              if (on && sub == 0) {
+                for (int k = 1; k < tpr; ++k) {
+                  const float m2 = c.red[k][b][0];
+                  if (m2 > m) { m = m2; am = __float_as_int(c.red[k][b][1]); }
+                }
+                atomicMax(lm.fkeys + (size_t)kstep * Bq + b, pack_key(m, am));
+              }
+            }
+            grid_arrive();
+            grid_wait();
+            if (et < B && c.pend[et]) {
+              const unsigned long long key = __ldcg(lm.fkeys + (size_t)kstep * Bq + et);
+              c.am[et] = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+            }
+            named_bar_sync(1, 128);
+          }
+        }
         if (et < B) {
           const int bb = et;
           unsigned char emit = 0;
           if (c.active[bb]) {
-            const unsigned long long key = __ldcg(p.keys + (size_t)min(step, p.max_steps - 1) * Bq + bb);
-            const int am2 = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
-            const int t = c.t[bb];
+            const int am2 = c.am[bb], t = c.t[bb];
             c.n_eval[bb] += 1;
             const int it = c.it[bb] + 1;
             bool advance;
-            if (am2 == w.blank) {
+            if (am2 == w.blank && !c.pend[bb]) {
               advance = true;
             } else {
               const int n = c.ntok[bb];
@@ -594,6 +909,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
               c.ntok[bb] = n + 1;
               c.tok[bb] = am2;
               emit = 1;
+              if (LM) c.lm_valid[bb] = 1;   // the LM advances on this token (lm.py:50-54)
               advance = it >= p.max_iters;
             }
             if (advance) {
@@ -612,6 +928,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
           int ae = 0, aa = 0;
           for (int i = 0; i < B; ++i) { ae |= c.emit[i]; aa |= c.active[i]; }
           c.flags[0] = ae; c.flags[1] = aa;
+          if (!LM) c.flags[2] = 0;
           mbar_arrive(ctlbar);
         }
         named_bar_sync(1, 128);
@@ -619,11 +936,19 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
       const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
       stamp(3);
       if (any_emit) {
-        for (int l = 0; l < Lp; ++l) { predictor_phase(l); stamp(4 + l); }
+        const int nph = (LM && Ll > Lp) ? Ll : Lp;
+        for (int i = 0; i < nph; ++i) { layer_phase(i, true); stamp(4 + (i < 3 ? i : 3)); }
         par ^= 1;
+        if (LM) { lpar ^= 1; lm_pending = true; }
       }
       any_upd = any_emit;
       if (!any_active) break;
+    }
+    if (LM && lm_pending) {   // the fuser must hold the row of the last emitted token (lm.py:50-54)
+      lm_out_epilogue(false);
+      ++lm_runs;
+      grid_arrive();
+      grid_wait();
     }
 
     // ---- results and state ----
@@ -641,6 +966,28 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
 #pragma unroll
         for (int i = 0; i < DT_MAX_RPT; ++i)
           if (i < upt) p.pred_out[(size_t)b * H + unit0 + i] = gval[i];
+    }
+    if constexpr (LM) {   // fuser state back into the blob (buffer 0 of h), same layout as the fp32 kernel's
+      const int Bp = lm.Bp, Hl = lm.Hl;
+      if (in_L && bvalid)
+        for (int l = 0; l < Ll; ++l)
+          for (int i = 0; i < upt_l; ++i) {
+            const size_t si = (size_t)(lunit0 + i) * Bp + b;
+            lm.st.h[(size_t)l * 2 * Hl * Bp + si] = lmh[(l * upt_l + i) * 128 + et];
+            lm.st.c[(size_t)l * Hl * Bp + si] = lmc[(l * upt_l + i) * 128 + et];
+          }
+      if (in_B && bvalid)
+        for (int i = 0; i < rptB; ++i)
+          if (vB0 + i < V) lm.st.logits[(size_t)(vB0 + i) * Bp + b] = lmv[i * 128 + et];
+      if (cta == 0 && et < B) {
+        lm.st.valid[et] = c.lm_valid[et] ? 1.f : 0.f;
+        if (lm_runs > 0) {
+          const double* ls = lm.lmstat + ((size_t)(lm_runs - 1) * Bq + et) * 2;
+          standardize_consts(__ldcg(ls), __ldcg(ls + 1), V, &c.lm_mean[et], &c.lm_rstd[et]);
+        }
+        lm.st.stats[et] = c.lm_mean[et];
+        lm.st.stats[Bp + et] = c.lm_rstd[et];
+      }
     }
   }
   tc_fence_before();
@@ -700,11 +1047,13 @@ __global__ void trace_normalize_kernel(float* trace, const float* lse, int B, in
 }  // namespace
 
 cudaError_t configure_decode_tc() {
-  return cudaFuncSetAttribute(decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(decode_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(decode_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 // weight-side plan (independent of the batch): slices per CTA
-bool decode_tc_wplan(int H, int J, int V, int sms, DecodeTcPlan* pl) {
+bool decode_tc_wplan(int H, int J, int V, int sms, DecodeTcPlan* pl, int lm_layers, int lm_hidden) {
   if (H % 64 || J % 64) return false;
   int Uc = 0;
   for (int u : {8, 16, 32})
@@ -716,12 +1065,22 @@ bool decode_tc_wplan(int H, int J, int V, int sms, DecodeTcPlan* pl) {
   pl->NC_A = (int)round_up(ceil_div(J, pl->G), 8);
   pl->NC_B = (int)round_up(ceil_div(V, pl->G), 8);
   pl->NC_max = std::max(pl->NC_C, std::max(pl->NC_A, pl->NC_B));
+  pl->Ul = pl->NC_L = pl->G_l = 0;
+  if (lm_layers > 0) {   // LM units per CTA: a multiple of 4 (whole units per epilogue thread at 2 or 4 threads per stream)
+    if (lm_layers > kTcLmLayers || lm_hidden % 64) return false;
+    for (int u = 4; u <= 16; u += 4)
+      if (lm_hidden % u == 0 && lm_hidden / u <= pl->G) { pl->Ul = u; break; }
+    if (!pl->Ul) return false;
+    pl->NC_L = 4 * pl->Ul;
+    pl->G_l = lm_hidden / pl->Ul;
+    pl->NC_max = std::max(pl->NC_max, pl->NC_L);
+  }
   return 2 * pl->NC_max <= 256;
 }
 
-bool decode_tc_plan(int H, int J, int V, int Lp, int B, int sms, DecodeTcPlan* pl) {
+bool decode_tc_plan(int H, int J, int V, int Lp, int B, int sms, DecodeTcPlan* pl, int lm_layers, int lm_hidden) {
   if (B < 1 || B > DT_MAXB) return false;
-  if (!decode_tc_wplan(H, J, V, sms, pl)) return false;
+  if (!decode_tc_wplan(H, J, V, sms, pl, lm_layers, lm_hidden)) return false;
   pl->Bpad8 = (int)round_up(B, 8);
   pl->Bq = pl->Bpad8 <= 32 ? 32 : 64;
   pl->mma_m = 2 * pl->Bpad8 <= 64 ? 64 : 128;
@@ -734,15 +1093,21 @@ bool decode_tc_plan(int H, int J, int V, int Lp, int B, int sms, DecodeTcPlan* p
   // rec_cols per predictor layer for the speculative recurrent products
   pl->rec_col0 = (int)round_up(2 * pl->NC_max, 16);
   pl->rec_cols = (int)round_up(2 * pl->NC_C, 16);
+  pl->lm_col0 = pl->rec_col0 + Lp * pl->rec_cols;
+  const int lm_cols = lm_layers > 0 ? (int)round_up(std::max(4 * pl->NC_L, 2 * pl->NC_B), 16) : 0;
+  if (lm_layers > 0 && pl->Ul * pl->Bq / 128 > DT_LM_UPT) return false;
   int cols = 32;
-  while (cols < pl->rec_col0 + Lp * pl->rec_cols) cols *= 2;
+  while (cols < pl->lm_col0 + lm_cols) cols *= 2;
   if (Lp < 1 || Lp > kMaxPredLayers || cols > 512) return false;
   pl->tmem_cols = cols;
   const size_t xkb = (size_t)2 * pl->Bpad8 * 128, wmax = (size_t)pl->NC_max * 256;
   const size_t guard = (size_t)pl->mma_m * 128;
   const size_t pre_bytes = round_up((size_t)2 * pl->Bq * (4 * pl->NC_max + 1) * 4, 1024);
   const size_t ctl_bytes = round_up(sizeof(Ctrl), 1024);
-  const size_t budget = 227 * 1024 - 2048 - guard - pre_bytes - ctl_bytes;
+  // LM per-thread state: lmh, lmc [Ll][upt_l][128], lmv, lvj [rptB][128] floats, dred [4][DT_MAXB][2] doubles
+  const size_t lm_bytes = lm_layers > 0 ? round_up(((size_t)2 * lm_layers * (pl->Ul * pl->Bq / 128) + 2 * (pl->NC_B * pl->Bq / 128)) * 128 * 4 +
+                                                       (size_t)4 * DT_MAXB * 2 * 8, 1024) : 0;
+  const size_t budget = 227 * 1024 - 2048 - guard - pre_bytes - ctl_bytes - lm_bytes;
   for (int kps : {4, 2, 1}) {
     const size_t stage = kps * (xkb + wmax);
     int S = (int)(budget / stage);
@@ -753,7 +1118,8 @@ bool decode_tc_plan(int H, int J, int V, int Lp, int B, int sms, DecodeTcPlan* p
     const size_t used = (size_t)S * stage + guard;
     pl->pre_offset = (int)round_up(used, 1024);
     pl->ctl_offset = pl->pre_offset + (int)pre_bytes;
-    pl->bar_offset = pl->ctl_offset + (int)ctl_bytes;
+    pl->lm_offset = pl->ctl_offset + (int)ctl_bytes;
+    pl->bar_offset = pl->lm_offset + (int)lm_bytes;
     pl->smem_bytes = pl->bar_offset + 1024 + 1024;
     return pl->smem_bytes <= 227 * 1024;
   }
@@ -766,8 +1132,9 @@ cudaError_t launch_decode_tc(const DecodeTcArgs& a, const DecodeTcPlan& pl, cuda
   args.Bpad8 = pl.Bpad8; args.Bq = pl.Bq; args.mma_m = pl.mma_m; args.kps = pl.kps; args.stages = pl.stages;
   args.pre_offset = pl.pre_offset; args.ctl_offset = pl.ctl_offset; args.bar_offset = pl.bar_offset; args.tmem_cols = pl.tmem_cols;
   args.rec_col0 = pl.rec_col0; args.rec_cols = pl.rec_cols;
+  args.Ul = pl.Ul; args.NC_L = pl.NC_L; args.G_l = pl.G_l; args.lm_col0 = pl.lm_col0; args.lm_offset = pl.lm_offset;
   void* kargs[] = {&args};
-  cudaError_t e = cudaLaunchCooperativeKernel((void*)decode_tc_kernel, dim3(pl.G), dim3(DT_THREADS), kargs, pl.smem_bytes, st);
+  cudaError_t e = cudaLaunchCooperativeKernel(a.lm.L > 0 ? (void*)decode_tc_kernel<true> : (void*)decode_tc_kernel<false>, dim3(pl.G), dim3(DT_THREADS), kargs, pl.smem_bytes, st);
   if (e != cudaSuccess) return e;
   const int nB = (int)ceil_div(a.w.V, pl.NC_B);
   decode_finish_kernel<<<a.B, 256, 0, st>>>(a.part, a.n_eval, nB, pl.Bq, a.max_steps, a.neg_logp, a.trace ? a.trace_lse : nullptr, a.trace_cap);

@@ -180,8 +180,29 @@ cudaError_t launch_decode(const DecodeArgs& a, int grid_blocks, cudaStream_t st)
 struct DecodeTcPlan {
   int G, Uc, NC_A, NC_B, NC_C, NC_max;                 // weight-side plan (batch independent)
   int Bpad8, Bq, mma_m, kps, stages, pre_offset, ctl_offset, bar_offset, smem_bytes, tmem_cols, rec_col0, rec_cols;
+  // fused language model (0 layers = none): G_l CTAs own Ul LM units (NC_L = 4*Ul gate rows) each
+  int Ul, NC_L, G_l, lm_col0, lm_offset;
+};
+// LM side of the tcgen05 decode kernel (lm.py:20-83); L == 0: no LM
+constexpr int kTcLmLayers = 6;
+struct DecodeTcLm {
+  int L, Hl;
+  float alpha, theta;
+  const float* table0;                 // [V][4Hl] gate-major: embed * W_ih0^T + b_ih0 + b_hh0
+  const float* bias[kTcLmLayers];      // layers >= 1: [4Hl] interleaved (b_ih + b_hh)
+  const float* bo;                     // [V]
+  const uint8_t* r_img[kTcLmLayers];   // operand images (TR = NC_L) of the interleaved W_hh
+  const uint8_t* w_img[kTcLmLayers];   // layers >= 1: ... of the interleaved W_ih
+  const uint8_t* wo_img;               // output projection [V][Hl] (TR = NC_B)
+  uint8_t* h_img[kTcLmLayers][2];      // activation images of the LM hidden state (ping-pong), TR = Bpad8
+  LmState st;                          // fuser state blob (feature-major, ld = Bp); zero = fresh fuser
+  int Bp;
+  double* jstat;                       // [max_steps][Bq][2] (sum, sum of squares) of the joint logits per evaluation, zero at launch
+  double* lmstat;                      // [max_steps][Bq][2] ... of the LM logits per LM run, zero at launch
+  unsigned long long* fkeys;           // [max_steps][Bq] packed arg-max keys of the fused scores, zero at launch
 };
 struct DecodeTcArgs {
+  DecodeTcLm lm;
   DecodeWeights w;                 // fp32 vectors / tables (table0, biases, h0, BatchNorm, b2)
   const uint8_t* w1p_img;          // operand images of the weight slices (TR = NC_A / NC_B / NC_C rows per CTA)
   const uint8_t* w2_img;
@@ -202,10 +223,11 @@ struct DecodeTcArgs {
   unsigned long long* dbg; int dbg_cap;   // optional (time, tag) trail of CTA 0 (tuning aid)
   // filled from the plan by the launcher
   int Uc, NC_A, NC_B, NC_C, NC_max, Bpad8, Bq, mma_m, kps, stages, pre_offset, ctl_offset, bar_offset, tmem_cols, rec_col0, rec_cols;
+  int Ul, NC_L, G_l, lm_col0, lm_offset;
 };
 cudaError_t configure_decode_tc();
-bool decode_tc_wplan(int H, int J, int V, int sms, DecodeTcPlan* pl);
-bool decode_tc_plan(int H, int J, int V, int Lp, int B, int sms, DecodeTcPlan* pl);
+bool decode_tc_wplan(int H, int J, int V, int sms, DecodeTcPlan* pl, int lm_layers = 0, int lm_hidden = 0);
+bool decode_tc_plan(int H, int J, int V, int Lp, int B, int sms, DecodeTcPlan* pl, int lm_layers = 0, int lm_hidden = 0);
 cudaError_t launch_decode_tc(const DecodeTcArgs& a, const DecodeTcPlan& pl, cudaStream_t st);
 
 // standalone predictor step / joint (same phase code, one launch per phase)
