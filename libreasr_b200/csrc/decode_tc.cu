@@ -480,9 +480,18 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     auto stamp = [&](int tag) {   // tuning aid: (time, tag) trail of CTA 0
       if (p.dbg && cta == 0 && et == 0 && ndbg < p.dbg_cap) { p.dbg[2 * ndbg] = gtimer(); p.dbg[2 * ndbg + 1] = (unsigned long long)tag; ++ndbg; }
     };
-    auto grid_arrive = [&]() {
+    // The phase counter only ever grows, and "barrier k complete" is tested as counter >= k * G.  That is only sound
+    // if no CTA makes its (k+1)-th arrival before barrier k is complete -- otherwise early arrivals stand in for late
+    // ones.  A CTA that consumed a gated operand in this phase has waited by data dependence; a CTA that SAT THE PHASE
+    // OUT (no slice of it, e.g. cta * NC_A >= J) has not, and must check the previous barrier itself (`waited` false).
+    auto grid_arrive = [&](bool waited = true) {
       named_bar_sync(1, 128);
-      if (et == 0) red_release_add(p.barrier, 1u);
+      if (et == 0) {
+        if (!waited)
+          while (ld_acquire_u32(p.barrier) < ebar * (unsigned)G) {
+          }
+        red_release_add(p.barrier, 1u);
+      }
       ++ebar;
     };
     auto grid_wait = [&]() {   // every CTA has made its ebar-th arrival
@@ -717,7 +726,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     auto layer_phase = [&](int i, bool with_lm) {
       if (i < Lp) predictor_phase(i);
       if (LM && with_lm && i < Ll) lm_phase(i, i < Lp);
-      grid_arrive();
+      // layer 0 follows an explicit grid wait (the rule R) or, for the BOS run, consumes operands gated on the initial
+      // images; deeper layers wait through their gated input product -- unless this CTA has none in this phase
+      grid_arrive(i == 0 || i < Lp || (LM && with_lm && i < Ll && in_L));
     };
 
     if (!p.use_state_in) {   // feed BOS from the learnable initial state (models.py:397-398); the LM only sees emitted tokens
@@ -749,12 +760,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
         }
         if (act) store_act(p.z_img, jA0, rptA, zv);
       }
+      const bool waited_A = !any_upd /* the rule's grid wait was the last barrier */ || in_A || (LM && lm_pending && in_B);
       if (LM && lm_pending) {   // rides on phase A: the row the fuser holds for the tokens emitted last step
         lm_out_epilogue(any_upd && in_A);
         ++lm_runs;
         lm_pending = false;
       }
-      grid_arrive();
+      grid_arrive(waited_A);
       stamp(0);
 
       // ---------------- phase B: logits slice + softmax partials ----------------
@@ -817,7 +829,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
           }
         }
       }
-      grid_arrive();
+      grid_arrive(in_B);
       stamp(1);
       grid_wait();   // every CTA's atomicMax has landed
       stamp(2);
@@ -947,7 +959,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     if (LM && lm_pending) {   // the fuser must hold the row of the last emitted token (lm.py:50-54)
       lm_out_epilogue(false);
       ++lm_runs;
-      grid_arrive();
+      grid_arrive(in_B);
       grid_wait();
     }
 

@@ -485,3 +485,38 @@ def test_stream_session_many_streams_match_oracle_and_reset(with_lm):
         assert ticks == want, f"pass {rep}"
         sb.reset()
     sb.close()
+
+
+def test_decode_is_deterministic_when_ctas_sit_phases_out():
+    """cfg4 shape (H = 1536 -> 96 CTAs, J = 1024 -> only 64 of them own a slice of the joint's first projection): CTAs
+    that sit a grid phase out must not run ahead of the phase counter.  Repeated decodes are identical, equal the four
+    8-utterance sub-batches, and equal the fp32 cooperative kernel (cooperative-groups grid sync) on the first 8."""
+    from libreasr_b200.engine import Engine, EngineConfig, tokens_to_lists
+
+    cfg = weights.CONFIGS["cfg4"]
+    sd = weights.make_state_dict(cfg, 1234)
+
+    def mk(mode):
+        ec = EngineConfig(n_mels=cfg.n_mels, n_stack=cfg.n_stack, downsample=cfg.downsample, enc_layers=cfg.enc_layers,
+                          pred_layers=cfg.pred_layers, hidden_sz=cfg.hidden_sz, embed_sz=cfg.embed_sz,
+                          joint_sz=cfg.joint_sz, vocab_sz=cfg.vocab_sz, gemm_mode=mode)
+        return Engine(ec).load_state_dict(sd)
+
+    eng = mk(GEMM_MODE)
+    audio = torch.from_numpy(weights.make_audio(32, 6 * 16000, seed=4)).cuda()
+    enc, _ = eng.encode(eng.features(audio))
+    runs = []
+    for _ in range(5):
+        d = eng.decode_greedy(enc, max_iters=3)
+        runs.append(tokens_to_lists(d["tokens"], d["ntok"]))
+    assert all(r == runs[0] for r in runs[1:])
+    sub = []
+    for b0 in range(0, 32, 8):
+        d = eng.decode_greedy(enc[b0:b0 + 8].contiguous(), max_iters=3)
+        sub += tokens_to_lists(d["tokens"], d["ntok"])
+    assert sub == runs[0]
+    eng0 = mk(0)
+    enc0, _ = eng0.encode(eng0.features(audio[:8].contiguous()))
+    d0 = eng0.decode_greedy(enc0, max_iters=3)
+    assert tokens_to_lists(d0["tokens"], d0["ntok"]) == runs[0][:8]
+    eng.close(); eng0.close()
