@@ -231,8 +231,8 @@ def run_product(args):
         ]
         dom = max(per_kernel[:3], key=lambda k: k["ms_per_step"])
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
-        ncu_traffic = {"decode_tc_kernel": {"bytes": 69243392 + 4359936, "source": "profiles/r1_ncu_full_decode_tc_kernel.csv"},
-                       "lstm_layer_tc_kernel": {"bytes": 81891840 + 6472448, "source": "profiles/r1_ncu_full_lstm_layer_tc_kernel.csv"}}
+        ncu_traffic = {"decode_tc_kernel": {"bytes": 76083456 + 11085824, "source": "profiles/r1_ncu_full_decode_tc_kernel.csv"},
+                       "lstm_layer_tc_kernel": {"bytes": 81903360 + 6575104, "source": "profiles/r1_ncu_full_lstm_layer_tc_kernel.csv"}}
         roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
                     "frac": dom["frac"], "traffic": ncu_traffic.get(dom["kernel"], {}).get("bytes"),
                     "traffic_source": ncu_traffic.get(dom["kernel"], {}).get("source"), "peak_source": peaks["source"] + ", sustained bf16 GEMM",
