@@ -91,6 +91,9 @@ struct rnnt_b200_handle_s {
   DevBuf lm_himg, lm_stat;
   float* lm_blob = nullptr;   // caller-owned fuser state (rnnt_b200_set_lm_state); nullptr = fresh fuser per call
   int lm_blob_B = 0;
+  // transcribe_host: copy engine stream + events so that the H2D of utterance block i+1 overlaps the front end of block i
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t*> evsets;  // one set of events per profiled transcribe() call: 6 stage marks + 2 per encoder layer
@@ -300,6 +303,9 @@ int32_t rnnt_b200_destroy(rnnt_b200_handle h) {
                     &h->t_ntok, &h->t_nlp, &h->t_iters, &h->t_enc, &h->a_img, &h->x_img[0], &h->x_img[1], &h->gbar, &h->dimg, &h->dkeys,
                     &h->lm_ws, &h->lm_logitT, &h->lm_part, &h->lm_jpart, &h->lm_fpart, &h->lm_himg, &h->lm_stat};
   for (DevBuf* b : bufs) b->release();
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (cudaEvent_t e : h->copy_ev)
+    if (e) cudaEventDestroy(e);
   for (cudaEvent_t* set : h->evsets) {
     for (int i = 0; i < kEvPerSet; ++i) cudaEventDestroy(set[i]);
     delete[] set;
@@ -1163,9 +1169,11 @@ int32_t rnnt_b200_set_lm_state(rnnt_b200_handle h, void* blob_dev, int32_t B) {
   return RNNT_B200_OK;
 }
 
-int32_t rnnt_b200_transcribe(rnnt_b200_handle h, const float* audio, const int32_t* lens, int32_t B, int64_t n, int32_t max_iters,
-                             int32_t* tokens_out, int32_t U_cap, int32_t* ntok_out, double* neg_logp_out, uint8_t* iters_out,
-                             void* stream) {
+// audio_host != nullptr: `audio` is the device staging buffer and the samples still have to come from the host; the copy is
+// issued in utterance blocks on the copy stream so that block i+1 transfers while the front end works on block i.
+static int32_t transcribe_impl(rnnt_b200_handle h, const float* audio, const float* audio_host, const int32_t* lens, int32_t B, int64_t n,
+                               int32_t max_iters, int32_t* tokens_out, int32_t U_cap, int32_t* ntok_out, double* neg_logp_out,
+                               uint8_t* iters_out, void* stream) {
   if (int r = check_ready(h)) return r;
   const rnnt_b200_config& c = h->cfg;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1191,7 +1199,26 @@ int32_t rnnt_b200_transcribe(rnnt_b200_handle h, const float* audio, const int32
   } else {
     h->ev = nullptr;
   }
-  if (int r = rnnt_b200_features(h, audio, lens, B, n, h->feats.as<float>(), stream)) return r;
+  if (audio_host) {
+    if (!h->copy_stream) {
+      CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+      for (cudaEvent_t& e : h->copy_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(h->copy_ev[4], st));                 // the staging buffer may still be read by earlier work on `st`
+    CK(cudaStreamWaitEvent(h->copy_stream, h->copy_ev[4], 0));
+    const int nblk = B < 4 ? B : 4, per = (B + nblk - 1) / nblk;
+    float* stage = const_cast<float*>(audio);
+    for (int i = 0, b0 = 0; b0 < B; ++i, b0 += per) {
+      const int nb = std::min(per, B - b0);
+      CK(cudaMemcpyAsync(stage + (size_t)b0 * n, audio_host + (size_t)b0 * n, (size_t)nb * n * 4, cudaMemcpyHostToDevice, h->copy_stream));
+      CK(cudaEventRecord(h->copy_ev[i], h->copy_stream));
+      CK(cudaStreamWaitEvent(st, h->copy_ev[i], 0));
+      if (int r = rnnt_b200_features(h, audio + (size_t)b0 * n, lens ? lens + b0 : nullptr, nb, n, h->feats.as<float>() + (size_t)b0 * T * X, stream))
+        return r;
+    }
+  } else if (int r = rnnt_b200_features(h, audio, lens, B, n, h->feats.as<float>(), stream)) {
+    return r;
+  }
   if (lens) {
     int32_t* lt = h->t_lens.as<int32_t>() + B;
     LAUNCH(1, launch_lens_to_steps(lens, lt, B, c.hop_length, c.n_stack, c.downsample, (int)T, st));
@@ -1200,6 +1227,13 @@ int32_t rnnt_b200_transcribe(rnnt_b200_handle h, const float* audio, const int32
   if (int r = rnnt_b200_encode(h, h->feats.as<float>(), lens_T, B, (int)T, nullptr, nullptr, 0, h->t_enc.as<float>(), stream)) return r;
   return rnnt_b200_decode_greedy(h, h->t_enc.as<float>(), lens_T, B, (int)T, max_iters, nullptr, nullptr, 0, tokens_out, U_cap,
                                  ntok_out, neg_logp_out, iters_out, nullptr, 0, stream);
+}
+
+int32_t rnnt_b200_transcribe(rnnt_b200_handle h, const float* audio, const int32_t* lens, int32_t B, int64_t n, int32_t max_iters,
+                             int32_t* tokens_out, int32_t U_cap, int32_t* ntok_out, double* neg_logp_out, uint8_t* iters_out,
+                             void* stream) {
+  if (!audio) return fail(h, RNNT_B200_ERR_INVALID, "transcribe: null audio");
+  return transcribe_impl(h, audio, nullptr, lens, B, n, max_iters, tokens_out, U_cap, ntok_out, neg_logp_out, iters_out, stream);
 }
 
 int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, const int32_t* lens_host, int32_t B, int64_t n,
@@ -1213,10 +1247,9 @@ int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, c
   CK(h->t_tokens.ensure((size_t)B * U_cap * 4));
   CK(h->t_ntok.ensure((size_t)B * 4));
   CK(h->t_nlp.ensure((size_t)B * 8));
-  CK(cudaMemcpyAsync(h->t_audio.p, audio_host, (size_t)B * n * 4, cudaMemcpyHostToDevice, st));
   if (lens_host) CK(cudaMemcpyAsync(h->t_lens.p, lens_host, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  if (int r = rnnt_b200_transcribe(h, h->t_audio.as<float>(), lens_host ? h->t_lens.as<int32_t>() : nullptr, B, n, max_iters,
-                                   h->t_tokens.as<int32_t>(), U_cap, h->t_ntok.as<int32_t>(), h->t_nlp.as<double>(), nullptr, stream))
+  if (int r = transcribe_impl(h, h->t_audio.as<float>(), audio_host, lens_host ? h->t_lens.as<int32_t>() : nullptr, B, n, max_iters,
+                              h->t_tokens.as<int32_t>(), U_cap, h->t_ntok.as<int32_t>(), h->t_nlp.as<double>(), nullptr, stream))
     return r;
   CK(cudaMemcpyAsync(tokens_host, h->t_tokens.p, (size_t)B * U_cap * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ntok_host, h->t_ntok.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));

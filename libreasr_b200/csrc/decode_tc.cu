@@ -1010,16 +1010,17 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
 // Post-pass, off the decode loop's critical path: fold the per-step softmax partials into the
 // log-sum-exp of every evaluation (ascending vocabulary order, as the fp32 kernel does), accumulate
 // -sum(log p(arg max)) per utterance (models.py:422,455) and turn the traced raw logits into log_softmax rows.
-__global__ void __launch_bounds__(256) decode_finish_kernel(const float* __restrict__ part, const int* __restrict__ n_eval,
+__global__ void __launch_bounds__(1024) decode_finish_kernel(const float* __restrict__ part, const int* __restrict__ n_eval,
                                                             int nB, int Bq, int max_steps, double* __restrict__ neg_logp,
                                                             float* __restrict__ lse_out, int lse_cap) {
-  // one block per utterance, one warp per evaluation; lanes fold contiguous runs of the vocabulary partials and are
+  // one block (32 warps) per utterance, one warp per evaluation; lanes fold contiguous runs of the vocabulary partials and are
   // combined in a fixed shuffle tree (deterministic)
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ne = min(n_eval[b], max_steps);
   const int per = (nB + 31) / 32;
   double acc = 0.0;
-  for (int e = warp; e < ne; e += 8) {
+  const int nwarps = blockDim.x >> 5;
+  for (int e = warp; e < ne; e += nwarps) {
     float M = -INFINITY, S = 0.f;
     for (int k = lane * per; k < min(nB, (lane + 1) * per); ++k) {
       const float2 q = *reinterpret_cast<const float2*>(part + (((size_t)e * nB + k) * Bq + b) * 2);
@@ -1040,12 +1041,12 @@ __global__ void __launch_bounds__(256) decode_finish_kernel(const float* __restr
       if (lse_out && e < lse_cap) lse_out[(size_t)b * lse_cap + e] = lse;
     }
   }
-  __shared__ double red[8];
+  __shared__ double red[32];
   if (lane == 0) red[warp] = acc;
   __syncthreads();
   if (threadIdx.x == 0 && neg_logp) {
     double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += red[w];
+    for (int w = 0; w < nwarps; ++w) t += red[w];
     neg_logp[b] = -t;
   }
 }
@@ -1149,7 +1150,7 @@ cudaError_t launch_decode_tc(const DecodeTcArgs& a, const DecodeTcPlan& pl, cuda
   cudaError_t e = cudaLaunchCooperativeKernel(a.lm.L > 0 ? (void*)decode_tc_kernel<true> : (void*)decode_tc_kernel<false>, dim3(pl.G), dim3(DT_THREADS), kargs, pl.smem_bytes, st);
   if (e != cudaSuccess) return e;
   const int nB = (int)ceil_div(a.w.V, pl.NC_B);
-  decode_finish_kernel<<<a.B, 256, 0, st>>>(a.part, a.n_eval, nB, pl.Bq, a.max_steps, a.neg_logp, a.trace ? a.trace_lse : nullptr, a.trace_cap);
+  decode_finish_kernel<<<a.B, 1024, 0, st>>>(a.part, a.n_eval, nB, pl.Bq, a.max_steps, a.neg_logp, a.trace ? a.trace_lse : nullptr, a.trace_cap);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (a.trace) {
     trace_normalize_kernel<<<148, 256, 0, st>>>(a.trace, a.trace_lse, a.B, a.trace_cap, a.w.V);

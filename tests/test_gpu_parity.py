@@ -520,3 +520,18 @@ def test_decode_is_deterministic_when_ctas_sit_phases_out():
     d0 = eng0.decode_greedy(enc0, max_iters=3)
     assert tokens_to_lists(d0["tokens"], d0["ntok"]) == runs[0][:8]
     eng.close(); eng0.close()
+
+
+@pytest.mark.parametrize("B", [40, 72])
+def test_lm_fusion_wide_batches_match_oracle(B):
+    """LM fusion beyond 32 utterances: 33..64 take the 128-row MMA tiles of the tcgen05 kernel (2 threads per stream),
+    more than 64 run as sub-batches; every utterance still equals the oracle's single-utterance decode with its own fuser."""
+    cfg, lc, m, orc, olm = lm_model_for("tiny", "tiny")
+    eng = m.engine()
+    n = 24000
+    audio = weights.make_audio(B, n, seed=97)
+    r = eng.transcribe(torch.from_numpy(audio).cuda())
+    got = [r["tokens"][b, : int(r["ntok"][b])].tolist() for b in range(B)]
+    for b in list(range(0, B, 5)) + [B - 1]:
+        feats = O.features_offline(torch.from_numpy(audio[b:b + 1]), cfg)[0]
+        assert got[b] == orc.decode_greedy(feats, max_iters=3, impl="aten", lm=olm)["tokens"], f"utterance {b}"
