@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
   uint64_t* tempty_r = tfull_r + 1;  // ... and drained by the predictor phases that consumed them
   uint64_t* tfull_l = tempty_r + 1;  // LM accumulators (layer products / output projection) complete
   uint64_t* tempty_l = tfull_l + 1;  // ... and drained
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(tempty_l + 1);
+  uint64_t* ctlack = tempty_l + 1;   // the three GEMM-side warps have read the control flags of a step
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(ctlack + 1);
   const int nB = (V + p.NC_B - 1) / p.NC_B;                     // CTAs that produce a softmax partial
 
   if (threadIdx.x == 0) {
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
     mbar_init(tempty_r, 128);
     mbar_init(tfull_l, 1);
     mbar_init(tempty_l, 128);
+    mbar_init(ctlack, 3);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tptr, p.tmem_cols);
@@ -293,7 +295,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
       if (!spec_valid) { run_spec(par); spec_valid = true; }
       mbar_wait(ctlbar, step & 1);
       const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
-      if (LM && c.flags[2]) ++nbar;   // the fused-arg-max barrier of this step (no GEMM)
+      const bool any_pend = LM && c.flags[2] != 0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ctlack);   // the epilogue may now publish the next step's flags
+      if (any_pend) ++nbar;   // the fused-arg-max barrier of this step (no GEMM)
       if (any_emit) {
         const int nph = (LM && Ll > Lp) ? Ll : Lp;
         for (int i = 0; i < nph; ++i) run_layer_phase(i, true);
@@ -395,6 +400,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
       if (!spec_valid) { run_spec(par); spec_valid = true; }
       mbar_wait(ctlbar, step & 1);
       const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ctlack);
       if (any_emit) {
         const int nph = (LM && Ll > Lp) ? Ll : Lp;
         for (int i = 0; i < nph; ++i) run_layer_phase(i, true);
@@ -837,6 +844,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
       // ---------------- R: greedy rule (models.py:408-437), identical in every CTA ----------------
       {
         const int kstep = min(step, p.max_steps - 1);
+        // the flags are a single-slot mailbox: the GEMM-side warps must have read the previous step's before they
+        // are overwritten (and before ctlbar can complete another phase)
+        if (step > 0) mbar_wait(ctlack, (step - 1) & 1);
         if (et < B) {
           const int bb = et;
           c.pend[bb] = 0;
