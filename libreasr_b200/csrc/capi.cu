@@ -284,7 +284,7 @@ int32_t rnnt_b200_create(const rnnt_b200_config* cfg, rnnt_b200_handle* out) {
   h = new rnnt_b200_handle_s();
   h->cfg = *cfg;
   h->sm_count = prop.multiProcessorCount;
-  if ((e = configure_lstm()) != cudaSuccess || (e = configure_gemm_tc()) != cudaSuccess ||
+  if ((e = configure_lstm()) != cudaSuccess || (e = configure_gemm_tc()) != cudaSuccess || (e = configure_gemm_tc2()) != cudaSuccess ||
       (e = configure_lstm_tc()) != cudaSuccess || (e = configure_decode_tc()) != cudaSuccess || (e = configure_decode(cfg->device, &h->coop_blocks)) != cudaSuccess) {
     delete h;
     return fail_cuda(nullptr, e, "kernel configuration");
@@ -1382,13 +1382,15 @@ int32_t rnnt_b200_selftest_gemm(rnnt_b200_handle h, const float* A, const float*
     LAUNCH(1, launch_gemm_nt_f32(A, K, W, K, bias, C, N, M, N, K, st));
     return RNNT_B200_OK;
   }
-  if (gemm_mode != RNNT_B200_GEMM_TC_FP16X3) return fail(h, RNNT_B200_ERR_INVALID, "selftest_gemm: unknown gemm_mode");
+  const bool pair = gemm_mode == 3;   // test hook: force the CTA-pair (cta_group::2) kernel
+  if (gemm_mode != RNNT_B200_GEMM_TC_FP16X3 && !pair) return fail(h, RNNT_B200_ERR_INVALID, "selftest_gemm: unknown gemm_mode");
   void *ai = nullptr, *wi = nullptr;
   CK(cudaMalloc(&ai, gemm_tc_a_image_bytes(M, K)));
   CK(cudaMalloc(&wi, gemm_tc_w_image_bytes(N, K)));
   cudaError_t e = launch_to_image(A, K, M, K, 128, (uint8_t*)ai, st);
   if (e == cudaSuccess) e = launch_to_image(W, K, N, K, 256, (uint8_t*)wi, st);
-  if (e == cudaSuccess) e = launch_gemm_tc((uint8_t*)ai, (uint8_t*)wi, bias, C, N, M, N, K, st);
+  if (e == cudaSuccess) e = pair ? launch_gemm_tc2((uint8_t*)ai, (uint8_t*)wi, bias, C, N, M, N, K, st)
+                                 : launch_gemm_tc_1cta((uint8_t*)ai, (uint8_t*)wi, bias, C, N, M, N, K, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(ai);
   cudaFree(wi);

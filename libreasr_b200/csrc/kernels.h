@@ -45,6 +45,12 @@ size_t gemm_tc_w_image_bytes(int N, int K);       // weight operand image, 256-r
 // fp32 row-major [R][ld] -> hi/lo fp16 operand image with TR-row tiles (tc_common.cuh)
 cudaError_t launch_to_image(const float* src, int ld, int64_t R, int K, int TR, uint8_t* img, cudaStream_t st);
 // C[M,N] = A * W^T + bias from operand images (A: TR=128, W: TR=256)
+// gemm_tc2.cu: CTA-pair (cta_group::2) variant, 256 x 256 pair tiles; a_img must hold an even number of 128-row tiles
+cudaError_t configure_gemm_tc2();
+cudaError_t launch_gemm_tc_1cta(const uint8_t* a_img, const uint8_t* w_img, const float* bias, float* C, int ldc, int64_t M, int N, int K,
+                                cudaStream_t st);
+cudaError_t launch_gemm_tc2(const uint8_t* a_img, const uint8_t* w_img, const float* bias, float* C, int ldc, int64_t M, int N, int K,
+                            cudaStream_t st);
 cudaError_t launch_gemm_tc(const uint8_t* a_img, const uint8_t* w_img, const float* bias, float* C, int ldc, int64_t M, int N,
                            int K, cudaStream_t st);
 
