@@ -26,6 +26,9 @@ constexpr int GT_B_BYTES = 2 * GT_BN * 128;
 constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
 constexpr int GT_SMEM_BYTES = GT_STAGES * GT_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int GT_THREADS = 192;
+#ifndef GT_CHUNK
+#define GT_CHUNK 8192
+#endif
 
 struct GemmTcArgs {
   const uint8_t* a_img;  // image(TR=128) of A
@@ -71,8 +74,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_f16x3_kernel(GemmTcArgs
       if (elect_one()) {
         mbar_arrive_expect_tx(&full[s], GT_STAGE_BYTES);
         uint8_t* dst = smem + s * GT_STAGE_BYTES;
-        tma_bulk_g2s(dst, p.a_img + img_tile_offset(mt, kb, 0, p.KB, GT_BM), GT_A_BYTES, &full[s]);
-        tma_bulk_g2s(dst + GT_A_BYTES, p.b_img + img_tile_offset(nt, kb, 0, p.KB, GT_BN), GT_B_BYTES, &full[s]);
+        // several medium-sized bulk copies in flight instead of two large ones (GT_CHUNK bytes each)
+        const uint8_t* asrc = p.a_img + img_tile_offset(mt, kb, 0, p.KB, GT_BM);
+        const uint8_t* bsrc = p.b_img + img_tile_offset(nt, kb, 0, p.KB, GT_BN);
+#pragma unroll
+        for (int o = 0; o < GT_A_BYTES; o += GT_CHUNK) tma_bulk_g2s(dst + o, asrc + o, GT_CHUNK, &full[s]);
+#pragma unroll
+        for (int o = 0; o < GT_B_BYTES; o += GT_CHUNK) tma_bulk_g2s(dst + GT_A_BYTES + o, bsrc + o, GT_CHUNK, &full[s]);
       }
       __syncwarp();
     }
