@@ -535,3 +535,23 @@ def test_lm_fusion_wide_batches_match_oracle(B):
     for b in list(range(0, B, 5)) + [B - 1]:
         feats = O.features_offline(torch.from_numpy(audio[b:b + 1]), cfg)[0]
         assert got[b] == orc.decode_greedy(feats, max_iters=3, impl="aten", lm=olm)["tokens"], f"utterance {b}"
+
+
+def test_stream_session_beyond_64_streams():
+    """70 lock-step streams: more than the tcgen05 decode kernel's 64, so the stateful decode falls through to the fp32
+    cooperative kernel while the encoder stays on its own path; spot-checked streams equal the oracle."""
+    from libreasr_b200.api import StreamBatch
+
+    cfg, sd, m, orc = model_for("tiny")
+    S, n_chunks = 70, 14
+    audio = weights.make_audio(S, n_chunks * CHUNK, seed=73)
+    sb = StreamBatch(m.engine(), S, max_iters=10)
+    ticks = [[] for _ in range(S)]
+    for j in range(n_chunks):
+        new = sb.push(torch.from_numpy(np.ascontiguousarray(audio[:, j * CHUNK:(j + 1) * CHUNK])))
+        if new is not None:
+            for b in range(S):
+                ticks[b].append(new[b])
+    sb.close()
+    for b in (0, 33, 64, 69):
+        assert ticks[b] == _oracle_stream_tokens(orc, cfg, audio[b], n_chunks), f"stream {b}"
