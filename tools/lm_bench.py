@@ -16,8 +16,9 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--lm", default="en", help="en = shipped override 4x768 (testing.yaml:306-313), default = 6x1024 (testing.yaml:293-299)")
     a = ap.parse_args()
-    cfg, lc = synth.CONFIGS["cfg2"], synth.LM_CONFIGS["en"]
+    cfg, lc = synth.CONFIGS["cfg2"], synth.LM_CONFIGS[a.lm]
     base = EngineConfig(n_mels=cfg.n_mels, n_stack=cfg.n_stack, downsample=cfg.downsample, enc_layers=cfg.enc_layers,
                         pred_layers=cfg.pred_layers, hidden_sz=cfg.hidden_sz, embed_sz=cfg.embed_sz, joint_sz=cfg.joint_sz,
                         vocab_sz=cfg.vocab_sz)
@@ -26,7 +27,7 @@ def main():
     sets = [torch.from_numpy(synth.make_audio(a.batch, n, seed=synth.BENCH_AUDIO_SEED + i)).cuda() for i in range(2)]
     out = {}
     for tag, ec, lsd in (("no_lm", base, None),
-                         ("lm_4x768", dataclasses.replace(base, lm_layers=lc.num_layers, lm_hidden_sz=lc.hidden_sz, lm_embed_sz=lc.embed_sz),
+                         ("lm_%dx%d" % (lc.num_layers, lc.hidden_sz), dataclasses.replace(base, lm_layers=lc.num_layers, lm_hidden_sz=lc.hidden_sz, lm_embed_sz=lc.embed_sz),
                           synth.make_lm_state_dict(lc, 4321))):
         eng = Engine(ec).load_state_dict(sd, lm_state_dict=lsd)
         eng.lib.rnnt_b200_set_profiling(eng._h, 1)
