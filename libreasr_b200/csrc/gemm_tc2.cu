@@ -8,11 +8,14 @@
 // read A and W halves from both CTAs' shared memory; each CTA keeps its 128 rows of the accumulators
 // (D0 | D1, 512 TMEM columns) and runs its own epilogue.  One third fewer bytes per FLOP, one more pipeline stage.
 //
-//   warp 0      producer (both CTAs): TMA bulk copies of [A hi|lo 32 KB][W-half hi 16 KB][W-half lo 16 KB]
-//   warp 1      leader CTA: MMA issuer; peer CTA: relays "my stage landed" to the leader (a plain bulk copy can only
-//               complete on a barrier of the CTA it writes to, so the peer forwards it with a remote arrive)
+//   warp 0      producer (both CTAs): four 2-D tensor-map TMA loads per stage ([A hi][A lo][W-half hi][W-half lo], 16 KB
+//               boxes of 128 image rows x 128 B); `.cta_group::2` lets every load complete on the LEADER's mbarrier, so
+//               one barrier per stage tells the leader that both CTAs' operands have landed
+//   warp 1      leader CTA: MMA issuer (idle in the peer)
 //   warps 2-5   epilogue (both CTAs)
 // Stage hand-back and "accumulators ready" use tcgen05.commit ... multicast::cluster to the same barrier in both CTAs.
+#include <cuda.h>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -46,14 +49,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t cta_rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(smem_u32(local_bar)), "r"(cta_rank)
-      : "memory");
-}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
   while (!ok) {
@@ -65,6 +60,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   }
+}
+// 2-D tensor-map load of one 128 x 128 B box into this CTA's shared memory; the transaction bytes are credited to the
+// barrier at the same offset in the even (leader) CTA of the pair (peer bit of the shared::cluster address cleared)
+__device__ __forceinline__ void tma_2d_pair(void* smem_dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar) & 0xFEFFFFFFu)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {  // the same warp of BOTH CTAs
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
@@ -88,12 +90,12 @@ __device__ __forceinline__ void tc_mma2_f16(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1) gemm_tc2_f16x3_kernel(Gemm2Args p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_tc2_f16x3_kernel(Gemm2Args p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);   // this CTA's stage landed
-  uint64_t* pfull = full + G2_STAGES;    // (leader) the peer's stage landed
-  uint64_t* empty = pfull + G2_STAGES;   // the MMAs that read the stage (in both CTAs) have completed
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);   // (leader) both CTAs' stage landed
+  uint64_t* empty = full + G2_STAGES;    // the MMAs that read the stage (in both CTAs) have completed
   uint64_t* tfull = empty + G2_STAGES;
   uint32_t* tptr = reinterpret_cast<uint32_t*>(tfull + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,7 +106,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1) gemm_
   if (threadIdx.x == 0) {
     for (int s = 0; s < G2_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&pfull[s], 1);
       mbar_init(&empty[s], 1);
     }
     mbar_init(tfull, 1);
@@ -113,7 +114,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1) gemm_
   if (warp == 1) tmem_alloc2(tptr, 512);
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / multicast commit
+  cluster_sync_all();   // both CTAs' barriers exist before any TMA completion / multicast commit targets them
   tc_fence_after();
   const uint32_t tmem = *tptr;
 
@@ -123,12 +124,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1) gemm_
       const uint32_t ph = (kb / G2_STAGES) & 1;
       mbar_wait_cluster(&empty[s], ph ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&full[s], G2_STAGE_BYTES);
+        if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * G2_STAGE_BYTES);   // both CTAs' four boxes
         uint8_t* dst = smem + s * G2_STAGE_BYTES;
-        tma_bulk_g2s(dst, p.a_img + img_tile_offset(mt, kb, 0, p.KB, G2_BM), G2_A_BYTES, &full[s]);
-        const uint8_t* wt = p.b_img + img_tile_offset(nt, kb, 0, p.KB, G2_BN) + (size_t)rank * G2_BH_BYTES;   // rows rank*128..
-        tma_bulk_g2s(dst + G2_A_BYTES, wt, G2_BH_BYTES, &full[s]);                                   // hi part
-        tma_bulk_g2s(dst + G2_A_BYTES + G2_BH_BYTES, wt + (size_t)G2_BN * 128, G2_BH_BYTES, &full[s]);   // lo part
+        const int32_t rowA = (int32_t)(img_tile_offset(mt, kb, 0, p.KB, G2_BM) >> 7);                       // image rows of 128 B
+        const int32_t rowW = (int32_t)(img_tile_offset(nt, kb, 0, p.KB, G2_BN) >> 7) + (int32_t)rank * (G2_BN / 2);
+        tma_2d_pair(dst, &tmA, 0, rowA, &full[s]);                                       // A hi
+        tma_2d_pair(dst + G2_BM * 128, &tmA, 0, rowA + G2_BM, &full[s]);                 // A lo
+        tma_2d_pair(dst + G2_A_BYTES, &tmW, 0, rowW, &full[s]);                          // this CTA's half of W, hi part
+        tma_2d_pair(dst + G2_A_BYTES + G2_BH_BYTES, &tmW, 0, rowW + G2_BN, &full[s]);    // ... lo part
       }
       __syncwarp();
     }
@@ -138,8 +141,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1) gemm_
       for (int kb = 0; kb < p.KB; ++kb) {
         const int s = kb % G2_STAGES;
         const uint32_t ph = (kb / G2_STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        mbar_wait_cluster(&pfull[s], ph);
+        mbar_wait_cluster(&full[s], ph);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smem + s * G2_STAGE_BYTES);
         const uint32_t b_base = a_base + G2_A_BYTES;
@@ -159,14 +161,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1) gemm_
       }
       if (elect_one()) tc_commit2(tfull);
       __syncwarp();
-    } else {
-      for (int kb = 0; kb < p.KB; ++kb) {   // relay: my operands of fill kb have landed
-        const int s = kb % G2_STAGES;
-        const uint32_t ph = (kb / G2_STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        if (elect_one()) mbar_arrive_remote(&pfull[s], 0);
-        __syncwarp();
-      }
     }
   } else {
     const int q = warp & 3;
@@ -212,14 +206,43 @@ cudaError_t configure_gemm_tc2() {
   return cudaFuncSetAttribute(gemm_tc2_f16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
 }
 
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// an operand image seen as a 2-D byte array [rows][128]; boxes of 128 rows (the swizzle is already in the data)
+bool image_map(CUtensorMap* m, const uint8_t* img, size_t bytes) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {128, (cuuint64_t)(bytes >> 7)};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {128, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(img), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
 // a_img must hold an EVEN number of 128-row tiles (gemm_tc_a_image_bytes rounds up)
 cudaError_t launch_gemm_tc2(const uint8_t* a_img, const uint8_t* w_img, const float* bias, float* C, int ldc, int64_t M, int N,
                             int K, cudaStream_t st) {
   if ((ldc & 3) || (N & 3)) return cudaErrorInvalidValue;
   Gemm2Args a;
   a.a_img = a_img; a.b_img = w_img; a.bias = bias; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.KB = (int)ceil_div(K, kImgK);
+  alignas(64) CUtensorMap tmA, tmW;
+  if (!image_map(&tmA, a_img, gemm_tc_a_image_bytes(M, K)) || !image_map(&tmW, w_img, gemm_tc_w_image_bytes(N, K)))
+    return cudaErrorNotSupported;
   dim3 grid((unsigned)(2 * ceil_div(M, 2 * G2_BM)), (unsigned)ceil_div(N, G2_BN));
-  gemm_tc2_f16x3_kernel<<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>(a);
+  gemm_tc2_f16x3_kernel<<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>(a, tmA, tmW);
   return cudaGetLastError();
 }
 
