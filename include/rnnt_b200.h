@@ -233,7 +233,7 @@ int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, c
 
 /* ---- streaming sessions: a14 + the serving loop around it ------------------------------------- */
 
-/* B concurrent streams advanced in lock step, one chunk per stream per push: the reference's serving
+/* B concurrent streams, one chunk per (active) stream per push, each in its own phase: the reference's serving
  * loop (ASRServicer.TranscribeStream, api-server.py:82-135) -- sliding window of `n_window` chunks
  * (api-server.py:26,95-102), stream transforms incl. StreamPostprocess and Buffer(n_buffer)
  * (config/testing.yaml:356-374, transforms.py:326-342,455-471), Transducer.transcribe_stream with
@@ -242,21 +242,24 @@ int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, c
  * LM fuser) owned by the session and resident in HBM.
  *   open:  chunk_samples = 1280 (80 ms, api-client.py:14), n_window = 3, n_buffer = 2, max_iters = 10 are the
  *          reference's values.  The session borrows the handle's workspaces: calls on one handle are serialised.
- *   push:  chunks [B, chunk_samples] fp32, DEVICE memory or (chunks_on_host != 0) HOST memory.  The first
- *          n_window - 1 pushes only fill the window (api-server.py:97-98); afterwards every push yields one
- *          feature row per stream and every n_buffer-th row the encoder + decode loop run.  *advanced_out = 1
- *          on those ticks, and tokens_host_out [B, U_cap] (U_cap >= max_iters * n_buffer) / ntok_host_out [B]
- *          receive the tokens each stream emitted in this tick (host memory; the call synchronises the stream
- *          then).  Otherwise *advanced_out = 0 and the outputs are untouched.
- *   reset: all streams back to the initial state (the `reset` closure of transcribe_stream, models.py:494-500,
- *          plus an empty window and Buffer). */
+ *   push:  chunks [B, chunk_samples] fp32, DEVICE memory or (chunks_on_host != 0) HOST memory; active_host [B] bytes or
+ *          NULL: streams with a zero byte are skipped this tick (no connection / no chunk: window, Buffer and state untouched).
+ *          Every stream runs its own phase of the serving loop: its first n_window - 1 chunks only fill the window
+ *          (api-server.py:97-98); afterwards every chunk yields one feature row and every n_buffer-th row the encoder +
+ *          decode loop run for that stream (streams whose Buffer is not full take part with zero frames).  *advanced_out = 1
+ *          when at least one stream ran the model; tokens_host_out [B, U_cap] (U_cap >= max_iters * n_buffer) / ntok_host_out
+ *          [B] then hold the tokens each stream emitted in this tick (host memory; 0 tokens for the streams that did not
+ *          run; the call synchronises the stream).  Otherwise *advanced_out = 0 and the outputs are untouched.
+ *   reset: stream `slot` (or all streams when slot = -1) back to the state of a fresh connection: the `reset` closure of
+ *          transcribe_stream (models.py:494-500: learnable encoder state, predictor fed BOS, LMFuser.reset) plus an empty
+ *          window and Buffer.  Streams may be reset at any tick; the others are not disturbed. */
 typedef struct rnnt_b200_stream_s* rnnt_b200_stream;
 int32_t rnnt_b200_stream_open(rnnt_b200_handle h, int32_t n_streams, int32_t chunk_samples, int32_t n_window,
                               int32_t n_buffer, int32_t max_iters, rnnt_b200_stream* out);
-int32_t rnnt_b200_stream_push(rnnt_b200_stream s, const float* chunks, int32_t chunks_on_host,
+int32_t rnnt_b200_stream_push(rnnt_b200_stream s, const float* chunks, int32_t chunks_on_host, const uint8_t* active_host,
                               int32_t* tokens_host_out, int32_t U_cap, int32_t* ntok_host_out,
                               int32_t* advanced_out, void* stream);
-int32_t rnnt_b200_stream_reset(rnnt_b200_stream s);
+int32_t rnnt_b200_stream_reset(rnnt_b200_stream s, int32_t slot);
 int32_t rnnt_b200_stream_close(rnnt_b200_stream s);
 
 /* ---- self test -------------------------------------------------------------------------------- */

@@ -60,7 +60,8 @@ class LibreASR:
 
 
 class StreamBatch:
-    """B concurrent streams advanced in lock step, one 80 ms chunk per stream per ``push``.
+    """B concurrent streams, one 80 ms chunk per (active) stream per ``push``; every stream runs its own phase of the
+    serving loop and can be reset (new connection) or skipped (no chunk this tick) independently.
 
     Reproduces, per stream, the reference serving loop: 3-chunk sliding window
     (api-server.py:26,95-102) -> stream transforms incl. ``Buffer(n_buffer=2)``
@@ -96,12 +97,16 @@ class StreamBatch:
         except Exception:
             pass
 
-    def reset(self):
-        self.engine._ck(self.engine.lib.rnnt_b200_stream_reset(self._s))
+    def reset(self, slot=None):
+        """``slot`` (or every stream when None) back to the state of a fresh connection (models.py:494-500)."""
+        self.engine._ck(self.engine.lib.rnnt_b200_stream_reset(self._s, -1 if slot is None else int(slot)))
+        for b in (range(self.B) if slot is None else [int(slot)]):
+            self.tokens[b] = []
 
-    def push(self, chunks):
-        """chunks [B, chunk] float32, CUDA or (ideally pinned) CPU tensor.  Returns the list of new token lists
-        when the encoder advanced on this call, else None."""
+    def push(self, chunks, active=None):
+        """chunks [B, chunk] float32, CUDA or (ideally pinned) CPU tensor; ``active``: optional [B] booleans, streams with
+        False are skipped this tick.  Returns the list of new token lists (empty for streams that did not run) when at
+        least one stream advanced its encoder on this call, else None."""
         import ctypes as C
 
         eng = self.engine
@@ -110,7 +115,13 @@ class StreamBatch:
         if tuple(chunks.shape) != (self.B, self.chunk):
             raise ValueError(f"expected chunks of shape {(self.B, self.chunk)}, got {tuple(chunks.shape)}")
         with torch.cuda.device(eng.device):
+            act = None
+            if active is not None:
+                act = np.ascontiguousarray(np.asarray(active, dtype=np.uint8))
+                if act.shape != (self.B,):
+                    raise ValueError(f"expected {self.B} activity flags")
             eng._ck(eng.lib.rnnt_b200_stream_push(self._s, C.c_void_p(chunks.data_ptr()), 0 if chunks.is_cuda else 1,
+                                                  C.c_void_p(act.ctypes.data) if act is not None else C.c_void_p(0),
                                                   C.c_void_p(self._tok.data_ptr()), self.U, C.c_void_p(self._ntok.data_ptr()),
                                                   C.byref(self._adv), eng._stream()))
         if not self._adv.value:

@@ -1262,12 +1262,42 @@ int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, c
 struct rnnt_b200_stream_s {
   rnnt_b200_handle h = nullptr;
   int B = 0, chunk = 0, n_window = 0, n_buffer = 0, max_iters = 0;
-  int64_t n_chunks = 0;   // pushes since open / reset
-  int n_rows = 0;         // feature rows waiting in the Buffer
-  bool fresh = true;      // no encoder / decode step yet: start from the learnable states and BOS
+  // per-stream phase of the serving loop: chunks seen since the stream (re)started, rows waiting in its Buffer
+  std::vector<int64_t> n_chunks;
+  std::vector<int> n_rows;
   int cur = 0;            // which window buffer is current
   DevBuf win[2], stage, row, rows, enc_h, enc_c, pred_h, pred_out, enc_out, tokens, ntok, lm;
+  DevBuf bos_h, bos_out;  // predictor state / output after feeding BOS from the learnable state (reset_predictor, models.py:484-489)
+  DevBuf ctl;             // device copy of the per-tick control words: pos[B] | lens_T[B]
+  int32_t* ctl_host = nullptr;   // pinned staging for `ctl`
 };
+
+namespace {
+// stream `slot` back to the state of a fresh connection
+int stream_reset_slot_impl(rnnt_b200_stream s, int slot, cudaStream_t st) {
+  rnnt_b200_handle h = s->h;
+  const rnnt_b200_config& c = h->cfg;
+  const size_t H = c.hidden_sz, W = (size_t)s->n_window * s->chunk;
+  const int B = s->B;
+  for (int i = 0; i < 2; ++i) CK(cudaMemsetAsync(s->win[i].as<float>() + (size_t)slot * W, 0, W * 4, st));
+  for (int l = 0; l < c.enc_layers; ++l) {   // state None -> the learnable hs[i] (custom_rnn.py:152-158)
+    CK(cudaMemcpyAsync(s->enc_h.as<float>() + ((size_t)l * B + slot) * H, h->enc[l].h0, H * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(s->enc_c.as<float>() + ((size_t)l * B + slot) * H, h->enc[l].c0, H * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  for (int l = 0; l < c.pred_layers; ++l)
+    CK(cudaMemcpyAsync(s->pred_h.as<float>() + ((size_t)l * B + slot) * H, s->bos_h.as<float>() + (size_t)l * H, H * 4,
+                       cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(s->pred_out.as<float>() + (size_t)slot * H, s->bos_out.p, H * 4, cudaMemcpyDeviceToDevice, st));
+  if (c.lm_layers > 0) {   // LMFuser.reset (lm.py:81-83): column `slot` of the feature-major blob
+    const int Bp = bp_of(B);
+    const size_t rows = lm_state_floats(c.lm_layers, c.lm_hidden_sz, c.vocab_sz, Bp) / Bp;
+    CK(cudaMemset2DAsync(s->lm.as<float>() + slot, (size_t)Bp * 4, 0, 4, rows, st));
+  }
+  s->n_chunks[slot] = 0;
+  s->n_rows[slot] = 0;
+  return RNNT_B200_OK;
+}
+}  // namespace
 
 int32_t rnnt_b200_stream_open(rnnt_b200_handle h, int32_t B, int32_t chunk, int32_t n_window, int32_t n_buffer,
                               int32_t max_iters, rnnt_b200_stream* out) {
@@ -1285,6 +1315,7 @@ int32_t rnnt_b200_stream_open(rnnt_b200_handle h, int32_t B, int32_t chunk, int3
   CK(cudaSetDevice(c.device));
   rnnt_b200_stream s = new rnnt_b200_stream_s();
   s->h = h; s->B = B; s->chunk = chunk; s->n_window = n_window; s->n_buffer = n_buffer; s->max_iters = max_iters;
+  s->n_chunks.assign(B, 0); s->n_rows.assign(B, 0);
   const size_t X = (size_t)c.n_mels * c.n_stack, H = c.hidden_sz;
   cudaError_t e = cudaSuccess;
   auto need = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.ensure(bytes); };
@@ -1295,20 +1326,39 @@ int32_t rnnt_b200_stream_open(rnnt_b200_handle h, int32_t B, int32_t chunk, int3
   need(s->pred_h, (size_t)c.pred_layers * B * H * 4); need(s->pred_out, (size_t)B * H * 4);
   need(s->enc_out, (size_t)B * n_buffer * H * 4);
   need(s->tokens, (size_t)B * max_iters * n_buffer * 4); need(s->ntok, (size_t)B * 4);
+  need(s->bos_h, (size_t)c.pred_layers * H * 4); need(s->bos_out, H * 4);
+  need(s->ctl, (size_t)2 * B * 4);
   if (c.lm_layers > 0) need(s->lm, lm_state_floats(c.lm_layers, c.lm_hidden_sz, c.vocab_sz, bp_of(B)) * 4);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->ctl_host, (size_t)2 * B * 4);
   if (e != cudaSuccess) { rnnt_b200_stream_close(s); return fail_cuda(h, e, "stream_open: allocation"); }
+  // The predictor state of a fresh stream = the decode loop's own BOS step (models.py:484-489): run the decode kernel on
+  // one stream with zero frames -- it feeds BOS from the learnable state, finds nothing to decode and hands the state back.
+  {
+    void* prev_blob = h->lm_blob; const int prev_B = h->lm_blob_B;
+    h->lm_blob = nullptr; h->lm_blob_B = 0;
+    int32_t* zero_len = s->ctl.as<int32_t>();   // ensure() zero-fills: lens_T = 0
+    const int r = rnnt_b200_decode_greedy(h, s->enc_out.as<float>(), zero_len, 1, 1, max_iters, s->bos_h.as<float>(), s->bos_out.as<float>(), 0,
+                                          s->tokens.as<int32_t>(), max_iters * n_buffer, s->ntok.as<int32_t>(), nullptr, nullptr, nullptr, 0,
+                                          nullptr);
+    h->lm_blob = static_cast<float*>(prev_blob); h->lm_blob_B = prev_B;
+    if (r) { rnnt_b200_stream_close(s); return r; }
+  }
+  for (int b = 0; b < B; ++b)
+    if (int r = stream_reset_slot_impl(s, b, nullptr)) { rnnt_b200_stream_close(s); return r; }
+  CK(cudaStreamSynchronize(nullptr));
   *out = s;
   return RNNT_B200_OK;
 }
 
-int32_t rnnt_b200_stream_reset(rnnt_b200_stream s) {
+int32_t rnnt_b200_stream_reset(rnnt_b200_stream s, int32_t slot) {
   if (!s) return RNNT_B200_ERR_INVALID;
   rnnt_b200_handle h = s->h;
+  if (slot < -1 || slot >= s->B) return fail(h, RNNT_B200_ERR_INVALID, "stream_reset: slot out of range (-1 = all streams)");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
-  for (DevBuf* b : {&s->win[0], &s->win[1], &s->lm})
-    if (b->p) CK(cudaMemset(b->p, 0, b->bytes));
-  s->n_chunks = 0; s->n_rows = 0; s->fresh = true; s->cur = 0;
+  for (int b = (slot < 0 ? 0 : slot); b < (slot < 0 ? s->B : slot + 1); ++b)
+    if (int r = stream_reset_slot_impl(s, b, nullptr)) return r;
+  CK(cudaStreamSynchronize(nullptr));
   return RNNT_B200_OK;
 }
 
@@ -1318,14 +1368,15 @@ int32_t rnnt_b200_stream_close(rnnt_b200_stream s) {
   cudaDeviceSynchronize();
   if (s->h->lm_blob == s->lm.p) { s->h->lm_blob = nullptr; s->h->lm_blob_B = 0; }
   for (DevBuf* b : {&s->win[0], &s->win[1], &s->stage, &s->row, &s->rows, &s->enc_h, &s->enc_c, &s->pred_h, &s->pred_out,
-                    &s->enc_out, &s->tokens, &s->ntok, &s->lm})
+                    &s->enc_out, &s->tokens, &s->ntok, &s->lm, &s->bos_h, &s->bos_out, &s->ctl})
     b->release();
+  if (s->ctl_host) cudaFreeHost(s->ctl_host);
   delete s;
   return RNNT_B200_OK;
 }
 
-int32_t rnnt_b200_stream_push(rnnt_b200_stream s, const float* chunks, int32_t on_host, int32_t* tokens_host, int32_t U_cap,
-                              int32_t* ntok_host, int32_t* advanced, void* stream) {
+int32_t rnnt_b200_stream_push(rnnt_b200_stream s, const float* chunks, int32_t on_host, const uint8_t* active_host,
+                              int32_t* tokens_host, int32_t U_cap, int32_t* ntok_host, int32_t* advanced, void* stream) {
   if (!s) return RNNT_B200_ERR_INVALID;
   rnnt_b200_handle h = s->h;
   const rnnt_b200_config& c = h->cfg;
@@ -1335,37 +1386,53 @@ int32_t rnnt_b200_stream_push(rnnt_b200_stream s, const float* chunks, int32_t o
   const int B = s->B, ck = s->chunk;
   const size_t W = (size_t)s->n_window * ck, X = (size_t)c.n_mels * c.n_stack;
   const int U = s->max_iters * s->n_buffer;
-  // slide every stream's window by one chunk (api-server.py:99-102): new = [old[chunk:], chunk]
+  // per-stream phase (api-server.py:95-115 + Buffer, transforms.py:463-471), advanced on the host; the kernels get it as words
+  StreamMask mask;
+  memset(&mask, 0, sizeof(mask));
+  int32_t* pos = s->ctl_host;
+  int32_t* lens = s->ctl_host + B;
+  bool any_row = false, any_ready = false;
+  CK(cudaStreamSynchronize(st));   // the staging words of the previous tick have been consumed
+  for (int b = 0; b < B; ++b) {
+    pos[b] = -1; lens[b] = 0;
+    if (active_host && !active_host[b]) continue;
+    mask.bits[b >> 5] |= 1u << (b & 31);
+    s->n_chunks[b] += 1;
+    if (s->n_chunks[b] < s->n_window) continue;       // server: `continue` until the window is full
+    pos[b] = s->n_rows[b];
+    any_row = true;
+    if (++s->n_rows[b] == s->n_buffer) { s->n_rows[b] = 0; lens[b] = s->n_buffer; any_ready = true; }
+  }
+  const float* chunks_dev = chunks;
+  if (on_host) {
+    CK(cudaMemcpyAsync(s->stage.p, chunks, (size_t)B * ck * 4, cudaMemcpyHostToDevice, st));
+    chunks_dev = s->stage.as<float>();
+  }
   float* wold = s->win[s->cur].as<float>();
   float* wnew = s->win[s->cur ^ 1].as<float>();
-  if (s->n_window > 1)
-    CK(cudaMemcpy2DAsync(wnew, W * 4, wold + ck, W * 4, (W - ck) * 4, B, cudaMemcpyDeviceToDevice, st));
-  CK(cudaMemcpy2DAsync(wnew + (W - ck), W * 4, chunks, (size_t)ck * 4, (size_t)ck * 4, B,
-                       on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+  LAUNCH(1, launch_slide_window(wold, wnew, chunks_dev, B, (int)W, ck, mask, st));
   s->cur ^= 1;
-  s->n_chunks += 1;
-  if (s->n_chunks < s->n_window) return RNNT_B200_OK;
-  // stream transforms -> one stacked row per stream, appended to the Buffer (transforms.py:326-342,463-471)
+  if (!any_row) return RNNT_B200_OK;
+  CK(cudaMemcpyAsync(s->ctl.p, s->ctl_host, (size_t)2 * B * 4, cudaMemcpyHostToDevice, st));
+  // stream transforms -> one stacked row per stream, appended to its Buffer (transforms.py:326-342,463-471)
   if (int r = rnnt_b200_features_stream(h, wnew, B, (int64_t)W, s->row.as<float>(), stream)) return r;
-  CK(cudaMemcpy2DAsync(s->rows.as<float>() + (size_t)s->n_rows * X, (size_t)s->n_buffer * X * 4, s->row.p, X * 4, X * 4, B,
-                       cudaMemcpyDeviceToDevice, st));
-  if (++s->n_rows < s->n_buffer) return RNNT_B200_OK;
-  s->n_rows = 0;
+  LAUNCH(1, launch_store_rows(s->row.as<float>(), s->rows.as<float>(), s->ctl.as<int32_t>(), B, (int)X, s->n_buffer, st));
+  if (!any_ready) return RNNT_B200_OK;
   if (!tokens_host || !ntok_host || U_cap < U) return fail(h, RNNT_B200_ERR_INVALID, "stream_push: token outputs missing or U_cap < max_iters * n_buffer");
-  // Transducer.transcribe_stream, one chunk of n_buffer encoder steps (models.py:503-571)
-  const int use_in = s->fresh ? 0 : 1;
-  if (int r = rnnt_b200_encode(h, s->rows.as<float>(), nullptr, B, s->n_buffer, s->enc_h.as<float>(), s->enc_c.as<float>(), use_in,
+  // Transducer.transcribe_stream, one chunk of n_buffer encoder steps for the streams whose Buffer filled (models.py:503-571);
+  // the others take part with zero frames (state untouched)
+  const int32_t* lens_dev = s->ctl.as<int32_t>() + B;
+  if (int r = rnnt_b200_encode(h, s->rows.as<float>(), lens_dev, B, s->n_buffer, s->enc_h.as<float>(), s->enc_c.as<float>(), 1,
                                s->enc_out.as<float>(), stream))
     return r;
   void* prev_blob = h->lm_blob;
   const int prev_B = h->lm_blob_B;
   if (c.lm_layers > 0) { h->lm_blob = s->lm.as<float>(); h->lm_blob_B = B; }
-  const int r = rnnt_b200_decode_greedy(h, s->enc_out.as<float>(), nullptr, B, s->n_buffer, s->max_iters, s->pred_h.as<float>(),
-                                        s->pred_out.as<float>(), use_in, s->tokens.as<int32_t>(), U, s->ntok.as<int32_t>(), nullptr,
+  const int r = rnnt_b200_decode_greedy(h, s->enc_out.as<float>(), lens_dev, B, s->n_buffer, s->max_iters, s->pred_h.as<float>(),
+                                        s->pred_out.as<float>(), 1, s->tokens.as<int32_t>(), U, s->ntok.as<int32_t>(), nullptr,
                                         nullptr, nullptr, 0, stream);
   h->lm_blob = static_cast<float*>(prev_blob); h->lm_blob_B = prev_B;
   if (r) return r;
-  s->fresh = false;
   CK(cudaMemcpy2DAsync(tokens_host, (size_t)U_cap * 4, s->tokens.p, (size_t)U * 4, (size_t)U * 4, B, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ntok_host, s->ntok.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

@@ -4,6 +4,8 @@
 
 namespace rnnt {
 
+constexpr int kDecodeMaxBatchWords = 8;   // 256 streams / 32
+
 // ---------------- frontend.cu ----------------
 constexpr int kFrontendMaxWarps = 16;
 
@@ -105,6 +107,12 @@ cudaError_t launch_state_broadcast_T(const float* vec_H, float* out_HB, int B, i
 // steps[b] = min(T_max, encoder steps of an utterance with lens[b] samples)
 cudaError_t launch_lens_to_steps(const int32_t* lens, int32_t* steps, int B, int hop, int n_stack, int D, int T_max,
                                  cudaStream_t st);
+
+// ---------------- stream.cu (streaming session helpers) ----------------
+struct StreamMask { uint32_t bits[kDecodeMaxBatchWords]; };   // one bit per stream
+cudaError_t launch_slide_window(const float* w_old, float* w_new, const float* chunks, int B, int W, int ck, const StreamMask& active,
+                                cudaStream_t st);
+cudaError_t launch_store_rows(const float* row, float* rows, const int32_t* pos, int B, int X, int n_buffer, cudaStream_t st);
 
 // ---------------- decode.cu ----------------
 constexpr int kMaxPredLayers = 4;

@@ -555,3 +555,37 @@ def test_stream_session_beyond_64_streams():
     sb.close()
     for b in (0, 33, 64, 69):
         assert ticks[b] == _oracle_stream_tokens(orc, cfg, audio[b], n_chunks), f"stream {b}"
+
+
+def test_stream_session_independent_lifecycles():
+    """Streams of one session start, pause and restart independently: stream 1 connects 3 ticks late, stream 2 skips two
+    ticks in the middle (no chunk), stream 0 is reset (new connection) at tick 11.  Every stream's tokens equal the
+    oracle's transcribe_stream on the chunks that stream actually received since its (re)start."""
+    from libreasr_b200.api import StreamBatch
+
+    cfg, sd, m, orc = model_for("tiny")
+    S, n_ticks = 3, 26
+    audio = weights.make_audio(S, n_ticks * CHUNK, seed=75)
+    sb = StreamBatch(m.engine(), S, max_iters=10)
+    got = [[] for _ in range(S)]
+    fed = [[] for _ in range(S)]          # chunk indices each stream consumed since its last (re)start
+    for j in range(n_ticks):
+        if j == 11:
+            sb.reset(0)
+            got[0], fed[0] = [], []
+        active = [True, j >= 3, j not in (8, 9)]
+        for b in range(S):
+            if active[b]:
+                fed[b].append(j)
+        new = sb.push(torch.from_numpy(np.ascontiguousarray(audio[:, j * CHUNK:(j + 1) * CHUNK])), active=active)
+        if new is not None:
+            for b in range(S):
+                if new[b] or True:
+                    got[b].append(new[b])
+    sb.close()
+    for b in range(S):
+        seq = np.concatenate([audio[b, j * CHUNK:(j + 1) * CHUNK] for j in fed[b]])
+        want = _oracle_stream_tokens(orc, cfg, seq, len(fed[b]))
+        flat_got = [t for tick in got[b] for t in tick]
+        flat_want = [t for tick in want for t in tick]
+        assert flat_got == flat_want, f"stream {b}"
