@@ -148,6 +148,16 @@ int32_t rnnt_b200_logmel(rnnt_b200_handle h, const float* audio_dev, const int32
 int32_t rnnt_b200_features_stream(rnnt_b200_handle h, const float* window_dev, int32_t B, int64_t W,
                                   float* feats_dev, void* stream);
 
+/* ---- resampling: a2 ------------------------------------------------------------------ */
+
+/* Replaces Resample.encodes (transforms.py:135-144): torchaudio.transforms.Resample(orig_freq = orig_sr,
+ * new_freq = cfg.sample_rate) with its defaults (windowed-sinc, lowpass_filter_width 6, rolloff 0.99) for B utterances.
+ * audio_dev [B, n] -> out_dev [B, rnnt_b200_resample_len(n, orig_sr)]; orig_sr == cfg.sample_rate copies.
+ * ChannelCut (transforms.py:122-132) needs no kernel: the caller passes the first channel. */
+int64_t rnnt_b200_resample_len(rnnt_b200_handle h, int64_t n, int32_t orig_sr);
+int32_t rnnt_b200_resample(rnnt_b200_handle h, const float* audio_dev, int32_t B, int64_t n, int32_t orig_sr,
+                           float* out_dev, void* stream);
+
 /* ---- encoder: a7 + a8 + a9 -------------------------------------------------------- */
 
 /* Replaces Encoder.forward(x, state, lengths, return_state) (models.py:105-113) and

@@ -47,6 +47,8 @@ SIGNATURES = {
     "rnnt_b200_features": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "rnnt_b200_logmel": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "rnnt_b200_features_stream": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
+    "rnnt_b200_resample_len": (_i64, [_vp, _i64, _i32]),
+    "rnnt_b200_resample": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp]),
     "rnnt_b200_encode": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "rnnt_b200_predict": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "rnnt_b200_joint": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),

@@ -32,10 +32,12 @@ class LibreASR:
 
     # offline: ASRServicer.Transcribe (api-server.py:64-80) for one or many utterances
     def transcribe(self, audio, lens=None, max_iters=3, sr=16000):
-        if int(sr) != self.engine.cfg.sample_rate:
-            raise NotImplementedError("only 16 kHz input is built (Resample is an identity on this path)")
         a = _as_audio(audio)
         single = a.shape[0] == 1 and not (torch.is_tensor(audio) and audio.dim() == 2)
+        if int(sr) != self.engine.cfg.sample_rate:   # Resample (transforms.py:135-144) on the device, then the 16 kHz path
+            if lens is not None:
+                raise ValueError("lens are not supported together with resampling; trim the utterances first")
+            a = self.engine.resample(a.to(self.engine.device), int(sr))
         if a.is_cuda:
             r = self.engine.transcribe(a, lens, max_iters)
         else:

@@ -91,6 +91,9 @@ struct rnnt_b200_handle_s {
   DevBuf lm_himg, lm_stat;
   float* lm_blob = nullptr;   // caller-owned fuser state (rnnt_b200_set_lm_state); nullptr = fresh fuser per call
   int lm_blob_B = 0;
+  // resampler filter banks per source rate (built on first use)
+  struct ResampleTab { int o = 0, n = 0, width = 0, K = 0; float* dev = nullptr; };
+  std::map<int, ResampleTab> resample_tabs;
   // transcribe_host: copy engine stream + events so that the H2D of utterance block i+1 overlaps the front end of block i
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -789,6 +792,59 @@ int32_t rnnt_b200_features_stream(rnnt_b200_handle h, const float* window, int32
   a.window = h->window; a.tw = h->tw; a.mel_start = h->mel_start; a.mel_count = h->mel_count; a.mel_off = h->mel_off;
   a.mel_w = h->mel_w; a.log_offset = c.log_offset;
   LAUNCH(1, launch_mel_stack(a, B, (cudaStream_t)stream));
+  return RNNT_B200_OK;
+}
+
+namespace {
+int64_t gcd64(int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; }
+}
+
+int64_t rnnt_b200_resample_len(rnnt_b200_handle h, int64_t n, int32_t orig_sr) {
+  if (!h || n < 0 || orig_sr < 1) return -1;
+  const int64_t g = gcd64(orig_sr, h->cfg.sample_rate), o = orig_sr / g, nn = h->cfg.sample_rate / g;
+  return (nn * n + o - 1) / o;   // ceil(new * n / orig)
+}
+
+int32_t rnnt_b200_resample(rnnt_b200_handle h, const float* audio, int32_t B, int64_t n, int32_t orig_sr, float* out, void* stream) {
+  if (!h) return RNNT_B200_ERR_INVALID;
+  if (!audio || !out || B < 1 || B > 65535 || n < 1 || orig_sr < 1) return fail(h, RNNT_B200_ERR_INVALID, "resample: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const rnnt_b200_config& c = h->cfg;
+  CK(cudaSetDevice(c.device));
+  if (orig_sr == c.sample_rate) {
+    CK(cudaMemcpyAsync(out, audio, (size_t)B * n * 4, cudaMemcpyDeviceToDevice, st));
+    return RNNT_B200_OK;
+  }
+  auto it = h->resample_tabs.find(orig_sr);
+  if (it == h->resample_tabs.end()) {
+    // torchaudio.functional._get_sinc_resample_kernel (sinc_interp_hann, lowpass_filter_width = 6, rolloff = 0.99):
+    // float64 grid, the phase term -p / new formed in float32, result rounded to float32
+    const int64_t g = gcd64(orig_sr, c.sample_rate);
+    rnnt_b200_handle_s::ResampleTab t;
+    t.o = (int)(orig_sr / g); t.n = (int)(c.sample_rate / g);
+    const double lpw = 6.0, base = (double)std::min(t.o, t.n) * 0.99;
+    t.width = (int)std::ceil(lpw * t.o / base);
+    t.K = 2 * t.width + t.o;
+    if ((int64_t)t.n * t.K > (int64_t)64 << 20) return fail(h, RNNT_B200_ERR_UNSUPPORTED, "resample: rate ratio needs an unreasonably large filter bank");
+    std::vector<float> tab((size_t)t.n * t.K);
+    const double pi = 3.14159265358979323846;
+    for (int p = 0; p < t.n; ++p) {
+      const double phase = (double)((float)(-p) / (float)t.n);
+      for (int k = 0; k < t.K; ++k) {
+        double x = (phase + (double)(k - t.width) / (double)t.o) * base;
+        x = std::min(std::max(x, -lpw), lpw);
+        const double cw = std::cos(x * pi / lpw / 2.0), window = cw * cw;
+        x *= pi;
+        const double sinc = (x == 0.0) ? 1.0 : std::sin(x) / x;
+        tab[(size_t)p * t.K + k] = (float)(sinc * window * (base / (double)t.o));
+      }
+    }
+    CK(upload(h, tab, &t.dev));
+    it = h->resample_tabs.emplace(orig_sr, t).first;
+  }
+  const auto& t = it->second;
+  const int64_t L = rnnt_b200_resample_len(h, n, orig_sr);
+  LAUNCH(1, launch_resample(audio, B, n, t.dev, t.o, t.n, t.width, t.K, out, L, st));
   return RNNT_B200_OK;
 }
 

@@ -171,6 +171,26 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
   for (int i = lane; i < X; i += 32) o[i] = (r[i] - mean) * inv * gamma[i] + beta[i];
 }
 
+// Polyphase windowed-sinc resampler (torchaudio.transforms.Resample as the reference calls it, transforms.py:135-144):
+// out[b][j * n_new + p] = sum_k tab[p][k] * x[b][j * n_orig + k - width]   (zero outside the utterance)
+__global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ tab,
+                                                       int n_orig, int n_new, int width, int K, float* __restrict__ out, int64_t L) {
+  const int b = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const int64_t j = i / n_new;
+  const int p = (int)(i - j * n_new);
+  const float* xb = x + (size_t)b * n;
+  const float* t = tab + (size_t)p * K;
+  const int64_t s0 = j * n_orig - width;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const int64_t s = s0 + k;
+    if (s >= 0 && s < n) acc = fmaf(t[k], xb[s], acc);
+  }
+  out[(size_t)b * L + i] = acc;
+}
+
 }  // namespace
 
 size_t frontend_smem_bytes(int n_stack, int n_mels) {
@@ -192,6 +212,13 @@ cudaError_t launch_layernorm(const float* in, float* out, const float* gamma, co
                              float eps, cudaStream_t st) {
   const int64_t blocks = ceil_div(rows, 8);
   layernorm_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, out, gamma, beta, rows, X, eps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resample(const float* x, int B, int64_t n, const float* tab, int n_orig, int n_new, int width, int K, float* out,
+                            int64_t L, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(L, 256), (unsigned)B);
+  resample_kernel<<<grid, 256, 0, st>>>(x, n, tab, n_orig, n_new, width, K, out, L);
   return cudaGetLastError();
 }
 

@@ -28,6 +28,8 @@ struct FrontendArgs {
 };
 size_t frontend_smem_bytes(int n_stack, int n_mels);
 cudaError_t launch_mel_stack(const FrontendArgs& a, int B, cudaStream_t st);
+cudaError_t launch_resample(const float* x, int B, int64_t n, const float* tab, int n_orig, int n_new, int width, int K, float* out,
+                            int64_t L, cudaStream_t st);
 cudaError_t launch_layernorm(const float* in, float* out, const float* gamma, const float* beta, int64_t rows, int X,
                              float eps, cudaStream_t st);
 

@@ -219,6 +219,16 @@ class Engine:
         self._ck(self.lib.rnnt_b200_features_stream(self._h, _ptr(window), B, W, _ptr(out), self._stream()))
         return out
 
+    # ---- resampling (Resample, transforms.py:135-144) ---------------------------------------------
+    def resample(self, audio, orig_sr):
+        """audio [B, n] at ``orig_sr`` -> [B, ceil(sample_rate * n / orig_sr)] at the model's sample rate."""
+        audio = self._f32(audio)
+        B, n = audio.shape
+        L = int(self.lib.rnnt_b200_resample_len(self._h, n, int(orig_sr)))
+        out = torch.empty(B, L, device=self.device)
+        self._ck(self.lib.rnnt_b200_resample(self._h, _ptr(audio), B, n, int(orig_sr), _ptr(out), self._stream()))
+        return out
+
     # ---- encoder -------------------------------------------------------------------------
     def encode(self, feats, lens_T=None, state=None, want_state=False):
         """feats [B, T, X]; state = (h [L,B,H], c [L,B,H]) or None.  Returns (enc [B,T,H], state|None)."""

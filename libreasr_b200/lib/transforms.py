@@ -21,15 +21,23 @@ def tensorize(x):
 
 
 class Resample:
-    """transforms.py:135-144.  The built path is 16 kHz in / 16 kHz out (identity)."""
+    """transforms.py:135-144: ``torchaudio.transforms.Resample(orig_freq=i.sr, new_freq=target_sr)`` on the GPU
+    (``rnnt_b200_resample``: the same windowed-sinc filter bank).  ``engine`` may be omitted for the identity case."""
 
-    def __init__(self, target_sr=16000, **kwargs):
+    def __init__(self, target_sr=16000, engine=None, **kwargs):
         self.sr = target_sr
+        self.engine = engine
 
     def encodes(self, i, sr=None):
-        if sr is not None and int(sr) != int(self.sr):
-            raise NotImplementedError(f"resampling {sr} -> {self.sr} Hz is outside the built path; feed 16 kHz audio")
-        return i
+        sr = getattr(i, "sr", sr) if sr is None else sr
+        if sr is None or int(sr) == int(self.sr):
+            return i
+        if self.engine is None:
+            raise RuntimeError("Resample needs the CUDA engine for sr != target_sr (there is no CPU path): Resample(sr, engine=...)")
+        if int(self.engine.cfg.sample_rate) != int(self.sr):
+            raise ValueError("target_sr differs from the engine's sample rate")
+        x = i if i.dim() == 2 else i[None]
+        return self.engine.resample(x.to(self.engine.device, torch.float32), int(sr))
 
     __call__ = encodes
 

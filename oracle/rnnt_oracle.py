@@ -38,6 +38,40 @@ BOS = 2  # models.py:226-227
 # ----------------------------------------------------------------------------
 # features (a3, a4, a5, a6)
 # ----------------------------------------------------------------------------
+def resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """Polyphase windowed-sinc filter bank of ``torchaudio.transforms.Resample(orig_freq, new_freq)`` with its defaults
+    (sinc_interp_hann) -- the call the reference makes per utterance (transforms.py:135-144; the pinned torchaudio 0.6.0 routed
+    it through kaldi.resample_waveform, the same algorithm).  Returns (kernels [new, K] float32, width, orig/gcd, new/gcd)."""
+    import math
+
+    g = math.gcd(int(orig_freq), int(new_freq))
+    o, n = int(orig_freq) // g, int(new_freq) // g
+    base = min(o, n) * rolloff
+    width = math.ceil(lowpass_filter_width * o / base)
+    idx = np.arange(-width, width + o, dtype=np.float64)[None, :] / o
+    # the phase term is formed in float32 (int64 / python int under torch's default dtype) before it meets the float64 grid
+    t = (np.arange(0, -n, -1).astype(np.float32) / np.float32(n)).astype(np.float64)[:, None] + idx
+    t = t * base
+    t = np.clip(t, -lowpass_filter_width, lowpass_filter_width)
+    window = np.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k = np.where(t == 0, 1.0, np.sin(t) / t)
+    k = k * window * (base / o)
+    return k.astype(np.float32), width, o, n
+
+
+def resample(audio: torch.Tensor, orig_freq: int, new_freq: int = 16000) -> torch.Tensor:
+    """``Resample.encodes`` (transforms.py:135-144): audio [C, n] at orig_freq -> [C, ceil(new * n / orig)]."""
+    if int(orig_freq) == int(new_freq):
+        return audio
+    k, width, o, n = resample_kernel(orig_freq, new_freq)
+    x = F.pad(audio, (width, width + o))
+    y = F.conv1d(x[:, None], torch.from_numpy(k)[:, None], stride=o)          # [C, new, frames]
+    y = y.transpose(1, 2).reshape(audio.shape[0], -1)
+    return y[:, : int(np.ceil(n * audio.shape[1] / o))]
+
+
 def mel_fbanks_htk(n_freqs: int, n_mels: int, sample_rate: int) -> torch.Tensor:
     """[n_freqs, n_mels] HTK triangular filterbank, f_min=0, f_max=sr/2, norm=None
     (what ``MelSpectrogram(sample_rate, n_fft, n_mels)`` builds by default;

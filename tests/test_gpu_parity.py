@@ -589,3 +589,21 @@ def test_stream_session_independent_lifecycles():
         flat_got = [t for tick in got[b] for t in tick]
         flat_want = [t for tick in want for t in tick]
         assert flat_got == flat_want, f"stream {b}"
+
+
+@pytest.mark.parametrize("orig", [8000, 44100, 22050, 48000, 16000])
+def test_resample_matches_oracle(orig):
+    """Row a2: Resample to 16 kHz on the GPU vs the oracle's restatement of torchaudio.transforms.Resample (2e-6 abs), and the
+    facade resamples before transcribing."""
+    from libreasr_b200 import LibreASR
+
+    cfg, sd, m, orc = model_for("tiny")
+    eng = m.engine()
+    x = weights.make_audio(3, int(orig * 1.3), seed=6)
+    got = eng.resample(torch.from_numpy(x).cuda(), orig)
+    want = O.resample(torch.from_numpy(x), orig, 16000)
+    assert tuple(got.shape) == tuple(want.shape)
+    np.testing.assert_allclose(cpu(got), want.numpy(), atol=2e-6)
+    toks = LibreASR(m).transcribe(torch.from_numpy(x[0]), sr=orig)
+    feats = O.features_offline(want[:1], cfg)[0]
+    assert toks == orc.decode_greedy(feats, max_iters=3, impl="aten")["tokens"]

@@ -139,3 +139,15 @@ def test_lm_fusion_matches_reference(name):
     yields = list(orc.transcribe_stream(iter(rows), max_iters=10, lm=lm))
     assert [len(ys) for _, ys in yields] == g["stream_chunk_counts"].tolist()
     assert (yields[-1][0] if yields else []) == g["stream_tokens_all"].tolist()
+
+
+@pytest.mark.parametrize("orig", [8000, 44100, 22050, 48000])
+def test_resample_restatement_matches_torchaudio(orig):
+    """the reference resamples with ``torchaudio.transforms.Resample(orig_freq=sr, new_freq=16000)``
+    (transforms.py:135-144); the oracle's explicit filter bank + strided correlation equals that call."""
+    torchaudio = pytest.importorskip("torchaudio")
+    x = torch.from_numpy(weights.make_audio(2, 9000, seed=5))
+    ref = torchaudio.transforms.Resample(orig_freq=orig, new_freq=16000)(x)
+    got = O.resample(x, orig, 16000)
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-7)
