@@ -18,12 +18,19 @@ def main():
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--seconds", type=float, default=20.0)
     ap.add_argument("--gemm-mode", type=int, default=1)
+    ap.add_argument("--lm", default="", help="fuse a language model: en (4x768) or default (6x1024)")
     a = ap.parse_args()
     cfg = synth.CONFIGS["cfg2"]
     ec = EngineConfig(n_mels=cfg.n_mels, n_stack=cfg.n_stack, downsample=cfg.downsample, enc_layers=cfg.enc_layers,
                       pred_layers=cfg.pred_layers, hidden_sz=cfg.hidden_sz, embed_sz=cfg.embed_sz, joint_sz=cfg.joint_sz,
                       vocab_sz=cfg.vocab_sz, gemm_mode=a.gemm_mode)
-    eng = Engine(ec).load_state_dict(synth.make_state_dict(cfg, 1234))
+    lsd = None
+    if a.lm:
+        import dataclasses
+        lc = synth.LM_CONFIGS[a.lm]
+        ec = dataclasses.replace(ec, lm_layers=lc.num_layers, lm_hidden_sz=lc.hidden_sz, lm_embed_sz=lc.embed_sz)
+        lsd = synth.make_lm_state_dict(lc, 4321)
+    eng = Engine(ec).load_state_dict(synth.make_state_dict(cfg, 1234), lm_state_dict=lsd)
     chunk = 1280
     n_chunks = int(a.seconds * 16000) // chunk
     audio = synth.make_audio(a.streams, n_chunks * chunk, seed=1)   # seed 1: BASELINE.md config 3
@@ -47,7 +54,7 @@ def main():
                       "streams": a.streams, "audio_s_per_stream": round((n_chunks - warm) * 0.08, 2), "wall_s": round(dt, 3),
                       "model_tick_ms_mean": round(1e3 * float(np.mean(lat)), 3), "model_tick_ms_p50": round(1e3 * float(np.median(lat)), 3), "model_tick_ms_p99": round(1e3 * float(np.quantile(lat, 0.99)), 3),
                       "ticks_with_model_step": len(lat), "tokens_total": int(sum(len(t) for t in sb.tokens)),
-                      "gemm_mode": a.gemm_mode, "note": "rnnt_b200_stream_push per tick (host chunks in, host tokens out); one model step (encoder T=2 -> greedy decode) every second 80 ms chunk"}))
+                      "gemm_mode": a.gemm_mode, "lm": a.lm or None, "note": "rnnt_b200_stream_push per tick (host chunks in, host tokens out); one model step (encoder T=2 -> greedy decode) every second 80 ms chunk"}))
 
 
 if __name__ == "__main__":
