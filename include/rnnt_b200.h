@@ -258,8 +258,8 @@ int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, c
  *          (api-server.py:97-98); afterwards every chunk yields one feature row and every n_buffer-th row the encoder +
  *          decode loop run for that stream (streams whose Buffer is not full take part with zero frames).  *advanced_out = 1
  *          when at least one stream ran the model; tokens_host_out [B, U_cap] (U_cap >= max_iters * n_buffer) / ntok_host_out
- *          [B] then hold the tokens each stream emitted in this tick (host memory; 0 tokens for the streams that did not
- *          run; the call synchronises the stream).  Otherwise *advanced_out = 0 and the outputs are untouched.
+ *          [B] then hold the tokens each stream emitted in this tick (host memory; ntok = -1 marks a stream that did not run
+ *          the model in this tick, 0 one that ran and emitted nothing; the call synchronises the stream).  Otherwise *advanced_out = 0 and the outputs are untouched.
  *   reset: stream `slot` (or all streams when slot = -1) back to the state of a fresh connection: the `reset` closure of
  *          transcribe_stream (models.py:494-500: learnable encoder state, predictor fed BOS, LMFuser.reset) plus an empty
  *          window and Buffer.  Streams may be reset at any tick; the others are not disturbed. */

@@ -129,7 +129,8 @@ class StreamBatch:
         if not self._adv.value:
             return None
         t, n = self._tok.numpy(), self._ntok.numpy()
-        new = [t[b, : int(n[b])].tolist() for b in range(self.B)]
+        self.ran = [int(n[b]) >= 0 for b in range(self.B)]   # which streams took part in this model step
+        new = [t[b, : max(int(n[b]), 0)].tolist() for b in range(self.B)]
         for b in range(self.B):
             self.tokens[b].extend(new[b])
         return new

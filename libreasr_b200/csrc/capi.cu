@@ -1492,6 +1492,8 @@ int32_t rnnt_b200_stream_push(rnnt_b200_stream s, const float* chunks, int32_t o
   CK(cudaMemcpy2DAsync(tokens_host, (size_t)U_cap * 4, s->tokens.p, (size_t)U * 4, (size_t)U * 4, B, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ntok_host, s->ntok.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  for (int b = 0; b < B; ++b)
+    if (lens[b] == 0) ntok_host[b] = -1;   // this stream did not run the model in this tick
   *advanced = 1;
   return RNNT_B200_OK;
 }

@@ -607,3 +607,69 @@ def test_resample_matches_oracle(orig):
     toks = LibreASR(m).transcribe(torch.from_numpy(x[0]), sr=orig)
     feats = O.features_offline(want[:1], cfg)[0]
     assert toks == orc.decode_greedy(feats, max_iters=3, impl="aten")["tokens"]
+
+
+def test_grpc_streaming_end_to_end():
+    """The serving wire path (libreasr_b200/serve.py) on the real engine: gRPC `ASR.ASR/TranscribeStream` over loopback, three
+    concurrent clients sending `Audio{data, sr}` frames of 80 ms; each client's `Transcript` messages equal the oracle's
+    transcribe_stream on that client's audio passed through the reference's diffing (api-server.py:117-135).  Unary
+    `Transcribe` at 8 kHz goes through the resampler."""
+    import itertools as it
+    import threading
+    import time
+    from concurrent import futures
+
+    grpc = pytest.importorskip("grpc")
+    from libreasr_b200 import LibreASR
+    from libreasr_b200 import serve as S
+
+    cfg, sd, m, orc = model_for("tiny")
+    denum = lambda ids: "".join(chr(0x100 + int(t)) for t in ids)   # noqa: E731
+    asr = LibreASR(m)
+    server = grpc.server(futures.ThreadPoolExecutor(max_workers=12))
+    servicer = S.ASRServicer(asr, n_streams=4, denumericalize=denum)
+    S.add_servicer_to_server(servicer, server)
+    port = server.add_insecure_port("127.0.0.1:0")
+    server.start()
+    try:
+        ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+        ident = lambda b: b  # noqa: E731
+        stream = ch.stream_stream(f"/{S.SERVICE}/TranscribeStream", request_serializer=ident, response_deserializer=ident)
+        n_chunks = 30
+        audio = weights.make_audio(3, n_chunks * CHUNK, seed=77)
+
+        def client(b, out):
+            def gen():
+                for j in range(n_chunks):
+                    yield S.encode_audio(audio[b, j * CHUNK:(j + 1) * CHUNK].astype("<f4").tobytes(), 16000)
+                    time.sleep(0.001 * (b + 1))
+            out.extend(S.decode_transcript(r) for r in stream(gen(), timeout=60))
+
+        outs = [[] for _ in range(3)]
+        ths = [threading.Thread(target=client, args=(b, outs[b])) for b in range(3)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join(timeout=90)
+        for b in range(3):
+            steps = _oracle_stream_tokens(orc, cfg, audio[b], n_chunks)
+            want, last, last_diff, y = [], "", "", []
+            for new in steps:
+                y = y + new
+                if denum(new) != "":
+                    now = denum(y)
+                    diff = "".join(c2 for c1, c2 in it.zip_longest(last, now) if c1 != c2)
+                    last = now
+                    if diff == last_diff:
+                        continue
+                    last_diff = diff
+                    want.append(diff)
+            assert outs[b] == want, f"client {b}"
+        unary = ch.unary_unary(f"/{S.SERVICE}/Transcribe", request_serializer=ident, response_deserializer=ident)
+        x8 = weights.make_audio(1, 12000, seed=78)[0]
+        got = S.decode_transcript(unary(S.encode_audio(x8.astype("<f4").tobytes(), 8000), timeout=30))
+        feats = O.features_offline(O.resample(torch.from_numpy(x8[None]), 8000, 16000), cfg)[0]
+        assert got == denum(orc.decode_greedy(feats, max_iters=3, impl="aten")["tokens"])
+    finally:
+        server.stop(0)
+        servicer.close()
