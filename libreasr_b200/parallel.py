@@ -23,6 +23,27 @@ def shard_bounds(n_items: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def balanced_order(lens, world: int) -> List[int]:
+    """Permutation that evens out the work of ragged batches ("optionally length-sorted then round-robin
+    to balance T"): utterances sorted by length are dealt to the ranks in snake order, and each rank's share is laid out as
+    its contiguous block of ``shard_bounds``.  ``order[i]`` = index of the utterance placed at position i."""
+    n = len(lens)
+    idx = sorted(range(n), key=lambda i: (-int(lens[i]), i))
+    per_rank = [[] for _ in range(world)]
+    caps = [shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0] for r in range(world)]
+    r, step = 0, 1
+    for i in idx:
+        while len(per_rank[r]) >= caps[r]:          # a rank that is full is skipped
+            r, step = (r + step, step) if 0 <= r + step < world else (r, -step)
+        per_rank[r].append(i)
+        nr = r + step
+        if nr < 0 or nr >= world:
+            step = -step                             # snake: 0..w-1, w-1..0, ...
+        else:
+            r = nr
+    return [i for part in per_rank for i in part]
+
+
 def scatter_audio(audio: Optional[torch.Tensor], lens: Optional[torch.Tensor], n_items: int, n_samples: int,
                   device: torch.device, src: int = 0):
     """Rank ``src`` passes ``audio [N, n]`` (and optional ``lens [N]``); every rank returns its
@@ -80,10 +101,16 @@ def gather_tokens(tokens: torch.Tensor, ntok: torch.Tensor, n_items: int, dst: i
 
 
 def transcribe_sharded(engine, audio: Optional[torch.Tensor], lens: Optional[torch.Tensor], n_items: int, n_samples: int,
-                       max_iters: int = 3, transcribe_fn=None):
+                       max_iters: int = 3, transcribe_fn=None, balance: bool = False):
     """scatter -> per-rank ``engine.transcribe`` -> gather.  ``transcribe_fn(audio, lens, max_iters)``
-    may replace the engine call (used by the CPU tests of the plumbing)."""
+    may replace the engine call (used by the CPU tests of the plumbing).  ``balance`` (rank 0 decides, needs ``lens``):
+    deal the utterances by length (``balanced_order``) instead of contiguous blocks; results come back in input order."""
     device = engine.device if engine is not None else torch.device("cpu")
+    order = None
+    if balance and dist.get_rank() == 0 and lens is not None:
+        order = balanced_order(lens.tolist(), dist.get_world_size())
+        sel = torch.as_tensor(order, dtype=torch.long, device=audio.device)
+        audio, lens = audio.index_select(0, sel), lens.index_select(0, sel.to(lens.device))
     a, l = scatter_audio(audio, lens, n_items, n_samples, device)
     fn = transcribe_fn or (lambda x, ln, mi: engine.transcribe(x, ln, mi))
     if a.shape[0] > 0:
@@ -93,4 +120,10 @@ def transcribe_sharded(engine, audio: Optional[torch.Tensor], lens: Optional[tor
         U = max_iters * max(1, (n_samples // 160 + 1 - 10) // 8 + 1)
         tokens = torch.zeros(0, U, dtype=torch.int32, device=device)
         ntok = torch.zeros(0, dtype=torch.int32, device=device)
-    return gather_tokens(tokens, ntok, n_items)
+    out = gather_tokens(tokens, ntok, n_items)
+    if out is not None and order is not None:
+        restored = [None] * n_items
+        for pos, i in enumerate(order):
+            restored[i] = out[pos]
+        out = restored
+    return out

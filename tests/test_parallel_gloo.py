@@ -34,7 +34,7 @@ def _fake_transcribe(audio, lens, max_iters):
     return {"tokens": tokens, "ntok": ntok}
 
 
-def _worker(rank, world, port, n_items, with_lens, q):
+def _worker(rank, world, port, n_items, with_lens, q, balance=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -44,7 +44,7 @@ def _worker(rank, world, port, n_items, with_lens, q):
         if rank == 0:
             audio = torch.arange(n_items, dtype=torch.float32)[:, None].repeat(1, n) + 1.0
             lens = torch.tensor([n - (i % 5) for i in range(n_items)], dtype=torch.int32) if with_lens else None
-        out = parallel.transcribe_sharded(None, audio, lens, n_items, n, transcribe_fn=_fake_transcribe)
+        out = parallel.transcribe_sharded(None, audio, lens, n_items, n, transcribe_fn=_fake_transcribe, balance=balance)
         if rank == 0:
             want = _fake_transcribe(audio, lens, 3)
             exp = [want["tokens"][i, : int(want["ntok"][i])].tolist() for i in range(n_items)]
@@ -78,3 +78,38 @@ def test_shard_bounds_cover_and_balance():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_balanced_sharding_world2_returns_input_order():
+    """Length-balanced dealing permutes what each rank computes but not what the caller gets back."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 9, True, q, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [("none", True), ("ok", True)]
+
+
+def test_balanced_order_is_a_permutation_that_evens_out_lengths():
+    import random
+
+    rnd = random.Random(0)
+    for n, w in ((9, 2), (32, 4), (33, 8), (5, 8), (2048, 8)):
+        lens = [rnd.choice([160000, 240000]) - rnd.randrange(0, 20000) for _ in range(n)]
+        order = parallel.balanced_order(lens, w)
+        assert sorted(order) == list(range(n))
+        loads, sizes = [], []
+        for r in range(w):
+            lo, hi = parallel.shard_bounds(n, w, r)
+            loads.append(sum(lens[i] for i in order[lo:hi]))
+            sizes.append(hi - lo)
+        contiguous = [sum(lens[lo:hi]) for lo, hi in (parallel.shard_bounds(n, w, r) for r in range(w))]
+        if n >= 4 * w:   # with enough utterances per rank the dealt split is tighter than (or as tight as) contiguous blocks
+            full = [l for l, s in zip(loads, sizes) if s == max(sizes)]
+            assert max(full) - min(full) <= max(lens)
+            assert max(loads) <= max(contiguous) + max(lens) // 8
