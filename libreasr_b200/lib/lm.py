@@ -17,15 +17,20 @@ MIN_VAL = -10.0  # lm.py:15
 
 
 class LM(nn.Module):
+    """Parameter container with the reference's attribute names (they define the ``state_dict`` keys: ``embed.weight``,
+    ``rnn.weight_ih_l{k}`` ..., ``linear.weight`` / ``linear.bias``)."""
+
     def __init__(self, vocab_sz, embed_sz, hidden_sz, num_layers, p=0.2, **kwargs):
         super().__init__()
-        self.embed = nn.Embedding(vocab_sz, embed_sz, padding_idx=0)
-        self.rnn = nn.LSTM(embed_sz, hidden_sz, batch_first=True, num_layers=num_layers)
-        self.drop = nn.Dropout(p)
-        self.linear = nn.Linear(hidden_sz, vocab_sz)
-        if embed_sz == hidden_sz:
-            self.linear.weight = self.embed.weight  # tied (lm.py:27-29)
-        self.vocab_sz, self.embed_sz, self.hidden_sz, self.num_layers = vocab_sz, embed_sz, hidden_sz, num_layers
+        self.vocab_sz, self.embed_sz, self.hidden_sz, self.num_layers = int(vocab_sz), int(embed_sz), int(hidden_sz), int(num_layers)
+        shapes = dict(embed=nn.Embedding(self.vocab_sz, self.embed_sz, padding_idx=0),                  # blank row stays zero
+                      rnn=nn.LSTM(input_size=self.embed_sz, hidden_size=self.hidden_sz, num_layers=self.num_layers, batch_first=True),
+                      drop=nn.Dropout(p),                                                               # identity at inference
+                      linear=nn.Linear(self.hidden_sz, self.vocab_sz))
+        for name, mod in shapes.items():
+            setattr(self, name, mod)
+        if self.embed_sz == self.hidden_sz:   # weight tying (lm.py:27-29): one tensor under both keys
+            self.linear.weight = self.embed.weight
 
     def forward(self, x, state=None):
         raise NotImplementedError("the language model runs fused inside the CUDA decode loop (attach it with "
