@@ -94,9 +94,8 @@ def decode_audio(b: bytes):
     for fno, wt, v in _fields(b):
         if fno == 1 and wt == 2:
             data = bytes(v)
-        elif fno == 3 and wt == 0:
-            sr = v - (1 << 64) if v >> 63 else v
-            sr = int(np.int32(sr & 0xFFFFFFFF)) if sr >= 0 else int(sr)
+        elif fno == 3 and wt == 0:   # int32 on the wire: sign-extended to 64 bits, keep the low 32 as a signed value
+            sr = (v & 0xFFFFFFFF) - (1 << 32) if v & 0x80000000 else v & 0xFFFFFFFF
     return data, sr
 
 

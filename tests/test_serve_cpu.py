@@ -35,7 +35,7 @@ def _proto_classes():
     return mk(pool.FindMessageTypeByName("ASR.Audio")), mk(pool.FindMessageTypeByName("ASR.Transcript"))
 
 
-@pytest.mark.parametrize("n,sr", [(0, 0), (5, 16000), (1280, 16000), (40000, 44100), (3, 8000)])
+@pytest.mark.parametrize("n,sr", [(0, 0), (5, 16000), (1280, 16000), (40000, 44100), (3, 8000), (2, -1), (1, -2**31), (1, 2**31 - 1)])
 def test_audio_message_bytes_match_protobuf(n, sr):
     Audio, _ = _proto_classes()
     data = np.random.default_rng(n).standard_normal(n).astype("<f4").tobytes()
