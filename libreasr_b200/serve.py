@@ -18,7 +18,6 @@ import itertools as it
 import queue
 import struct
 import threading
-import time
 from concurrent import futures
 
 import numpy as np
@@ -169,6 +168,9 @@ class TranscriptDiffer:
 # ---------------------------------------------------------------------------------------------------------------
 # scheduler: connections <-> slots of one streaming session
 # ---------------------------------------------------------------------------------------------------------------
+_CLOSE = object()   # in-band end-of-stream marker of a connection's frame queue
+
+
 class StreamScheduler:
     """``session`` exposes ``B``, ``chunk``, ``push(chunks [B, chunk] float32 tensor, active=[B] bools) -> list of token lists
     | None`` and ``reset(slot)`` -- i.e. ``libreasr_b200.api.StreamBatch``.  All session calls happen on the thread that calls
@@ -215,6 +217,12 @@ class StreamScheduler:
         self._inq[slot].put(None)   # takes effect in order with the frames
         self._wake.set()
 
+    def close(self, slot):
+        """End of the client's stream: handled by the scheduler thread in order, i.e. after every frame fed before it has
+        been pushed and its tokens delivered; then the end-of-stream marker is queued and the slot is freed."""
+        self._inq[slot].put(_CLOSE)
+        self._wake.set()
+
     def results(self, slot):
         return self._outq[slot]
 
@@ -236,6 +244,7 @@ class StreamScheduler:
             live = list(self._live)
             fresh, self._fresh = self._fresh, [False] * self.B
         resets = [b for b in range(self.B) if live[b] and fresh[b]]
+        closing = []
         for b in range(self.B):
             if not live[b]:
                 continue
@@ -248,11 +257,16 @@ class StreamScheduler:
                     if b not in resets:
                         resets.append(b)
                     continue
+                if item is _CLOSE:                    # everything fed before it has been pushed in earlier ticks
+                    closing.append(b)
+                    break
                 self._buf[b].copy_(torch.from_numpy(item))
                 active[b] = True
                 break
+        for b in closing:
+            self.disconnect(b)
         if not resets and not any(active):
-            return False
+            return bool(closing)
         with self.lock:
             for b in resets:
                 self.session.reset(b)
@@ -327,14 +341,10 @@ class ASRServicer:
                     if sr and sr != self.asr.engine.cfg.sample_rate:
                         raise ValueError(f"streaming expects {self.asr.engine.cfg.sample_rate} Hz frames (got {sr}); resample at the client")
                     sch.feed(slot, tensorize(data)[0])
-                # drain: wait until the scheduler has consumed this stream's frames
-                while not sch._inq[slot].empty():
-                    time.sleep(0.001)
-                time.sleep(0.005)
+                sch.close(slot)            # in order: after the last frame's tokens have been delivered
             except Exception as e:  # noqa: BLE001 -- reported to the client below
                 err.append(e)
-            finally:
-                sch.disconnect(slot)
+                sch.disconnect(slot)       # abort: free the slot right away
 
         threading.Thread(target=reader, daemon=True).start()
         out = sch.results(slot)
