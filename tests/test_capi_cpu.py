@@ -97,3 +97,27 @@ def test_state_dict_keys_match_reference_contract():
     for k, v in m.state_dict().items():
         assert tuple(v.shape) == tuple(sd[k].shape), k
     m.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()}, strict=True)
+
+
+def test_engine_config_from_reference_style_conf():
+    """``EngineConfig.from_conf`` reads the keys of config/testing.yaml (values below are that file's: melkwargs :131-135,
+    StackDownsample :352-355, model :202-229, lm :293-299 and the `en` inference override :306-313)."""
+    from libreasr_b200.engine import EngineConfig
+
+    conf = {
+        "sr": 16000, "win_length": 0.025, "hop_length": 0.01, "melkwargs": {"n_fft": 1024, "n_mels": 128},
+        "transforms": {"x": [{"name": "TransformTime"}, {"name": "StackDownsample", "args": {"n_stack": 10, "downsample": 8}}]},
+        "model": {"feature_sz": 1280, "embed_sz": 512, "vocab_sz": 2048, "hidden_sz": 1024, "out_sz": 1024, "joint_sz": 1024,
+                  "encoder": {"num_layers": 6}, "predictor": {"num_layers": 2}, "joint": {"method": "concat"}},
+        "lm": {"enable": True, "vocab_sz": 2048, "embed_sz": 1024, "hidden_sz": 1024, "num_layers": 6, "p": 0.2},
+    }
+    ec = EngineConfig.from_conf(conf)
+    assert (ec.n_mels, ec.n_stack, ec.downsample, ec.win_length, ec.hop_length) == (128, 10, 8, 400, 160)
+    assert (ec.enc_layers, ec.pred_layers, ec.hidden_sz, ec.embed_sz, ec.joint_sz, ec.vocab_sz) == (6, 2, 1024, 512, 1024, 2048)
+    assert (ec.lm_layers, ec.lm_hidden_sz, ec.lm_embed_sz) == (6, 1024, 1024)
+    conf["lm"].update({"embed_sz": 768, "hidden_sz": 768, "num_layers": 4, "p": 0.3})      # overrides.en.lm
+    ec = EngineConfig.from_conf(conf)
+    assert (ec.lm_layers, ec.lm_hidden_sz, ec.lm_embed_sz) == (4, 768, 768)
+    conf["lm"]["enable"] = False
+    assert EngineConfig.from_conf(conf).lm_layers == 0
+    assert ec.feature_sz == conf["model"]["feature_sz"]
