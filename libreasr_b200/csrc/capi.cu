@@ -70,6 +70,8 @@ struct rnnt_b200_handle_s {
   std::vector<uint8_t*> Wih_img;       // TC modes: operand images of the interleaved W_ih
   std::vector<uint8_t*> Whh_img;       // TC modes: operand images (TR = NC) of the interleaved W_hh
   bool lstm_tc_ok = false;             // persistent tcgen05 LSTM layer usable for this H / SM count
+  std::vector<uint8_t*> Whh_img2;      // ... (TR = 128) for the cluster split-K kernel (lstm_tc2.cu)
+  bool lstm_tc2_ok = false;            // cluster split-K LSTM layer usable (H % 256 == 0, H <= 1024, clusters co-resident)
   bool dec_tc_ok = false;              // tcgen05 decode kernel usable
   uint8_t *W1p_img = nullptr, *W2_img = nullptr;
   uint8_t* R_img[kMaxPredLayers] = {nullptr, nullptr, nullptr, nullptr};
@@ -288,7 +290,7 @@ int32_t rnnt_b200_create(const rnnt_b200_config* cfg, rnnt_b200_handle* out) {
   h->cfg = *cfg;
   h->sm_count = prop.multiProcessorCount;
   if ((e = configure_lstm()) != cudaSuccess || (e = configure_gemm_tc()) != cudaSuccess || (e = configure_gemm_tc2()) != cudaSuccess ||
-      (e = configure_lstm_tc()) != cudaSuccess || (e = configure_decode_tc()) != cudaSuccess || (e = configure_decode(cfg->device, &h->coop_blocks)) != cudaSuccess) {
+      (e = configure_lstm_tc()) != cudaSuccess || (e = configure_lstm_tc2()) != cudaSuccess || (e = configure_decode_tc()) != cudaSuccess || (e = configure_decode(cfg->device, &h->coop_blocks)) != cudaSuccess) {
     delete h;
     return fail_cuda(nullptr, e, "kernel configuration");
   }
@@ -476,6 +478,15 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
         h->weight_allocs.push_back(wimg);
         h->Whh_img.push_back((uint8_t*)wimg);
         LAUNCH(1, launch_to_image(d_whh_r, H, 4 * H, H, pl.NC, (uint8_t*)wimg, st));
+      }
+      LstmTc2Plan pl2;
+      h->lstm_tc2_ok = lstm_tc2_plan(H, 1, h->sm_count, &pl2);
+      if (h->lstm_tc2_ok) {
+        void* wimg = nullptr;
+        CK(cudaMalloc(&wimg, img_bytes(4 * H, H, 128)));
+        h->weight_allocs.push_back(wimg);
+        h->Whh_img2.push_back((uint8_t*)wimg);
+        LAUNCH(1, launch_to_image(d_whh_r, H, 4 * H, H, 128, (uint8_t*)wimg, st));
       }
     }
   }
@@ -879,16 +890,65 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
     if (h->ev) cudaEventRecord(h->ev[6 + 2 * l], st);
     LstmTcPlan pl;
     const bool tc_rec = tc && h->lstm_tc_ok && B <= 128 && lstm_tc_plan(H, B, h->sm_count, &pl);
+    static const int lstm_v = [] { const char* e = getenv("RNNT_LSTM_V"); return e ? atoi(e) : 2; }();
+    LstmTc2Plan pl2;
+    const bool tc_rec2 = tc && lstm_v == 2 && h->lstm_tc2_ok && B <= 32 && lstm_tc2_plan(H, B, h->sm_count, &pl2);
     if (tc) {
       CK(h->a_img.ensure(gemm_tc_a_image_bytes(M, std::max(L.in, H))));
       // layer 0 reads the LayerNorm output; deeper layers find their operand image already written
       // by the previous layer's recurrent kernel (when that ran on the tensor-core path)
-      if (l == 0 || !tc_rec) LAUNCH(1, launch_to_image(A, L.in, M, L.in, 128, h->a_img.as<uint8_t>(), st));
+      if (l == 0 || !(tc_rec || tc_rec2)) LAUNCH(1, launch_to_image(A, L.in, M, L.in, 128, h->a_img.as<uint8_t>(), st));
       LAUNCH(1, launch_gemm_tc(h->a_img.as<uint8_t>(), h->Wih_img[l], L.bias_r, h->xp.as<float>(), 4 * H, M, 4 * H, L.in, st));
     } else {
       LAUNCH(1, launch_gemm_nt_f32(A, L.in, L.Wih_r, L.in, L.bias_r, h->xp.as<float>(), 4 * H, M, 4 * H, L.in, st));
     }
     if (h->ev) cudaEventRecord(h->ev[7 + 2 * l], st);
+    if (tc_rec2) {
+      // cluster split-K kernel (lstm_tc2.cu): 4x less operand ingest per step, tagged h exchange
+      const size_t ximg = (size_t)pl2.KB * 8192;
+      CK(h->x_img[0].ensure(img_bytes(128, H, 128)));
+      CK(h->x_img[1].ensure(img_bytes(128, H, 128)));
+      (void)ximg;
+      CK(h->gbar.ensure(1024));
+      CK(cudaMemsetAsync(h->gbar.p, 0, 4, st));
+      LstmTc2Args a;
+      memset(&a, 0, sizeof(a));
+      a.w_img = h->Whh_img2[l];
+      a.x_img[0] = h->x_img[0].as<uint8_t>(); a.x_img[1] = h->x_img[1].as<uint8_t>();
+      a.xp = h->xp.as<float>(); a.bn_scale = L.bn_scale; a.bn_shift = L.bn_shift;
+      a.y = y; a.y_img = (l == c.enc_layers - 1) ? nullptr : h->a_img.as<uint8_t>();
+      a.lens_T = lens_T; a.h_init_vec = L.h0; a.c_init_vec = L.c0;
+      a.state_h_in = use_state_in ? state_h + (size_t)l * B * H : nullptr;
+      a.state_c_in = use_state_in ? state_c + (size_t)l * B * H : nullptr;
+      a.state_h_out = state_h ? state_h + (size_t)l * B * H : nullptr;
+      a.state_c_out = state_c ? state_c + (size_t)l * B * H : nullptr;
+      a.barrier = h->gbar.as<unsigned int>();
+      a.T = T; a.B = B; a.H = H;
+      static const bool dbg_on2 = getenv("RNNT_LSTM_DBG") != nullptr;
+      unsigned long long* dbg = nullptr;
+      if (dbg_on2 && l == 0) {
+        CK(cudaMalloc((void**)&dbg, (size_t)T * 32));
+        CK(cudaMemset(dbg, 0, (size_t)T * 32));
+        a.dbg = dbg;
+      }
+      LAUNCH(1, launch_lstm_layer_tc2(a, pl2, st));
+      if (dbg) {
+        std::vector<unsigned long long> hb((size_t)T * 4);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(hb.data(), dbg, (size_t)T * 32, cudaMemcpyDeviceToHost));
+        cudaFree(dbg);
+        double ld = 0, mma = 0, red = 0, fin = 0;
+        for (int t = 1; t < T; ++t) {
+          ld += (double)(hb[t * 4 + 0] - hb[(t - 1) * 4 + 3]);   // previous publish -> K slice of h landed in smem
+          mma += (double)(hb[t * 4 + 1] - hb[t * 4 + 0]);        // -> accumulators ready
+          red += (double)(hb[t * 4 + 2] - hb[t * 4 + 1]);        // TMEM drain + DSMEM scatter + partial tiles complete
+          fin += (double)(hb[t * 4 + 3] - hb[t * 4 + 2]);        // cell + publish
+        }
+        fprintf(stderr, "[lstm_tc2 dbg] B=%d T=%d steps avg ns: publish->h landed %.0f | ->tmem_full %.0f | drain+reduce %.0f | cell+publish %.0f | total/step %.0f\n",
+                B, T, ld / (T - 1), mma / (T - 1), red / (T - 1), fin / (T - 1), (double)(hb[(T - 1) * 4 + 3] - hb[3]) / (T - 1));
+      }
+      continue;
+    }
     if (tc_rec) {
       const size_t ximg = img_bytes(128, H, 128);
       CK(h->x_img[0].ensure(ximg));

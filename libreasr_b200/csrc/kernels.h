@@ -87,6 +87,33 @@ cudaError_t configure_lstm_tc();
 bool lstm_tc_plan(int H, int B, int sms, LstmTcPlan* pl);
 cudaError_t launch_lstm_layer_tc(const LstmTcArgs& a, const LstmTcPlan& pl, cudaStream_t st);
 
+// ---------------- lstm_tc2.cu (persistent tcgen05 LSTM layer, cluster split-K over DSMEM) ----------------
+struct LstmTc2Plan {
+  int KS;          // k-blocks (64 k) of the K slice one CTA keeps resident (H / 256)
+  int KB;          // H / 64
+  int grid;        // H / 8 CTAs = H / 32 clusters of 4
+  int smem_bytes;
+};
+struct LstmTc2Args {
+  const uint8_t* w_img;      // operand image (TR = 128) of the interleaved W_hh [4H][H]
+  uint8_t* x_img[2];         // h images: [H/64][hi|lo][32 rows x 128 B], tagged 16-byte chunks (see lstm_tc2.cu)
+  const float* xp;           // [B*T][4H] hoisted input projection incl. biases, interleaved gate columns
+  const float* bn_scale; const float* bn_shift;
+  float* y;                  // [B*T][H] BatchNorm(h_t) fp32, or nullptr
+  uint8_t* y_img;            // operand image (TR = 128) of the same rows, or nullptr
+  const int32_t* lens_T;
+  const float* h_init_vec; const float* c_init_vec;
+  const float* state_h_in; const float* state_c_in;
+  float* state_h_out; float* state_c_out;
+  unsigned int* barrier;     // one launch-start counter, zero at launch
+  unsigned long long* dbg;   // optional [T][4] globaltimer stamps of CTA 0, or nullptr
+  int T, B, H;
+  int KS, KB;                // filled from the plan by the launcher
+};
+cudaError_t configure_lstm_tc2();
+bool lstm_tc2_plan(int H, int B, int sms, LstmTc2Plan* pl);
+cudaError_t launch_lstm_layer_tc2(const LstmTc2Args& a, const LstmTc2Plan& pl, cudaStream_t st);
+
 // ---------------- lstm.cu ----------------
 struct LstmStepArgs {
   const float* Whh_t;   // [H][4H] k-major, columns interleaved unit*4 + gate(i,f,g,o)

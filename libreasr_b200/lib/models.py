@@ -68,6 +68,8 @@ class Encoder(nn.Module):
         super().__init__()
         if hidden_sz != out_sz:
             raise NotImplementedError("hidden_sz != out_sz (extra Linear, models.py:97-98) is outside the built path")
+        if layer_norm:
+            raise NotImplementedError("layer_norm=True selects the Haste LayerNormLSTM (custom_rnn.py:30-36), outside the built path")
         self.num_layers = num_layers
         self.input_norm = nn.LayerNorm(feature_sz)
         self.rnn_stack = CustomRNNParams(feature_sz, hidden_sz, num_layers, rnn_type=rnn_type)
@@ -96,6 +98,8 @@ class Predictor(nn.Module):
         super().__init__()
         if hidden_sz != out_sz:
             raise NotImplementedError("hidden_sz != out_sz (extra Linear, models.py:173-174) is outside the built path")
+        if layer_norm:
+            raise NotImplementedError("layer_norm=True selects the Haste LayerNorm cell (custom_rnn.py:37-44), outside the built path")
         self.vocab_sz, self.num_layers = vocab_sz, num_layers
         self.embed = nn.Embedding(vocab_sz, embed_sz, padding_idx=blank)
         self.ffn = nn.Linear(embed_sz, hidden_sz) if embed_sz != hidden_sz else nn.Sequential()
@@ -181,7 +185,14 @@ class Transducer(nn.Module):
             p_j=conf["model"]["joint"].get("dropout", 0.0), joint_method=conf["model"]["joint"]["method"],
             encoder_kwargs=conf["model"]["encoder"], predictor_kwargs=conf["model"]["predictor"],
             n_stack=ecfg.n_stack, downsample=ecfg.downsample, gemm_mode=conf.get("gemm_mode", 1),
-        ).to(conf["cuda"]["device"])
+        )
+        # the front end (sr / window / hop / n_fft / n_mels) comes from the conf too, not from defaults
+        import dataclasses
+
+        if ecfg.feature_sz != conf["model"]["feature_sz"]:
+            raise ValueError(f'model.feature_sz {conf["model"]["feature_sz"]} != n_mels * n_stack = {ecfg.feature_sz}')
+        m._ecfg = dataclasses.replace(ecfg, gemm_mode=conf.get("gemm_mode", 1), blank=m.blank, bos=m.bos, lm_layers=0)
+        m = m.to(conf["cuda"]["device"])
         m.mp = conf.get("mp", False)
         return m
 
@@ -235,6 +246,22 @@ class Transducer(nn.Module):
         super().__setattr__(name, value)
         if name == "lm" and getattr(self, "_engine", None) is not None and value is not getattr(self, "_engine_lm", None):
             self._drop_engine()  # the engine bakes the LM in at finalize
+
+    def start_perf(self):
+        """models.py:278-280 (the device is synchronised so that the figure is the stage's time, not its launch)."""
+        if self.perf:
+            import time
+
+            torch.cuda.synchronize()
+            self.t = time.time()
+
+    def stop_perf(self, name="unknown"):
+        if self.perf:  # models.py:282-285
+            import time
+
+            torch.cuda.synchronize()
+            t = (time.time() - self.t) * 1000.0
+            print(f"{name.ljust(10, ' ')} | {t:4.2f}ms")
 
     def forward(self, tpl):
         raise NotImplementedError("training forward (models.py:308-359) is outside the built inference path")
@@ -291,8 +318,12 @@ class Transducer(nn.Module):
                 continue
             x = chunk.to(eng.device, torch.float32)
             x = x.reshape(1, x.size(0), -1)
+            self.start_perf()
             enc, st["enc"] = eng.encode(x, state=st["enc"], want_state=True)
+            self.stop_perf("encoder")  # models.py:516-524
+            self.start_perf()
             r = eng.decode_greedy(enc, max_iters=max_iters, state=st["pred"], want_state=True, lm_state=st["lm"])
+            self.stop_perf("joint + predictor")  # models.py:526-577
             st["pred"] = r["state"]
             y_seq = tokens_to_lists(r["tokens"], r["ntok"])[0]
             y = y + y_seq

@@ -288,12 +288,24 @@ def main():
         "cfg2_stream": lambda: stream_fixture("cfg2", n_chunks=50, audio_seed=47),
         "ref_offline": lambda: offline_fixture("ref", n_utt=1, n_samples=48000, audio_seed=25),
         "cfg4_offline": lambda: offline_fixture("cfg4", n_utt=1, n_samples=32000, audio_seed=26),
+        "cfg4_b8": lambda: offline_fixture("cfg4", n_utt=8, n_samples=160000, audio_seed=27),   # BASELINE configs[3] shape, >= 10 s
         "cfg1_demo": lambda: demo_fixture("ref"),
         "tiny_lm": lambda: lm_fixture("tiny", "tiny", n_utt=3, n_samples=40000, audio_seed=21, n_chunks=40, stream_seed=22),
         "tiny_lm_untied": lambda: lm_fixture("tiny", "tiny_untied", n_utt=2, n_samples=40000, audio_seed=31, n_chunks=30, stream_seed=32),
         "cfg2_lm": lambda: lm_fixture("cfg2", "en", n_utt=2, n_samples=80000, audio_seed=105, n_chunks=50, stream_seed=47),
     }
     only = sys.argv[1:]
+    if not only or "testing_conf" in only:
+        # the reference's shipped configuration (config/testing.yaml), verbatim as JSON: the GPU box has no reference tree
+        import json
+
+        import yaml
+
+        with open(os.path.join(ref_shim.REFERENCE_ROOT, "config", "testing.yaml")) as f:
+            conf = yaml.safe_load(f)
+        with open(os.path.join(GOLDEN_DIR, "testing_conf.json"), "w") as f:
+            json.dump(conf, f, indent=1, sort_keys=True)
+        print("wrote testing_conf.json")
     for k, fn in jobs.items():
         if only and k not in only:
             continue
