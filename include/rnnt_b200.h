@@ -270,6 +270,12 @@ int32_t rnnt_b200_stream_push(rnnt_b200_stream s, const float* chunks, int32_t c
                               int32_t* tokens_host_out, int32_t U_cap, int32_t* ntok_host_out,
                               int32_t* advanced_out, void* stream);
 int32_t rnnt_b200_stream_reset(rnnt_b200_stream s, int32_t slot);
+/* Mid-stream reset = the `reset_fn` that Transducer.transcribe_stream yields (libreasr/lib/models.py:480-500), called by
+ * the server's silence logic (api-server.py:133-135): encoder state -> learnable initial state, predictor -> BOS
+ * state, LM fuser cleared.  The 3-chunk audio window and the Buffer of the serving loop (api-server.py:83-115,
+ * transforms.py:455-471) are NOT touched (rnnt_b200_stream_reset above = new connection clears them too).
+ * slot = -1: every stream. */
+int32_t rnnt_b200_stream_reset_state(rnnt_b200_stream s, int32_t slot);
 int32_t rnnt_b200_stream_close(rnnt_b200_stream s);
 
 /* ---- self test -------------------------------------------------------------------------------- */

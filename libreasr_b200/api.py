@@ -105,6 +105,12 @@ class StreamBatch:
         for b in (range(self.B) if slot is None else [int(slot)]):
             self.tokens[b] = []
 
+    def reset_state(self, slot=None):
+        """Mid-stream reset = the ``reset_fn`` of ``transcribe_stream`` (models.py:480-500; the server calls it on
+        silence, api-server.py:133-135): encoder / predictor / LM-fuser state only -- the audio window and the Buffer
+        of the serving loop keep their contents (unlike ``reset``, which is a new connection)."""
+        self.engine._ck(self.engine.lib.rnnt_b200_stream_reset_state(self._s, -1 if slot is None else int(slot)))
+
     def push(self, chunks, active=None):
         """chunks [B, chunk] float32, CUDA or (ideally pinned) CPU tensor; ``active``: optional [B] booleans, streams with
         False are skipped this tick.  Returns the list of new token lists (empty for streams that did not run) when at

@@ -1389,13 +1389,16 @@ struct rnnt_b200_stream_s {
 };
 
 namespace {
-// stream `slot` back to the state of a fresh connection
-int stream_reset_slot_impl(rnnt_b200_stream s, int slot, cudaStream_t st) {
+// stream `slot` back to the state of a fresh connection; keep_audio: only what the reference's reset_fn resets
+// (encoder state, predictor -> BOS, LM fuser; models.py:480-500) -- the 3-chunk audio window and the Buffer live in the
+// serving loop (api-server.py:83-115, transforms.py:455-471) and survive it
+int stream_reset_slot_impl(rnnt_b200_stream s, int slot, cudaStream_t st, bool keep_audio = false) {
   rnnt_b200_handle h = s->h;
   const rnnt_b200_config& c = h->cfg;
   const size_t H = c.hidden_sz, W = (size_t)s->n_window * s->chunk;
   const int B = s->B;
-  for (int i = 0; i < 2; ++i) CK(cudaMemsetAsync(s->win[i].as<float>() + (size_t)slot * W, 0, W * 4, st));
+  if (!keep_audio)
+    for (int i = 0; i < 2; ++i) CK(cudaMemsetAsync(s->win[i].as<float>() + (size_t)slot * W, 0, W * 4, st));
   for (int l = 0; l < c.enc_layers; ++l) {   // state None -> the learnable hs[i] (custom_rnn.py:152-158)
     CK(cudaMemcpyAsync(s->enc_h.as<float>() + ((size_t)l * B + slot) * H, h->enc[l].h0, H * 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(s->enc_c.as<float>() + ((size_t)l * B + slot) * H, h->enc[l].c0, H * 4, cudaMemcpyDeviceToDevice, st));
@@ -1409,8 +1412,10 @@ int stream_reset_slot_impl(rnnt_b200_stream s, int slot, cudaStream_t st) {
     const size_t rows = lm_state_floats(c.lm_layers, c.lm_hidden_sz, c.vocab_sz, Bp) / Bp;
     CK(cudaMemset2DAsync(s->lm.as<float>() + slot, (size_t)Bp * 4, 0, 4, rows, st));
   }
-  s->n_chunks[slot] = 0;
-  s->n_rows[slot] = 0;
+  if (!keep_audio) {
+    s->n_chunks[slot] = 0;
+    s->n_rows[slot] = 0;
+  }
   return RNNT_B200_OK;
 }
 }  // namespace
@@ -1466,17 +1471,19 @@ int32_t rnnt_b200_stream_open(rnnt_b200_handle h, int32_t B, int32_t chunk, int3
   return RNNT_B200_OK;
 }
 
-int32_t rnnt_b200_stream_reset(rnnt_b200_stream s, int32_t slot) {
+static int32_t stream_reset_common(rnnt_b200_stream s, int32_t slot, bool keep_audio) {
   if (!s) return RNNT_B200_ERR_INVALID;
   rnnt_b200_handle h = s->h;
   if (slot < -1 || slot >= s->B) return fail(h, RNNT_B200_ERR_INVALID, "stream_reset: slot out of range (-1 = all streams)");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
   for (int b = (slot < 0 ? 0 : slot); b < (slot < 0 ? s->B : slot + 1); ++b)
-    if (int r = stream_reset_slot_impl(s, b, nullptr)) return r;
+    if (int r = stream_reset_slot_impl(s, b, nullptr, keep_audio)) return r;
   CK(cudaStreamSynchronize(nullptr));
   return RNNT_B200_OK;
 }
+int32_t rnnt_b200_stream_reset(rnnt_b200_stream s, int32_t slot) { return stream_reset_common(s, slot, false); }
+int32_t rnnt_b200_stream_reset_state(rnnt_b200_stream s, int32_t slot) { return stream_reset_common(s, slot, true); }
 
 int32_t rnnt_b200_stream_close(rnnt_b200_stream s) {
   if (!s) return RNNT_B200_OK;

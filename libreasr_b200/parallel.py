@@ -100,19 +100,75 @@ def gather_tokens(tokens: torch.Tensor, ntok: torch.Tensor, n_items: int, dst: i
     return out
 
 
+def scatter_audio_blocks(audio: Optional[torch.Tensor], n_items: int, n_samples: int, device: torch.device, block: int, src: int = 0):
+    """Block-pipelined scatter: every rank's shard travels as blocks of ``block`` utterances, dealt round-robin over the
+    ranks (block 0 of every rank first), so that each rank can start on its first block while the rest is still in flight
+    (the NCCL send/recv kernels run on NCCL's own stream, next to the compute stream).  Returns the list of
+    (local buffer slice, request | None) in order; ``request.wait()`` before using a slice."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    lo, hi = shard_bounds(n_items, world, rank)
+    local = torch.empty(hi - lo, n_samples, dtype=torch.float32, device=device)
+    parts = []
+    if rank == src:
+        reqs = []
+        k = 0
+        while True:
+            any_left = False
+            for r in range(world):
+                a, b = shard_bounds(n_items, world, r)
+                s0, s1 = a + k * block, min(b, a + (k + 1) * block)
+                if s0 >= s1:
+                    continue
+                any_left = True
+                if r == src:
+                    local[s0 - a:s1 - a].copy_(audio[s0:s1])
+                else:
+                    reqs.append(dist.isend(audio[s0:s1], dst=r))
+            if not any_left:
+                break
+            k += 1
+        for b0 in range(0, hi - lo, block):
+            parts.append((local[b0:min(hi - lo, b0 + block)], None))
+        return parts, reqs
+    for b0 in range(0, hi - lo, block):
+        sl = local[b0:min(hi - lo, b0 + block)]
+        parts.append((sl, dist.irecv(sl, src=src)))
+    return parts, []
+
+
 def transcribe_sharded(engine, audio: Optional[torch.Tensor], lens: Optional[torch.Tensor], n_items: int, n_samples: int,
-                       max_iters: int = 3, transcribe_fn=None, balance: bool = False):
+                       max_iters: int = 3, transcribe_fn=None, balance: bool = False, block: int = 0):
     """scatter -> per-rank ``engine.transcribe`` -> gather.  ``transcribe_fn(audio, lens, max_iters)``
     may replace the engine call (used by the CPU tests of the plumbing).  ``balance`` (rank 0 decides, needs ``lens``):
-    deal the utterances by length (``balanced_order``) instead of contiguous blocks; results come back in input order."""
+    deal the utterances by length (``balanced_order``) instead of contiguous blocks; results come back in input order.
+    ``block`` > 0 (no ``lens``): block-pipelined scatter (``scatter_audio_blocks``), each block is transcribed as soon as it
+    has arrived, overlapping the rest of the scatter with compute."""
     device = engine.device if engine is not None else torch.device("cpu")
+    fn = transcribe_fn or (lambda x, ln, mi: engine.transcribe(x, ln, mi))
     order = None
+    if block > 0 and lens is None and not balance:
+        parts, reqs = scatter_audio_blocks(audio.to(device) if audio is not None else None, n_items, n_samples, device, block)
+        toks, nts = [], []
+        for sl, rq in parts:
+            if rq is not None:
+                rq.wait()
+            r = fn(sl, None, max_iters)
+            toks.append(r["tokens"])
+            nts.append(r["ntok"])
+        for q in reqs:
+            q.wait()
+        if toks:
+            tokens, ntok = torch.cat(toks, 0), torch.cat(nts, 0)
+        else:
+            U = max_iters * max(1, (n_samples // 160 + 1 - 10) // 8 + 1)
+            tokens = torch.zeros(0, U, dtype=torch.int32, device=device)
+            ntok = torch.zeros(0, dtype=torch.int32, device=device)
+        return gather_tokens(tokens, ntok, n_items)
     if balance and dist.get_rank() == 0 and lens is not None:
         order = balanced_order(lens.tolist(), dist.get_world_size())
         sel = torch.as_tensor(order, dtype=torch.long, device=audio.device)
         audio, lens = audio.index_select(0, sel), lens.index_select(0, sel.to(lens.device))
     a, l = scatter_audio(audio, lens, n_items, n_samples, device)
-    fn = transcribe_fn or (lambda x, ln, mi: engine.transcribe(x, ln, mi))
     if a.shape[0] > 0:
         r = fn(a, l, max_iters)
         tokens, ntok = r["tokens"], r["ntok"]

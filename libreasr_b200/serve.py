@@ -243,7 +243,8 @@ class StreamScheduler:
         with self._mu:
             live = list(self._live)
             fresh, self._fresh = self._fresh, [False] * self.B
-        resets = [b for b in range(self.B) if live[b] and fresh[b]]
+        resets = [b for b in range(self.B) if live[b] and fresh[b]]   # new connections: full reset (window, Buffer, state)
+        state_resets = []                                              # reset_fn requests: model state only (models.py:480-500)
         closing = []
         for b in range(self.B):
             if not live[b]:
@@ -254,8 +255,8 @@ class StreamScheduler:
                 except queue.Empty:
                     break
                 if item is None:                      # reset request from the transcript logic
-                    if b not in resets:
-                        resets.append(b)
+                    if b not in resets and b not in state_resets:
+                        state_resets.append(b)
                     continue
                 if item is _CLOSE:                    # everything fed before it has been pushed in earlier ticks
                     closing.append(b)
@@ -265,11 +266,13 @@ class StreamScheduler:
                 break
         for b in closing:
             self.disconnect(b)
-        if not resets and not any(active):
+        if not resets and not state_resets and not any(active):
             return bool(closing)
         with self.lock:
             for b in resets:
                 self.session.reset(b)
+            for b in state_resets:
+                getattr(self.session, "reset_state", self.session.reset)(b)
             new = self.session.push(self._buf, active=active) if any(active) else None
         self.ticks += 1
         if new is not None:

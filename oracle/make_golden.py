@@ -124,8 +124,9 @@ def offline_fixture(name, n_utt, n_samples, audio_seed, full=False, enc_stride=8
     return out
 
 
-def stream_fixture(name, n_chunks, audio_seed, lead_zero_chunks=1):
-    """api-client.py:32-47 sends one leading zero chunk, then the audio in 80 ms chunks."""
+def stream_fixture(name, n_chunks, audio_seed, lead_zero_chunks=1, reset_after=()):
+    """api-client.py:32-47 sends one leading zero chunk, then the audio in 80 ms chunks.  ``reset_after``: yield indices
+    after which the consumer calls the yielded reset_fn, as the server's silence logic does (api-server.py:133-135)."""
     cfg = weights.CONFIGS[name]
     ref = build_reference(cfg)
     audio = weights.make_audio(1, n_chunks * CHUNK, audio_seed)[0]
@@ -134,8 +135,13 @@ def stream_fixture(name, n_chunks, audio_seed, lead_zero_chunks=1):
     rows = [c for c in ref_stream_chunks(a, cfg)]
     feats = [c[..., 0].numpy() for c in rows if c is not None]
     with torch.no_grad():
-        yields = [(list(y), list(ys)) for (y, ys, _reset) in ref.transcribe_stream(iter(rows), lambda t: list(t), max_iters=10)]
+        yields = []
+        for i, (y, ys, reset_fn) in enumerate(ref.transcribe_stream(iter(rows), lambda t: list(t), max_iters=10)):
+            yields.append((list(y), list(ys)))
+            if i in reset_after:
+                reset_fn()
     out = {
+        "reset_after": np.asarray(sorted(reset_after), dtype=np.int32),
         "config": name, "weight_seed": WEIGHT_SEED, "audio_seed": audio_seed, "n_chunks": n_chunks,
         "lead_zero_chunks": lead_zero_chunks, "max_iters": 10,
         "n_yields": len(yields),
@@ -283,6 +289,7 @@ def main():
     jobs = {
         "tiny_offline": lambda: offline_fixture("tiny", n_utt=3, n_samples=40000, audio_seed=21, full=True),
         "tiny_stream": lambda: stream_fixture("tiny", n_chunks=40, audio_seed=22),
+        "tiny_stream_reset": lambda: stream_fixture("tiny", n_chunks=44, audio_seed=23, reset_after=(4, 11)),
         "tiny_modules": lambda: modules_fixture("tiny"),
         "cfg2_offline": lambda: offline_fixture("cfg2", n_utt=2, n_samples=80000, audio_seed=105),
         "cfg2_stream": lambda: stream_fixture("cfg2", n_chunks=50, audio_seed=47),

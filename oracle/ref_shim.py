@@ -16,7 +16,19 @@ import types
 
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("LIBREASR_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference_root():
+    """The authoring container has the tree at /root/reference; the GPU box only has the offline install of the same
+    unmodified package under baseline/_ref (git-ignored, travels with the snapshot; recipe in DESIGN.md section 2)."""
+    for cand in (os.environ.get("LIBREASR_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "libreasr", "lib", "models.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:

@@ -363,13 +363,16 @@ class OracleTransducer:
                 res["logp"] = torch.stack(outs)
             return res
 
-    def transcribe_stream(self, stream, max_iters: int = 10, impl: str = "explicit", lm=None):
+    def transcribe_stream(self, stream, max_iters: int = 10, impl: str = "explicit", lm=None, reset_after=()):
         """``Transducer.transcribe_stream`` (models.py:457-577; LM fusion at :558,569): generator over
-        chunks ([T_c, X] or None) yielding (all tokens so far, this chunk's tokens)."""
+        chunks ([T_c, X] or None) yielding (all tokens so far, this chunk's tokens).  ``reset_after``: yield indices
+        after which the consumer calls the yielded ``reset_fn`` (models.py:480-500: encoder state -> None,
+        predictor -> BOS, fuser reset; ``y`` keeps accumulating)."""
         with torch.no_grad():
             enc_state = None
             h_pred, pstate = self.predictor(torch.tensor([self.bos]))
             y = []
+            n_yield = 0
             if lm is not None:
                 lm.reset()
             for chunk in stream:
@@ -394,6 +397,12 @@ class OracleTransducer:
                             lm.advance(pred)
                 y = y + y_seq
                 yield list(y), list(y_seq)
+                if n_yield in reset_after:   # reset() of models.py:494-497, called by the consumer between two chunks
+                    enc_state = None
+                    h_pred, pstate = self.predictor(torch.tensor([self.bos]))
+                    if lm is not None:
+                        lm.reset()
+                n_yield += 1
 
 
 def transcribe_batch(model: OracleTransducer, audio: np.ndarray, max_iters: int = 3, impl: str = "aten", lm=None):

@@ -120,3 +120,35 @@ def test_from_config_with_the_reference_testing_yaml():
     with pytest.raises(ValueError):
         Transducer.from_config(bad, Lang())
     m._drop_engine()
+
+
+def test_stream_session_mid_stream_state_reset_matches_reference_fixture():
+    """ADVICE r1 (serve.py:216): the silence reset of the serving loop is the yielded reset_fn (models.py:480-500) --
+    model state only; window and Buffer persist.  Fixture `tiny_stream_reset`: the imported reference's
+    transcribe_stream with reset_fn called after yields 4 and 11.  The C session with rnnt_b200_stream_reset_state at
+    the same points gives the same per-yield token counts and the same transcript; a second stream of the same session
+    that is never reset is unaffected."""
+    from libreasr_b200.api import StreamBatch
+
+    g = load_golden("tiny_stream_reset")
+    cfg, sd, m, orc = model_for("tiny")
+    n_chunks = int(g["n_chunks"])
+    a = weights.make_audio(1, n_chunks * CHUNK, int(g["audio_seed"]))[0]
+    a[: int(g["lead_zero_chunks"]) * CHUNK] = 0.0
+    audio = np.stack([a, a])
+    reset_after = set(g["reset_after"].tolist())
+    sb = StreamBatch(m.engine(), 2, max_iters=10)
+    yields, other, n_yield = [], [], 0
+    for j in range(n_chunks):
+        new = sb.push(torch.from_numpy(np.ascontiguousarray(audio[:, j * CHUNK:(j + 1) * CHUNK])))
+        if new is not None:
+            yields.append(list(new[0]))
+            other.append(list(new[1]))
+            if n_yield in reset_after:
+                sb.reset_state(0)
+            n_yield += 1
+    sb.close()
+    assert [len(y) for y in yields] == g["chunk_counts"].tolist()
+    assert [t for y in yields for t in y] == g["tokens_all"].tolist()
+    assert other == _oracle_stream_tokens(orc, cfg, a, n_chunks)       # stream 1: no reset
+    assert other != yields

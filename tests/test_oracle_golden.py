@@ -41,7 +41,7 @@ def test_offline_greedy_matches_reference(name, impl):
             np.testing.assert_allclose(r["logp"][:n].numpy(), g[f"logp_first_{b}"], atol=5e-4)
 
 
-@pytest.mark.parametrize("name", ["tiny_stream", "cfg2_stream"])
+@pytest.mark.parametrize("name", ["tiny_stream", "cfg2_stream", "tiny_stream_reset"])
 def test_stream_matches_reference(name):
     g = load_golden(name)
     cfg, orc = _model(g)
@@ -53,7 +53,9 @@ def test_stream_matches_reference(name):
     feats = np.stack([r.numpy() for r in rows if r is not None])
     ref_feats = g["feats"]
     np.testing.assert_allclose(feats if name.startswith("tiny") else feats[:, :, ::7], ref_feats, atol=2e-5)
-    yields = list(orc.transcribe_stream(iter(rows), max_iters=int(g["max_iters"])))
+    # tiny_stream_reset: the consumer called the yielded reset_fn after these yields (api-server.py:133-135)
+    reset_after = set(g["reset_after"].tolist()) if "reset_after" in g else ()
+    yields = list(orc.transcribe_stream(iter(rows), max_iters=int(g["max_iters"]), reset_after=reset_after))
     assert len(yields) == int(g["n_yields"])
     assert [len(ys) for _, ys in yields] == g["chunk_counts"].tolist()
     assert yields[-1][0] == g["tokens_all"].tolist()

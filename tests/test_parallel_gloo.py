@@ -34,7 +34,7 @@ def _fake_transcribe(audio, lens, max_iters):
     return {"tokens": tokens, "ntok": ntok}
 
 
-def _worker(rank, world, port, n_items, with_lens, q, balance=False):
+def _worker(rank, world, port, n_items, with_lens, q, balance=False, block=0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -44,7 +44,7 @@ def _worker(rank, world, port, n_items, with_lens, q, balance=False):
         if rank == 0:
             audio = torch.arange(n_items, dtype=torch.float32)[:, None].repeat(1, n) + 1.0
             lens = torch.tensor([n - (i % 5) for i in range(n_items)], dtype=torch.int32) if with_lens else None
-        out = parallel.transcribe_sharded(None, audio, lens, n_items, n, transcribe_fn=_fake_transcribe, balance=balance)
+        out = parallel.transcribe_sharded(None, audio, lens, n_items, n, transcribe_fn=_fake_transcribe, balance=balance, block=block)
         if rank == 0:
             want = _fake_transcribe(audio, lens, 3)
             exp = [want["tokens"][i, : int(want["ntok"][i])].tolist() for i in range(n_items)]
@@ -61,6 +61,23 @@ def test_scatter_gather_world2(n_items, with_lens):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_items, with_lens, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [("none", True), ("ok", True)]
+
+
+@pytest.mark.parametrize("n_items,block", [(11, 2), (8, 4), (3, 64), (1, 2)])
+def test_block_pipelined_scatter_world2(n_items, block):
+    """The block-pipelined scatter (bench.py strong-scaling leg): blocks of `block` utterances dealt round-robin over the
+    ranks, each transcribed on arrival; the caller still gets every utterance back in global order."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_items, False, q, False, block)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(2)]
