@@ -74,6 +74,9 @@ struct rnnt_b200_handle_s {
   bool lstm_tc2_ok = false;            // cluster split-K LSTM layer usable (H % 256 == 0, H <= 1024, clusters co-resident)
   bool dec_tc_ok = false;              // tcgen05 decode kernel usable
   uint8_t *W1p_img = nullptr, *W2_img = nullptr;
+  // decode_tc2.cu (cluster split-K decode): row tiles of one cluster, TR = 32 / V/32 / 96
+  uint8_t *W1p_img2 = nullptr, *W2_img2 = nullptr, *K1_img2 = nullptr, *R_img2[2] = {nullptr, nullptr};
+  bool dec_tc2_ok = false;
   uint8_t* R_img[kMaxPredLayers] = {nullptr, nullptr, nullptr, nullptr};
   uint8_t* K_img[kMaxPredLayers] = {nullptr, nullptr, nullptr, nullptr};
   DevBuf dimg;                         // decode activation operand images
@@ -290,7 +293,7 @@ int32_t rnnt_b200_create(const rnnt_b200_config* cfg, rnnt_b200_handle* out) {
   h->cfg = *cfg;
   h->sm_count = prop.multiProcessorCount;
   if ((e = configure_lstm()) != cudaSuccess || (e = configure_gemm_tc()) != cudaSuccess || (e = configure_gemm_tc2()) != cudaSuccess ||
-      (e = configure_lstm_tc()) != cudaSuccess || (e = configure_lstm_tc2()) != cudaSuccess || (e = configure_decode_tc()) != cudaSuccess || (e = configure_decode(cfg->device, &h->coop_blocks)) != cudaSuccess) {
+      (e = configure_lstm_tc()) != cudaSuccess || (e = configure_lstm_tc2()) != cudaSuccess || (e = configure_decode_tc()) != cudaSuccess || (e = configure_decode_tc2()) != cudaSuccess || (e = configure_decode(cfg->device, &h->coop_blocks)) != cudaSuccess) {
     delete h;
     return fail_cuda(nullptr, e, "kernel configuration");
   }
@@ -527,6 +530,14 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
       h->R_img[l] = (uint8_t*)img;
       LAUNCH(1, launch_to_image(d_t2, H, 3 * H, H, dpl.NC_C, (uint8_t*)img, st));   // d_t2: [3H interleaved][H]
     }
+    h->dec_tc2_ok = c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && decode_tc2_plan(H, J, V, c.pred_layers, 1, h->sm_count, c.lm_layers);
+    if (h->dec_tc2_ok && l < 2) {
+      void* img = nullptr;
+      CK(cudaMalloc(&img, img_bytes(3 * H, H, 96)));
+      h->weight_allocs.push_back(img);
+      h->R_img2[l] = (uint8_t*)img;
+      LAUNCH(1, launch_to_image(d_t2, H, 3 * H, H, 96, (uint8_t*)img, st));
+    }
     float* d_k;
     CK(tmp_upload(*kern, &d_k));
     if (l == 0) {
@@ -568,6 +579,13 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
         h->K_img[l] = (uint8_t*)img;
         LAUNCH(1, launch_to_image(d_b, H, 3 * H, H, dpl.NC_C, (uint8_t*)img, st));   // d_b: [3H interleaved][H]
       }
+      if (h->dec_tc2_ok && l == 1) {
+        void* img = nullptr;
+        CK(cudaMalloc(&img, img_bytes(3 * H, H, 96)));
+        h->weight_allocs.push_back(img);
+        h->K1_img2 = (uint8_t*)img;
+        LAUNCH(1, launch_to_image(d_b, H, 3 * H, H, 96, (uint8_t*)img, st));
+      }
       CK(upload(h, interleave(*kb, 3), &t_kb));
       dw.Kt[l] = Kt; dw.kbias[l] = t_kb;
     }
@@ -608,6 +626,17 @@ int32_t rnnt_b200_finalize(rnnt_b200_handle h, void* stream) {
         h->W2_img = (uint8_t*)ib;
         LAUNCH(1, launch_to_image(h->W1, 2 * H, J, H, dpl.NC_A, h->W1p_img, st));   // pred half: first H columns
         LAUNCH(1, launch_to_image(d_w2, J, V, J, dpl.NC_B, h->W2_img, st));
+      }
+      if (h->dec_tc2_ok) {
+        void *ia = nullptr, *ib = nullptr;
+        CK(cudaMalloc(&ia, img_bytes(J, H, 32)));
+        CK(cudaMalloc(&ib, img_bytes(V, J, V / 32)));
+        h->weight_allocs.push_back(ia);
+        h->weight_allocs.push_back(ib);
+        h->W1p_img2 = (uint8_t*)ia;
+        h->W2_img2 = (uint8_t*)ib;
+        LAUNCH(1, launch_to_image(h->W1, 2 * H, J, H, 32, h->W1p_img2, st));
+        LAUNCH(1, launch_to_image(d_w2, J, V, J, V / 32, h->W2_img2, st));
       }
     }
   }
@@ -868,10 +897,13 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
   if ((state_h == nullptr) != (state_c == nullptr)) return fail(h, RNNT_B200_ERR_INVALID, "encode: state_h and state_c must both be given");
   cudaStream_t st = (cudaStream_t)stream;
   const int H = c.hidden_sz, X = c.n_mels * c.n_stack, Bp = bp_of(B);
-  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->lstm_tc_ok && B > 128 && !state_h) {
-    // independent utterances: stateless batches beyond the persistent LSTM kernel's capacity run as sub-batches of 128
-    for (int b0 = 0; b0 < B; b0 += 128) {
-      const int nb = std::min(128, B - b0);
+  static const int sub32 = [] { const char* e = getenv("RNNT_SUB32"); return e ? atoi(e) : 0; }();
+  static const int lstm_v0 = [] { const char* e = getenv("RNNT_LSTM_V"); return e ? atoi(e) : 2; }();
+  const int enc_cap = (sub32 && lstm_v0 == 2 && h->lstm_tc2_ok) ? 32 : 128;   // the cluster split-K kernel takes 32 rows per launch
+  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->lstm_tc_ok && B > enc_cap && !state_h) {
+    // independent utterances: stateless batches beyond the persistent LSTM kernel's capacity run as sub-batches
+    for (int b0 = 0; b0 < B; b0 += enc_cap) {
+      const int nb = std::min(enc_cap, B - b0);
       const int r = rnnt_b200_encode(h, feats + (size_t)b0 * T * X, lens_T ? lens_T + b0 : nullptr, nb, T, nullptr, nullptr, 0,
                                      enc_out + (size_t)b0 * T * H, stream);
       if (r) return r;
@@ -1085,6 +1117,9 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
           !decode_tc_plan(c.hidden_sz, c.joint_sz, c.vocab_sz, c.pred_layers, std::min(B, 64), h->sm_count, &probe, c.lm_layers, c.lm_hidden_sz) &&
           decode_tc_plan(c.hidden_sz, c.joint_sz, c.vocab_sz, c.pred_layers, 32, h->sm_count, &probe, c.lm_layers, c.lm_hidden_sz))
         cap = 32;
+      static const int sub32d = [] { const char* e = getenv("RNNT_SUB32"); return e ? atoi(e) : 0; }();
+      static const int dec_v0 = [] { const char* e = getenv("RNNT_DEC_V"); return e ? atoi(e) : 2; }();
+      if (sub32d && dec_v0 == 2 && h->dec_tc2_ok && !h->lm_blob) cap = 32;   // the cluster split-K decode kernel takes 32 utterances
     }
     const bool stateful = pred_state_h || pred_out || use_state_in || h->lm_blob;
     if (stateful && B > kDecodeMaxBatch)
@@ -1118,6 +1153,65 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     LAUNCH(1, launch_gemm_nt_f32(enc, H, h->W1 + H, 2 * H, h->dw.b1, h->ep.as<float>(), J, M, J, H, st));
   }
   if (h->ev) cudaEventRecord(h->ev[3], st);
+  static const int dec_v = [] { const char* e = getenv("RNNT_DEC_V"); return e ? atoi(e) : 2; }();
+  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && dec_v == 2 && h->dec_tc2_ok && !h->lm_blob &&
+      decode_tc2_plan(H, J, c.vocab_sz, c.pred_layers, B, h->sm_count, c.lm_layers)) {
+    // cluster split-K decode (decode_tc2.cu): up to 32 utterances per launch
+    const size_t one = decode_tc2_image_bytes();
+    CK(h->dimg.ensure(one * 10));
+    const int max_steps = max_iters * T + 2;
+    const int nBp = decode_tc2_part_ctas();
+    CK(h->dpart.ensure((size_t)max_steps * nBp * 32 * 8));
+    CK(h->dkeys.ensure(decode_tc2_keys_bytes() + (size_t)B * 4 + 64));
+    CK(h->dlse.ensure(std::max<size_t>((size_t)B * (trace_logp ? trace_cap : 1), 1) * 4));
+    CK(h->gbar.ensure(1024));
+    CK(cudaMemsetAsync(h->gbar.p, 0, 4, st));
+    if (trace_logp) {
+      CK(cudaMemsetAsync(h->dlse.p, 0, (size_t)B * trace_cap * 4, st));
+      CK(cudaMemsetAsync(trace_logp, 0, (size_t)B * trace_cap * c.vocab_sz * 4, st));
+    }
+    if (iters_out) CK(cudaMemsetAsync(iters_out, 0, (size_t)B * T, st));
+    DecodeTc2Args t;
+    memset(&t, 0, sizeof(t));
+    t.w = h->dw;
+    t.w1p_img = h->W1p_img2; t.w2_img = h->W2_img2; t.k1_img = h->K1_img2; t.r_img[0] = h->R_img2[0]; t.r_img[1] = h->R_img2[1];
+    for (int i = 0; i < 5; ++i) t.img[i] = h->dimg.as<uint8_t>() + (size_t)(2 * i) * one;
+    t.img_stride = one;
+    t.keys = h->dkeys.as<unsigned long long>();
+    t.n_eval = reinterpret_cast<int*>(h->dkeys.as<uint8_t>() + decode_tc2_keys_bytes());
+    t.ep = h->ep.as<float>(); t.lens_T = lens_T; t.B = B; t.T = T; t.max_iters = max_iters; t.use_state_in = use_state_in;
+    t.part = h->dpart.as<float>(); t.trace_lse = h->dlse.as<float>(); t.max_steps = max_steps;
+    t.state_h = pred_state_h; t.pred_out = pred_out;
+    t.tokens = tokens_out; t.U_cap = U_cap; t.ntok = ntok_out; t.neg_logp = neg_logp_out; t.iters = iters_out;
+    t.trace = trace_logp; t.trace_cap = trace_logp ? trace_cap : 0;
+    t.barrier = h->gbar.as<unsigned int>();
+    static const bool ddbg2 = getenv("RNNT_DEC_DBG") != nullptr;
+    unsigned long long* dbg = nullptr;
+    const int dcap = 8192;
+    if (ddbg2) {
+      CK(cudaMalloc((void**)&dbg, (size_t)dcap * 16));
+      CK(cudaMemset(dbg, 0, (size_t)dcap * 16));
+      t.dbg = dbg; t.dbg_cap = dcap;
+    }
+    LAUNCH(trace_logp ? 3 : 2, launch_decode_tc2(t, st));
+    if (dbg) {
+      std::vector<unsigned long long> hb((size_t)dcap * 2);
+      CK(cudaStreamSynchronize(st));
+      CK(cudaMemcpy(hb.data(), dbg, (size_t)dcap * 16, cudaMemcpyDeviceToHost));
+      cudaFree(dbg);
+      double sum[8] = {0}; int cnt[8] = {0}; int n = 0;
+      for (int i = 1; i < dcap && hb[2 * i]; ++i, ++n) {
+        const int tag = (int)hb[2 * i + 1];
+        if (tag < 8) { sum[tag] += (double)(hb[2 * i] - hb[2 * i - 2]); cnt[tag]++; }
+      }
+      fprintf(stderr, "[decode_tc2 dbg] B=%d stamps=%d avg ns per segment: ->z published %.0f (n=%d) | ->keys published %.0f | ->table reduced %.0f | rule %.0f | C0 %.0f (n=%d) | C1 %.0f | total %.0f us over %d steps\n",
+              B, n, cnt[0] ? sum[0] / cnt[0] : 0, cnt[0], cnt[1] ? sum[1] / cnt[1] : 0, cnt[2] ? sum[2] / cnt[2] : 0,
+              cnt[3] ? sum[3] / cnt[3] : 0, cnt[4] ? sum[4] / cnt[4] : 0, cnt[4], cnt[5] ? sum[5] / cnt[5] : 0,
+              n > 1 ? (double)(hb[2 * n] - hb[2]) / 1e3 : 0.0, cnt[3]);
+    }
+    if (h->ev) cudaEventRecord(h->ev[4], st);
+    return RNNT_B200_OK;
+  }
   DecodeTcPlan dpl;
   if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok && (c.lm_layers == 0 || h->lm_tc_ok) &&
       decode_tc_plan(H, J, c.vocab_sz, c.pred_layers, B, h->sm_count, &dpl, c.lm_layers, c.lm_hidden_sz)) {

@@ -1149,6 +1149,19 @@ bool decode_tc_plan(int H, int J, int V, int Lp, int B, int sms, DecodeTcPlan* p
   return false;
 }
 
+// post-pass shared with decode_tc2.cu
+cudaError_t launch_decode_finish(const float* part, const int* n_eval, int B, int nB, int Bq, int max_steps, double* neg_logp, float* trace,
+                                 float* trace_lse, int trace_cap, int V, cudaStream_t st) {
+  decode_finish_kernel<<<B, 1024, 0, st>>>(part, n_eval, nB, Bq, max_steps, neg_logp, trace ? trace_lse : nullptr, trace_cap);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (trace) {
+    trace_normalize_kernel<<<148, 256, 0, st>>>(trace, trace_lse, B, trace_cap, V);
+    return cudaGetLastError();
+  }
+  return cudaSuccess;
+}
+
 cudaError_t launch_decode_tc(const DecodeTcArgs& a, const DecodeTcPlan& pl, cudaStream_t st) {
   DecodeTcArgs args = a;
   args.Uc = pl.Uc; args.NC_A = pl.NC_A; args.NC_B = pl.NC_B; args.NC_C = pl.NC_C; args.NC_max = pl.NC_max;

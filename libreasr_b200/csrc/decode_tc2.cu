@@ -1,0 +1,727 @@
+// Device-resident batched greedy RNN-T decode, cluster split-K formulation (gemm_mode 1, up to 32 utterances,
+// H = J = 1024, two predictor layers, no fused LM; every other case keeps decode_tc.cu).
+//
+// Same loop as decode_tc.cu / decode.cu (reference libreasr/lib/models.py:403-443 / 528-571; predictor
+// haste/nbrc.py:46-56; joint models.py:132-140) with the dependent GEMMs of a lock-step
+//      A   pp = W1p g            z = tanh(pp + ep[b, t_b])
+//      B   logits = W2 z + b2    -> arg max over the vocabulary -> greedy rule R
+//      C0  GRU layer 0 (input = table row of the token, recurrent product R0 h0 speculative)
+//      C1  GRU layer 1 (input product K1 BN(h0'), recurrent product R1 h1 speculative) -> g = BN(h1')
+// re-partitioned like lstm_tc2.cu instead of "every CTA takes a slice of the rows and ingests the whole activation":
+//   * 32 clusters of 4 CTAs.  Cluster c owns a block of output rows of every matrix (32 rows of W1p, V/32 of W2,
+//     32 units = 96 interleaved gate rows of K1 / R0 / R1); CTA `rank` of the cluster holds the K-slice
+//     [256 rank, 256 rank + 256) of those rows.  Weight rows sit on the MMA M axis (M = 64 / 128), the batch on N
+//     ([h_hi ; h_lo] x W_hi, h_hi x W_lo: the 3xFP16 split of tc_common.cuh), so a GEMM job costs 32 tcgen05.mma and a
+//     CTA ingests 32 KB of activations per job instead of 128 KB.
+//   * Split-K reduction through distributed shared memory: every epilogue warp folds its TMEM lanes and writes the
+//     32-batch partial rows into the owner CTA's shared memory (st.shared::cluster + remote mbarrier arrive); the owner
+//     (rank r owns rows [r R/4, (r+1) R/4) of the cluster's block) sums the four partial tiles and finalises.
+//   * Activations (g, z, BN(h0'), h0', h1') travel as tagged 16-byte chunks (tc2_common.cuh): published with one
+//     st.relaxed.gpu.v4 by the finalising thread group, polled as data by the consumers' loader warps.  The per-step
+//     arg max is exchanged the same way: every CTA publishes one packed (logit, index, tag) key per utterance, every CTA
+//     reads the 128 x 32 table and reduces it: no atomics, no grid barrier anywhere in the loop.
+//   * W2 (needed by every lock-step) stays resident in shared memory; W1p, K1, R0, R1 stream through a 3-stage TMA ring
+//     ahead of their jobs.  The recurrent products R0 h0', R1 h1' are issued speculatively right after the predictor
+//     run that produced h0' / h1' (jobs JR0 / JR1), their reduced rows wait in registers for the next emission.
+//
+//   warps 0-3  epilogue / finalise (TMEM -> fold -> DSMEM scatter -> sum -> cell / softmax partials / rule -> publish)
+//   warps 4-7  loaders (tagged activation chunks -> 8 KB k-block stages of a 6-stage ring)
+//   warp  8    MMA issuer (accumulators double-buffered in TMEM, 2 x 128 columns)
+//   warp  9    weight streamer (TMA bulk copies, 24 KB k-block stages)
+#include <algorithm>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+#include "tc2_common.cuh"
+
+namespace rnnt {
+namespace {
+
+constexpr int D2_THREADS = 320;
+constexpr int D2_CL = 4;          // CTAs per cluster = K slices
+constexpr int D2_NCL = 32;        // clusters
+constexpr int D2_G = D2_CL * D2_NCL;
+constexpr int D2_NB = 32;         // batch rows (N tile: 32 hi + 32 lo)
+constexpr int D2_KS = 4;          // k-blocks per K slice (K = 1024)
+constexpr int D2_AST = 6;         // activation ring stages (8 KB each)
+constexpr int D2_WST = 3;         // streamed-weight ring stages (24 KB each)
+constexpr int D2_WSTAGE = 24576;
+constexpr int D2_RP = 24;         // row stride of a partial tile (max rows finalised per CTA)
+constexpr int D2_K = 1024;        // H = J
+
+enum { IMG_G = 0, IMG_Z = 1, IMG_X = 2, IMG_H0 = 3, IMG_H1 = 4, IMG_N = 5 };
+enum { JOB_A = 0, JOB_B = 1, JOB_K1 = 2, JOB_R0 = 3, JOB_R1 = 4 };
+
+struct Ctrl2 {
+  int t[D2_NB], it[D2_NB], ntok[D2_NB], tok[D2_NB], n_eval[D2_NB], len[D2_NB], am[D2_NB];
+  unsigned char active[D2_NB], emit[D2_NB];
+  int flags[2];                                  // any_emit, any_active of the current step
+  unsigned long long kred[8][D2_NB];             // partial maxima of the key table
+};
+
+__global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cta = blockIdx.x, cl = cta / D2_CL;
+  const DecodeWeights& w = p.w;
+  const int H = w.H, J = w.J, V = w.V, B = p.B, T = p.T;
+  const int RB = V / D2_NCL;                      // W2 rows per cluster (<= 64)
+  const int rpB = RB / D2_CL;                     // ... finalised per CTA (<= 16)
+  // ---- shared memory ----
+  uint8_t* W2s = base;                                             // [KS][hi RB x 128 B | lo RB x 128 B]
+  const uint32_t w2kb = (uint32_t)RB * 256u;
+  uint8_t* wring = W2s + 65536;                                    // D2_WST x 24 KB
+  uint8_t* aring = wring + D2_WST * D2_WSTAGE + 4096;              // D2_AST x 8 KB (4 KB guard: an M=128 lo tile is read 16 KB deep)
+  float* P = reinterpret_cast<float*>(aring + D2_AST * 8192);     // [2][4 src][32 b][24] fp32
+  Ctrl2& c = *reinterpret_cast<Ctrl2*>(reinterpret_cast<uint8_t*>(P) + 2 * D2_CL * D2_NB * D2_RP * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&c) + ((sizeof(Ctrl2) + 15) & ~15));
+  uint64_t* afull = bars;                 // [AST] loaders -> MMA (128 arrivals)
+  uint64_t* aempty = afull + D2_AST;      // [AST] MMA -> loaders
+  uint64_t* wfull = aempty + D2_AST;      // [WST] TMA -> MMA
+  uint64_t* wempty = wfull + D2_WST;      // [WST] MMA -> streamer
+  uint64_t* tfull = wempty + D2_WST;      // [2]
+  uint64_t* tempty = tfull + 2;           // [2] 128 arrivals
+  uint64_t* pbar = tempty + 2;            // [2] partial tiles of a job complete: 16 warp arrivals (4 CTAs x 4 warps)
+  uint64_t* pfree = pbar + 2;             // [2] partial tiles of a job consumed by their 4 owners: 16 warp arrivals
+  uint64_t* w2full = pfree + 2;
+  uint64_t* ctlbar = w2full + 1;          // flags of a step published
+  uint64_t* ctlack = ctlbar + 1;          // ... and read by the 6 GEMM-side warps
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(ctlack + 1);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < D2_AST; ++i) { mbar_init(&afull[i], 128); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < D2_WST; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+      mbar_init(&pbar[i], 16);
+      mbar_init(&pfree[i], 16);
+    }
+    mbar_init(w2full, 1);
+    mbar_init(ctlbar, 1);
+    mbar_init(ctlack, 6);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(tptr, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();
+  const uint32_t tmem = *tptr;
+  const size_t slice_off = (size_t)rank * D2_KS * 8192;   // this CTA's K slice inside an activation image
+
+  // image `i`, write number n (0-based) lives in buffer n & 1 and carries tag (n >> 1) & 1
+  auto img_ptr = [&](int i, unsigned n) -> uint8_t* { return p.img[i] + (size_t)(n & 1u) * p.img_stride; };
+
+  // The four roles walk the same job sequence; these helpers keep the shared bookkeeping identical.
+  //   job j: accumulators / partial tiles in buffer j & 1
+  if (warp < 4) {
+    // ======================================= epilogue / finalise =======================================
+    const int q = warp;
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    const int et = warp * 32 + lane;
+    const int fb = warp * 8 + (lane >> 2);      // batch row finalised by this thread
+    const int fw = lane & 3;
+    const bool bvalid = fb < B;
+    const int u0 = cl * 32 + rank * 8;          // first unit / joint row finalised by this CTA
+    const int unit = u0 + 2 * fw;
+    const int vB0 = cl * RB + rank * rpB;       // first vocabulary row finalised by this CTA
+    const int rptB = rpB / 4;                   // vocabulary rows per thread (1..4)
+    const uint32_t off_hi = (uint32_t)((u0 >> 6) * 2) * 4096u + (uint32_t)fb * 128u + (uint32_t)((((u0 & 63) >> 3) ^ (fb & 7)) << 4);
+    const uint32_t P_u32 = smem_u32(P);
+
+    for (int i = et; i < D2_NB; i += 128) {
+      const int len = (i < B) ? (p.lens_T ? min(p.lens_T[i], T) : T) : 0;
+      c.len[i] = len; c.t[i] = 0; c.it[i] = 0; c.ntok[i] = 0; c.n_eval[i] = 0; c.am[i] = 0;
+      c.tok[i] = w.bos; c.active[i] = len > 0; c.emit[i] = i < B;
+    }
+    // ---- persistent per-thread state ----
+    float pp[2] = {0.f, 0.f}, gval[2] = {0.f, 0.f}, hst[2][2], rec[2][6];
+    float bsc[2][2], bsh[2][2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        hst[l][i] = (bvalid && p.use_state_in) ? p.state_h[((size_t)l * B + fb) * H + unit + i] : w.h0[l][unit + i];
+        bsc[l][i] = w.bn_scale[l][unit + i];
+        bsh[l][i] = w.bn_shift[l][unit + i];
+      }
+#pragma unroll
+    for (int l = 0; l < 2; ++l)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) rec[l][i] = 0.f;
+    if (bvalid && p.use_state_in) {
+      gval[0] = p.pred_out[(size_t)fb * H + unit];
+      gval[1] = p.pred_out[(size_t)fb * H + unit + 1];
+    }
+    unsigned nw[IMG_N] = {0, 0, 0, 0, 0};   // writes issued so far per image
+    unsigned nkeys = 0;                     // key-table writes so far
+    // 8 consecutive k (the two values of the 4 lanes of a batch row) -> one hi and one lo 16-byte chunk, tagged
+    auto publish = [&](int img, float v0, float v1) {
+      const unsigned n = nw[img]++;
+      uint8_t* dst = img_ptr(img, n);
+      const uint32_t tag = (n >> 1) & 1u;
+      uint32_t h0, l0, h1, l1;
+      split_tag(v0, false, 0u, h0, l0);
+      split_tag(v1, fw == 3, tag, h1, l1);
+      const uint32_t hp = h0 | (h1 << 16), lp = l0 | (l1 << 16);
+      const int g0 = lane & ~3;
+      const uint32_t a0 = __shfl_sync(0xffffffffu, hp, g0), a1 = __shfl_sync(0xffffffffu, hp, g0 + 1);
+      const uint32_t a2 = __shfl_sync(0xffffffffu, hp, g0 + 2), a3 = __shfl_sync(0xffffffffu, hp, g0 + 3);
+      const uint32_t b0 = __shfl_sync(0xffffffffu, lp, g0), b1 = __shfl_sync(0xffffffffu, lp, g0 + 1);
+      const uint32_t b2 = __shfl_sync(0xffffffffu, lp, g0 + 2), b3 = __shfl_sync(0xffffffffu, lp, g0 + 3);
+      if (fw == 0) st_relaxed_v4(dst + off_hi, a0, a1, a2, a3);
+      else if (fw == 1) st_relaxed_v4(dst + off_hi + 4096u, b0, b1, b2, b3);
+    };
+    // ---- launch start: every image buffer gets a defined tag (stale chunks of an earlier launch must not validate) ----
+    {
+      // write #0 of g / h0 / h1 = the initial state (tag 0 in buffer 0); buffer 1 and both buffers of z / x: tag 1
+      publish(IMG_G, gval[0], gval[1]);
+      publish(IMG_H0, hst[0][0], hst[0][1]);
+      publish(IMG_H1, hst[1][0], hst[1][1]);
+      const uint4 one = make_uint4(0u, 0u, 0u, 0x00010000u);
+      if (fw < 2) {
+        const uint32_t off = off_hi + (fw == 1 ? 4096u : 0u);
+        st_relaxed_v4(p.img[IMG_G] + p.img_stride + off, one.x, one.y, one.z, one.w);
+        st_relaxed_v4(p.img[IMG_H0] + p.img_stride + off, one.x, one.y, one.z, one.w);
+        st_relaxed_v4(p.img[IMG_H1] + p.img_stride + off, one.x, one.y, one.z, one.w);
+        for (int bf = 0; bf < 2; ++bf) {
+          st_relaxed_v4(p.img[IMG_Z] + (size_t)bf * p.img_stride + off, one.x, one.y, one.z, one.w);
+          st_relaxed_v4(p.img[IMG_X] + (size_t)bf * p.img_stride + off, one.x, one.y, one.z, one.w);
+        }
+      }
+      // key table [2][128 cta][32 b] u64: tag 1 (bit 0) everywhere
+      if (et < 32) {
+        p.keys[(size_t)cta * D2_NB + et] = 1ull;
+        p.keys[(size_t)(D2_G + cta) * D2_NB + et] = 1ull;
+      }
+      __threadfence();
+      named_bar_sync(1, 128);
+      if (et == 0) {
+        red_release_add(p.barrier, 1u);
+        while (ld_acquire_u32(p.barrier) < (unsigned)D2_G) {
+        }
+      }
+      named_bar_sync(1, 128);
+    }
+
+    unsigned job = 0;
+    int ndbg = 0;
+    auto stamp = [&](int tag) {
+      if (p.dbg && cta == 0 && et == 0 && ndbg < p.dbg_cap) { p.dbg[2 * ndbg] = gtimer(); p.dbg[2 * ndbg + 1] = (unsigned long long)tag; ++ndbg; }
+    };
+    // Drain the accumulators of the current job, scatter this warp's rows to their owner CTAs, wait for the four
+    // partial tiles of the rows this CTA owns.  M: MMA M of the job, rows: valid rows of the cluster, rp: rows per owner.
+    auto reduce_job = [&](int M, int rows, int rp) -> const float* {
+      const unsigned j = job++;
+      const int ab = (int)(j & 1u);
+      const unsigned n = j >> 1;
+      mbar_wait(&tfull[ab], n & 1u);
+      tc_fence_after();
+      const int r = (M == 64) ? q * 16 + lane : q * 32 + lane;
+      const bool mine = (M == 64 ? lane < 16 : true) && r < rows;
+      const int dst_rank = mine ? r / rp : 0, lrow = mine ? r % rp : 0;
+      const uint32_t dst = mapa(P_u32 + (uint32_t)((((ab * D2_CL + rank) * D2_NB) * D2_RP + lrow) * 4), (uint32_t)dst_rank);
+      mbar_wait_cluster(&pfree[ab], (n & 1u) ^ 1u);   // the owners have consumed the tiles of job j - 2
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float d0[16], d1[16], d2[16];
+        const uint32_t tc = tl + (uint32_t)(ab * 128 + hf * 16);
+        tmem_ld16(tc, d0);          // W_hi * h_hi
+        tmem_ld16(tc + 32, d1);     // W_hi * h_lo (x 2^11)
+        tmem_ld16(tc + 64, d2);     // W_lo * h_hi (x 2^11)
+        tmem_ld_wait();
+        if (mine) {
+#pragma unroll
+          for (int b = 0; b < 16; ++b) st_cluster_f32(dst + (uint32_t)((hf * 16 + b) * D2_RP * 4), fmaf(d1[b] + d2[b], kLoInv, d0[b]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[ab]);
+      __syncwarp();
+      if (lane < D2_CL) mbar_arrive_cluster(mapa(smem_u32(&pbar[ab]), (uint32_t)lane));
+      mbar_wait_cluster(&pbar[ab], n & 1u);
+      return P + (size_t)((ab * D2_CL) * D2_NB + fb) * D2_RP;   // + src * 32 * 24 ; this thread's batch row
+    };
+    // all reads of the partial tiles of the job just finalised are done: hand the buffers back to the senders
+    auto release_job = [&]() {
+      const int ab = (int)((job - 1) & 1u);
+      __syncwarp();
+      if (lane < D2_CL) mbar_arrive_cluster(mapa(smem_u32(&pfree[ab]), (uint32_t)lane));
+    };
+    auto sum2 = [&](const float* pr, int off, float* o, int nfl) {   // o[i] = sum over the 4 sources, nfl in {2, 4, 6}
+#pragma unroll
+      for (int s = 0; s < D2_CL; ++s) {
+        const float* ps = pr + (size_t)s * D2_NB * D2_RP + off;
+#pragma unroll
+        for (int i = 0; i < 6; i += 2) {
+          if (i < nfl) {
+            const float2 v = *reinterpret_cast<const float2*>(ps + i);
+            if (s == 0) { o[i] = v.x; o[i + 1] = v.y; } else { o[i] += v.x; o[i + 1] += v.y; }
+          }
+        }
+      }
+    };
+    // speculative recurrent product of predictor layer l -> registers
+    auto epi_rec = [&](int l) {
+      const float* pr = reduce_job(128, 96, 24);
+      sum2(pr, fw * 6, rec[l], 6);
+      release_job();
+    };
+    // predictor layer l (GRU cell + BatchNorm eval, haste/nbrc.py:46-56); vx = input pre-activations incl. bias
+    auto gru_cell = [&](int l, const float (&vx)[6]) {
+      const bool em = bvalid && c.emit[fb] != 0;
+      if (em) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float* rb = w.rbias[l] + (size_t)(unit + i) * 3;
+          const float z = sigmoidf_acc(vx[3 * i + 0] + (rec[l][3 * i + 0] + rb[0]));
+          const float r = sigmoidf_acc(vx[3 * i + 1] + (rec[l][3 * i + 1] + rb[1]));
+          const float gg = tanhf(vx[3 * i + 2] + r * (rec[l][3 * i + 2] + rb[2]));
+          hst[l][i] = z * hst[l][i] + (1.0f - z) * gg;
+        }
+      }
+    };
+    auto phase_c0 = [&]() {
+      float vx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (bvalid && c.emit[fb]) {   // Embedding -> Linear -> kernel_0 folded into a [V][3H] table (models.py:182-183)
+        const float* row = w.table0 + (size_t)c.tok[fb] * (3 * H);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          vx[3 * i + 0] = row[unit + i]; vx[3 * i + 1] = row[H + unit + i]; vx[3 * i + 2] = row[2 * H + unit + i];
+        }
+      }
+      gru_cell(0, vx);
+      publish(IMG_H0, hst[0][0], hst[0][1]);
+      publish(IMG_X, hst[0][0] * bsc[0][0] + bsh[0][0], hst[0][1] * bsc[0][1] + bsh[0][1]);
+    };
+    auto phase_c1 = [&]() {
+      float kb[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) kb[i] = w.kbias[1][(size_t)unit * 3 + i];
+      const float* pr = reduce_job(128, 96, 24);
+      float vx[6];
+      sum2(pr, fw * 6, vx, 6);
+      release_job();
+#pragma unroll
+      for (int i = 0; i < 6; ++i) vx[i] += kb[i];
+      gru_cell(1, vx);
+      gval[0] = hst[1][0] * bsc[1][0] + bsh[1][0];
+      gval[1] = hst[1][1] * bsc[1][1] + bsh[1][1];
+      publish(IMG_H1, hst[1][0], hst[1][1]);
+      publish(IMG_G, gval[0], gval[1]);
+    };
+
+    if (!p.use_state_in) {   // feed BOS from the learnable initial state (models.py:397-398)
+      epi_rec(0);
+      epi_rec(1);
+      phase_c0();
+      phase_c1();
+    }
+    bool pending = true, any_upd = true;
+    for (int step = 0;; ++step) {
+      if (pending) epi_rec(0);
+      // ---------------- phase A: pp and z ----------------
+      {
+        const bool act = bvalid && c.active[fb] != 0;
+        float2 epv = make_float2(0.f, 0.f);
+        if (act) epv = *reinterpret_cast<const float2*>(p.ep + ((size_t)fb * T + c.t[fb]) * J + unit);
+        if (any_upd) {
+          const float* pr = reduce_job(64, 32, 8);
+          sum2(pr, fw * 2, pp, 2);
+          release_job();
+        }
+        publish(IMG_Z, act ? tanhf(pp[0] + epv.x) : 0.f, act ? tanhf(pp[1] + epv.y) : 0.f);
+      }
+      stamp(0);
+      if (pending) { epi_rec(1); pending = false; }
+      // ---------------- phase B: logits of this CTA's vocabulary rows, arg max exchange ----------------
+      {
+        float b2v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b2v[i] = (i < rptB) ? w.b2[vB0 + fw * rptB + i] : 0.f;
+        const float* pr = reduce_job(64, RB, rpB);
+        float lv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int s = 0; s < D2_CL; ++s) {
+          const float* ps = pr + (size_t)s * D2_NB * D2_RP + fw * rptB;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < rptB) lv[i] = (s == 0 ? b2v[i] : lv[i]) + ps[i];
+        }
+        release_job();
+        const bool act = bvalid && c.active[fb] != 0;
+        float m = -INFINITY, s = 0.f;
+        int am = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < rptB && lv[i] > m) { m = lv[i]; am = vB0 + fw * rptB + i; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < rptB) s += expf(lv[i] - m);
+        if (p.trace && act && c.n_eval[fb] < p.trace_cap) {
+          float* tr = p.trace + ((size_t)fb * p.trace_cap + c.n_eval[fb]) * V + vB0 + fw * rptB;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < rptB) tr[i] = lv[i];
+        }
+        // the 4 lanes of a batch row hold ascending vocabulary slices: strict > keeps the first maximum (torch.max)
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+          const float m2 = __shfl_down_sync(0xffffffffu, m, o), s2 = __shfl_down_sync(0xffffffffu, s, o);
+          const int am2 = __shfl_down_sync(0xffffffffu, am, o);
+          if ((fw & (2 * o - 1)) == 0) {
+            if (m2 > m) { s = s * expf(m - m2) + s2; m = m2; am = am2; }
+            else s += s2 * expf(m2 - m);
+          }
+        }
+        const unsigned nk = nkeys++;
+        const uint32_t ktag = (nk >> 1) & 1u;
+        unsigned long long key = (unsigned long long)ktag;
+        if (act && step < p.max_steps) {
+          unsigned u = __float_as_uint(m);
+          u ^= (u & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u;
+          key = ((unsigned long long)u << 32) | (unsigned long long)(((0x7FFFFFFFu - (unsigned)am) << 1) | ktag);
+          if (fw == 0) *reinterpret_cast<float2*>(p.part + (((size_t)step * D2_G + cta) * D2_NB + fb) * 2) = make_float2(m, s);
+        }
+        const unsigned long long key2 = __shfl_down_sync(0xffffffffu, key, 4);   // batch row fb + 1 (same warp: fb even)
+        unsigned long long* ktab = p.keys + (size_t)(nk & 1u) * D2_G * D2_NB;
+        if (fw == 0 && (fb & 1) == 0)
+          st_relaxed_v4(ktab + (size_t)cta * D2_NB + fb, (uint32_t)key, (uint32_t)(key >> 32), (uint32_t)key2, (uint32_t)(key2 >> 32));
+        stamp(1);
+        // every CTA reduces the whole table: thread -> batch pair et % 16, CTAs [16 (et / 16), +16)
+        {
+          const int bp = et & 15, g = et >> 4;
+          const unsigned long long* src = ktab + (size_t)(g * 16) * D2_NB + 2 * bp;
+          uint4 r[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = ld_relaxed_v4(src + (size_t)i * D2_NB);
+          uint32_t bad = 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if ((r[i].x & 1u) != ktag || (r[i].z & 1u) != ktag) bad |= 1u << i;
+          while (__any_sync(0xffffffffu, bad != 0u)) {   // stale entries are re-read in parallel rounds
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if ((bad >> i) & 1u) r[i] = ld_relaxed_v4(src + (size_t)i * D2_NB);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (((bad >> i) & 1u) && (r[i].x & 1u) == ktag && (r[i].z & 1u) == ktag) bad &= ~(1u << i);
+          }
+          unsigned long long k0 = 0ull, k1 = 0ull;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const unsigned long long a = ((unsigned long long)r[i].y << 32) | r[i].x, b = ((unsigned long long)r[i].w << 32) | r[i].z;
+            k0 = a > k0 ? a : k0;
+            k1 = b > k1 ? b : k1;
+          }
+          c.kred[g][2 * bp] = k0;
+          c.kred[g][2 * bp + 1] = k1;
+        }
+        named_bar_sync(1, 128);
+        stamp(2);
+      }
+      // ---------------- R: greedy rule (models.py:408-437), identical in every CTA ----------------
+      {
+        if (step > 0) mbar_wait(ctlack, (step - 1) & 1);
+        if (et < B) {
+          const int bb = et;
+          unsigned char emit = 0;
+          if (c.active[bb]) {
+            unsigned long long key = 0ull;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) key = c.kred[g][bb] > key ? c.kred[g][bb] : key;
+            const int am2 = (int)(0x7FFFFFFFu - (unsigned)((key & 0xFFFFFFFFull) >> 1));
+            const int t = c.t[bb];
+            c.n_eval[bb] += 1;
+            const int it = c.it[bb] + 1;
+            bool advance;
+            if (am2 == w.blank) {
+              advance = true;
+            } else {
+              const int n = c.ntok[bb];
+              if (cta == 0 && n < p.U_cap) p.tokens[(size_t)bb * p.U_cap + n] = am2;
+              c.ntok[bb] = n + 1;
+              c.tok[bb] = am2;
+              emit = 1;
+              advance = it >= p.max_iters;
+            }
+            if (advance) {
+              if (cta == 0 && p.iters) p.iters[(size_t)bb * T + t] = (uint8_t)it;
+              c.t[bb] = t + 1;
+              c.it[bb] = 0;
+              if (t + 1 >= c.len[bb]) c.active[bb] = 0;
+            } else {
+              c.it[bb] = it;
+            }
+          }
+          c.emit[bb] = emit;
+        }
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          int ae = 0, aa = 0;
+          for (int i = 0; i < B; ++i) { ae |= c.emit[i]; aa |= c.active[i]; }
+          c.flags[0] = ae; c.flags[1] = aa;
+          mbar_arrive(ctlbar);
+        }
+        named_bar_sync(1, 128);
+      }
+      const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
+      stamp(3);
+      if (any_emit) {
+        phase_c0();
+        stamp(4);
+        phase_c1();
+        stamp(5);
+        pending = true;
+      }
+      any_upd = any_emit;
+      if (!any_active) break;
+    }
+    // ---- results and state ----
+    if (cta == 0 && et < B) {
+      p.ntok[et] = c.ntok[et];
+      p.n_eval[et] = c.n_eval[et];
+    }
+    if (bvalid) {
+      if (p.state_h)
+#pragma unroll
+        for (int l = 0; l < 2; ++l)
+          *reinterpret_cast<float2*>(p.state_h + ((size_t)l * B + fb) * H + unit) = make_float2(hst[l][0], hst[l][1]);
+      if (p.pred_out) *reinterpret_cast<float2*>(p.pred_out + (size_t)fb * H + unit) = make_float2(gval[0], gval[1]);
+    }
+  } else if (warp < 8) {
+    // ======================================= loaders =======================================
+    const int lt = (warp - 4) * 32 + lane;
+    unsigned nw[IMG_N] = {1, 0, 0, 1, 1};   // writes that precede the point reached in the job sequence
+    unsigned ga = 0;                        // k-block stages filled so far
+    if (lane == 0) {
+      while (ld_acquire_u32(p.barrier) < (unsigned)D2_G) {
+      }
+    }
+    __syncwarp();
+    // K slice of the latest write of image `img` -> 4 ring stages
+    auto fetch = [&](int img) {
+      const unsigned n = nw[img] - 1;
+      const uint32_t tag = (n >> 1) & 1u;
+      const uint8_t* src = img_ptr(img, n) + slice_off + (size_t)lt * 16;
+      uint4 r[16];
+      poll_chunks<16>(src, 2048, 16, tag, r);
+#pragma unroll
+      for (int kb = 0; kb < D2_KS; ++kb, ++ga) {
+        const int s = (int)(ga % D2_AST);
+        mbar_wait(&aempty[s], ((ga / D2_AST) & 1u) ^ 1u);
+        uint8_t* dst = aring + (size_t)s * 8192 + (size_t)lt * 16;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          chunk_strip_tag(r[kb * 4 + jj]);
+          *reinterpret_cast<uint4*>(dst + (size_t)jj * 2048) = r[kb * 4 + jj];
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&afull[s]);
+      }
+    };
+    if (!p.use_state_in) {
+      fetch(IMG_H0);
+      fetch(IMG_H1);
+      nw[IMG_H0]++; nw[IMG_X]++;
+      fetch(IMG_X);
+      nw[IMG_H1]++; nw[IMG_G]++;
+    }
+    bool pending = true, any_upd = true;
+    for (int step = 0;; ++step) {
+      if (pending) fetch(IMG_H0);
+      if (any_upd) fetch(IMG_G);
+      nw[IMG_Z]++;
+      if (pending) { fetch(IMG_H1); pending = false; }
+      fetch(IMG_Z);
+      mbar_wait(ctlbar, step & 1);
+      const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ctlack);
+      if (any_emit) {
+        nw[IMG_H0]++; nw[IMG_X]++;
+        fetch(IMG_X);
+        nw[IMG_H1]++; nw[IMG_G]++;
+        pending = true;
+      }
+      any_upd = any_emit;
+      if (!any_active) break;
+    }
+  } else if (warp == 8) {
+    // ======================================= MMA issuer =======================================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w2full, (uint32_t)D2_KS * w2kb);
+      tma_bulk_g2s(W2s, p.w2_img + img_tile_offset(cl, rank * D2_KS, 0, D2_K / 64, RB), (uint32_t)D2_KS * w2kb, w2full);
+    }
+    __syncwarp();
+    const uint64_t a_ring0 = umma_desc_sw128(smem_u32(aring));
+    const uint64_t w_ring0 = umma_desc_sw128(smem_u32(wring));
+    const uint64_t w2_0 = umma_desc_sw128(smem_u32(W2s));
+    unsigned job = 0, ga = 0, gw = 0;
+    // one GEMM job: weights either resident (W2) or from the ring; hi part of a k-block = `rows` x 128 B
+    auto run_job = [&](int M, int rows, bool resident) {
+      const unsigned j = job++;
+      const int ab = (int)(j & 1u);
+      mbar_wait(&tempty[ab], ((j >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t idesc1 = umma_idesc_f16(M, 64), idesc2 = umma_idesc_f16(M, 32);
+      const uint32_t dcol = tmem + (uint32_t)(ab * 128);
+      const uint32_t lo_u = ((uint32_t)rows * 128u) >> 4;
+      for (int kb = 0; kb < D2_KS; ++kb, ++ga) {
+        const int sa = (int)(ga % D2_AST);
+        uint64_t wd;
+        int sw = 0;
+        if (resident) {
+          wd = w2_0 + (uint64_t)((uint32_t)kb * (w2kb >> 4));
+        } else {
+          sw = (int)(gw % D2_WST);
+          mbar_wait(&wfull[sw], (gw / D2_WST) & 1u);
+          wd = w_ring0 + (uint64_t)((uint32_t)sw * (D2_WSTAGE >> 4));
+        }
+        mbar_wait(&afull[sa], (ga / D2_AST) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t bd = a_ring0 + (uint64_t)((uint32_t)sa * (8192 >> 4));
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t accumulate = (kb | k4) ? 1u : 0u;
+            tc_mma_f16(dcol, wd + 2 * k4, bd + 2 * k4, idesc1, accumulate);
+            tc_mma_f16(dcol + 64, wd + lo_u + 2 * k4, bd + 2 * k4, idesc2, accumulate);
+          }
+          tc_commit(&aempty[sa]);
+          if (!resident) tc_commit(&wempty[sw]);
+          if (kb == D2_KS - 1) tc_commit(&tfull[ab]);
+        }
+        __syncwarp();
+        if (!resident) ++gw;
+      }
+    };
+    mbar_wait(w2full, 0);
+    if (!p.use_state_in) {
+      run_job(128, 96, false);   // R0 h0
+      run_job(128, 96, false);   // R1 h1
+      run_job(128, 96, false);   // K1 BN(h0')
+    }
+    bool pending = true, any_upd = true;
+    for (int step = 0;; ++step) {
+      if (pending) run_job(128, 96, false);
+      if (any_upd) run_job(64, 32, false);
+      if (pending) { run_job(128, 96, false); pending = false; }
+      run_job(64, RB, true);
+      mbar_wait(ctlbar, step & 1);
+      const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ctlack);
+      if (any_emit) {
+        run_job(128, 96, false);
+        pending = true;
+      }
+      any_upd = any_emit;
+      if (!any_active) break;
+    }
+  } else {
+    // ======================================= weight streamer =======================================
+    unsigned gw = 0;
+    auto stream = [&](const uint8_t* wimg, int TR) {   // this CTA's K slice of its cluster's row tile: 4 k-blocks of TR x 256 B
+      const uint32_t kbb = (uint32_t)TR * 256u;
+      const uint8_t* src = wimg + img_tile_offset(cl, rank * D2_KS, 0, D2_K / 64, TR);
+      for (int kb = 0; kb < D2_KS; ++kb, ++gw) {
+        const int s = (int)(gw % D2_WST);
+        mbar_wait(&wempty[s], ((gw / D2_WST) & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&wfull[s], kbb);
+          tma_bulk_g2s(wring + (size_t)s * D2_WSTAGE, src + (size_t)kb * kbb, kbb, &wfull[s]);
+        }
+        __syncwarp();
+      }
+    };
+    if (!p.use_state_in) {
+      stream(p.r_img[0], 96);
+      stream(p.r_img[1], 96);
+      stream(p.k1_img, 96);
+    }
+    bool pending = true, any_upd = true;
+    for (int step = 0;; ++step) {
+      if (pending) stream(p.r_img[0], 96);
+      if (any_upd) stream(p.w1p_img, 32);
+      if (pending) { stream(p.r_img[1], 96); pending = false; }
+      mbar_wait(ctlbar, step & 1);
+      const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ctlack);
+      if (any_emit) {
+        stream(p.k1_img, 96);
+        pending = true;
+      }
+      any_upd = any_emit;
+      if (!any_active) break;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) tmem_dealloc(tmem, 256);
+}
+
+int g_dec2_max_clusters = -1;
+
+}  // namespace
+
+// defined in decode_tc.cu: post-pass that folds the per-step softmax partials into log-probabilities
+cudaError_t launch_decode_finish(const float* part, const int* n_eval, int B, int nB, int Bq, int max_steps, double* neg_logp, float* trace,
+                                 float* trace_lse, int trace_cap, int V, cudaStream_t st);
+
+static size_t decode_tc2_smem() {
+  return 65536 + (size_t)D2_WST * D2_WSTAGE + 4096 + (size_t)D2_AST * 8192 + (size_t)2 * D2_CL * D2_NB * D2_RP * 4 + ((sizeof(Ctrl2) + 15) & ~15) + 512 + 1024;
+}
+
+cudaError_t configure_decode_tc2() {
+  return cudaFuncSetAttribute(decode_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+bool decode_tc2_plan(int H, int J, int V, int Lp, int B, int sms, int lm_layers) {
+  if (lm_layers > 0 || Lp != 2 || H != D2_K || J != D2_K || V % 512 || V < 512 || V > 2048 || B < 1 || B > D2_NB || sms < D2_G) return false;
+  if (decode_tc2_smem() > 227 * 1024) return false;
+  if (g_dec2_max_clusters < 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(D2_G);
+    cfg.blockDim = dim3(D2_THREADS);
+    cfg.dynamicSmemBytes = decode_tc2_smem();
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = D2_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, decode_tc2_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    g_dec2_max_clusters = n;
+  }
+  return g_dec2_max_clusters >= D2_NCL;
+}
+
+size_t decode_tc2_image_bytes() { return (size_t)(D2_K / 64) * 8192; }        // one buffer of one activation image
+size_t decode_tc2_keys_bytes() { return (size_t)2 * D2_G * D2_NB * 8; }
+int decode_tc2_part_ctas() { return D2_G; }
+
+cudaError_t launch_decode_tc2(const DecodeTc2Args& a, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(D2_G);
+  cfg.blockDim = dim3(D2_THREADS);
+  cfg.dynamicSmemBytes = decode_tc2_smem();
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = D2_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_tc2_kernel, a);
+  if (e != cudaSuccess) return e;
+  return launch_decode_finish(a.part, a.n_eval, a.B, D2_G, D2_NB, a.max_steps, a.neg_logp, a.trace, a.trace_lse, a.trace_cap, a.w.V, st);
+}
+
+}  // namespace rnnt

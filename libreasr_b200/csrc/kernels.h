@@ -273,6 +273,35 @@ bool decode_tc_wplan(int H, int J, int V, int sms, DecodeTcPlan* pl, int lm_laye
 bool decode_tc_plan(int H, int J, int V, int Lp, int B, int sms, DecodeTcPlan* pl, int lm_layers = 0, int lm_hidden = 0);
 cudaError_t launch_decode_tc(const DecodeTcArgs& a, const DecodeTcPlan& pl, cudaStream_t st);
 
+// ---------------- decode_tc2.cu (tcgen05 greedy decode, cluster split-K over DSMEM, tagged exchange) ----------------
+struct DecodeTc2Args {
+  DecodeWeights w;                 // fp32 vectors / tables (table0, biases, h0, BatchNorm, b2)
+  const uint8_t* w1p_img;          // operand images, row tiles of one cluster: TR = 32 (W1p), V/32 (W2), 96 (K1, R0, R1)
+  const uint8_t* w2_img;
+  const uint8_t* k1_img;
+  const uint8_t* r_img[2];
+  uint8_t* img[5];                 // tagged activation images g, z, BN(h0'), h0', h1': 2 buffers of img_stride bytes each
+  size_t img_stride;
+  unsigned long long* keys;        // [2][128 CTAs][32] packed (logit, index, tag) arg-max keys
+  const float* ep;                 // [B][T][J] encoder half of the joint incl. b1
+  const int32_t* lens_T;
+  int B, T, max_iters, use_state_in;
+  float* part;                     // [max_steps][128][32][2] per-step (max, sum exp) of every CTA's vocabulary rows
+  int* n_eval;                     // [B]
+  int max_steps;
+  float* trace_lse;
+  float* state_h; float* pred_out; // [2][B][H], [B][H] in/out (nullable unless use_state_in)
+  int32_t* tokens; int U_cap; int32_t* ntok; double* neg_logp; uint8_t* iters; float* trace; int trace_cap;
+  unsigned int* barrier;           // launch-start counter, zero at launch
+  unsigned long long* dbg; int dbg_cap;
+};
+cudaError_t configure_decode_tc2();
+bool decode_tc2_plan(int H, int J, int V, int Lp, int B, int sms, int lm_layers);
+size_t decode_tc2_image_bytes();   // one buffer of one activation image
+size_t decode_tc2_keys_bytes();
+int decode_tc2_part_ctas();
+cudaError_t launch_decode_tc2(const DecodeTc2Args& a, cudaStream_t st);
+
 // standalone predictor step / joint (same phase code, one launch per phase)
 struct PredictArgs {
   DecodeWeights w;

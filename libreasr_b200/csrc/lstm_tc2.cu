@@ -28,6 +28,7 @@
 //   warp  8    MMA issuer (one elected lane), accumulators double-buffered in TMEM
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "tc2_common.cuh"
 
 namespace rnnt {
 namespace {
@@ -37,91 +38,6 @@ constexpr int L2_CL = 4;          // CTAs per cluster = K slices
 constexpr int L2_UPC = 8;         // units finalised per CTA
 constexpr int L2_NB = 32;         // batch rows per launch (N tile: 32 hi + 32 lo)
 constexpr int L2_MAX_KS = 4;      // k-blocks (64 k) per K slice
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long gtimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
-  uint4 v;
-  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-// 32 lanes x 32 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// x ~= hi + lo * 2^-11; with `tagged`, the LSB of both halves is replaced by `tag` (hi first, so that lo is derived
-// from the tagged hi and the pair still represents x to ~2^-21 relative)
-__device__ __forceinline__ void split_tag(float x, bool tagged, uint32_t tag, uint32_t& hi, uint32_t& lo) {
-  __half h = __float2half_rn(x);
-  uint32_t hb = __half_as_ushort(h);
-  if (tagged) {
-    hb = (hb & 0xFFFEu) | tag;
-    h = __ushort_as_half((unsigned short)hb);
-  }
-  const __half l = __float2half_rn((x - __half2float(h)) * kLoScale);
-  uint32_t lb = __half_as_ushort(l);
-  if (tagged) lb = (lb & 0xFFFEu) | tag;
-  hi = hb;
-  lo = lb;
-}
 
 __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Args p) {
   extern __shared__ uint8_t smem_raw[];
@@ -298,21 +214,15 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
       const uint32_t tag = (uint32_t)((t >> 1) & 1);
       const uint8_t* src = p.x_img[t & 1] + slice_off + (size_t)lt * 16;
       uint4 r[L2_MAX_KS * 4];
-#pragma unroll
-      for (int i = 0; i < L2_MAX_KS * 4; ++i)
-        if (i < NL) r[i] = ld_relaxed_v4(src + (size_t)i * 2048);
+      poll_chunks<L2_MAX_KS * 4>(src, 2048, NL, tag, r);
 #pragma unroll
       for (int kb = 0; kb < L2_MAX_KS; ++kb) {
         if (kb < KS) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int i = kb * 4 + j;
-            while (((r[i].w >> 16) & 1u) != tag) r[i] = ld_relaxed_v4(src + (size_t)i * 2048);
-          }
           if (t > 0) mbar_wait(&hempty[kb], (t - 1) & 1);   // the MMAs of step t-1 have finished reading this k-block
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int i = kb * 4 + j;
+            chunk_strip_tag(r[i]);
             *reinterpret_cast<uint4*>(hs + (size_t)i * 2048 + (size_t)lt * 16) = r[i];
           }
           fence_proxy_async_smem();

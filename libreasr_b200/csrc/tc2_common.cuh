@@ -1,0 +1,129 @@
+// Building blocks shared by the cluster split-K kernels (lstm_tc2.cu, decode_tc2.cu): gpu-scope relaxed vector
+// loads / stores for the tagged-chunk exchange, distributed-shared-memory stores and remote mbarrier arrives,
+// cluster barriers, 32-column TMEM loads, the hi/lo split with an embedded sequence tag.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "tc_common.cuh"
+
+namespace rnnt {
+namespace {
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// x ~= hi + lo * 2^-11.  With `tagged`, the LSB of both halves is a 1-bit sequence tag on the wire: the VALUE uses
+// LSB = 0 (hi is truncated to an even code before lo is derived from it, so the pair still represents x to ~2^-21
+// relative), the consumer clears the bit again (`chunk_strip_tag`) -- the operand never depends on the tag.
+__device__ __forceinline__ void split_tag(float x, bool tagged, uint32_t tag, uint32_t& hi, uint32_t& lo) {
+  __half h = __float2half_rn(x);
+  uint32_t hb = __half_as_ushort(h);
+  if (tagged) {
+    hb &= 0xFFFEu;
+    h = __ushort_as_half((unsigned short)hb);
+  }
+  const __half l = __float2half_rn((x - __half2float(h)) * kLoScale);
+  uint32_t lb = __half_as_ushort(l);
+  if (tagged) lb &= 0xFFFEu;
+  hi = hb | (tagged ? tag : 0u);
+  lo = lb | (tagged ? tag : 0u);
+}
+// a 16-byte chunk carries its tag in the LSB of its last half (bit 16 of word 3)
+__device__ __forceinline__ bool chunk_tag_ok(const uint4& r, uint32_t tag) { return ((r.w >> 16) & 1u) == tag; }
+__device__ __forceinline__ void chunk_strip_tag(uint4& r) { r.w &= 0xFFFEFFFFu; }
+
+// Polls N tagged chunks (src + i * stride, i < n) until every one carries `tag`.  The warp first spins, converged, on
+// chunk 0 only (one coalesced request per round trip: nothing else can be valid before it is worth looking), then
+// issues all the remaining loads back to back and re-issues only the stale ones, again in parallel rounds -- a
+// serial "load, check, reload" chain would cost one L2 round trip per chunk.
+template <int N>
+__device__ __forceinline__ void poll_chunks(const uint8_t* src, size_t stride, int n, uint32_t tag, uint4 (&r)[N]) {
+  for (;;) {
+    r[0] = ld_relaxed_v4(src);
+    if (__all_sync(0xffffffffu, chunk_tag_ok(r[0], tag))) break;
+  }
+#pragma unroll
+  for (int i = 1; i < N; ++i)
+    if (i < n) r[i] = ld_relaxed_v4(src + (size_t)i * stride);
+  uint32_t bad = 0;
+#pragma unroll
+  for (int i = 1; i < N; ++i)
+    if (i < n && !chunk_tag_ok(r[i], tag)) bad |= 1u << i;
+  while (__any_sync(0xffffffffu, bad != 0u)) {
+#pragma unroll
+    for (int i = 1; i < N; ++i)
+      if ((bad >> i) & 1u) r[i] = ld_relaxed_v4(src + (size_t)i * stride);
+#pragma unroll
+    for (int i = 1; i < N; ++i)
+      if (((bad >> i) & 1u) && chunk_tag_ok(r[i], tag)) bad &= ~(1u << i);
+  }
+}
+
+}  // namespace
+}  // namespace rnnt

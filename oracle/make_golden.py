@@ -203,6 +203,34 @@ def demo_fixture(name="ref"):
             "maxlogp": logp.max(-1).values.numpy().astype(np.float32), "margins": margins.astype(np.float32)}
 
 
+def beam_fixture(name, widths, n_utt, n_samples, audio_seed, max_iters=3):
+    """Beam search (BASELINE configs[3], [4]) -- PARITY UNPINNED IN THE REFERENCE (it has none): the algorithm is defined by
+    oracle/beam.py; what is pinned here is that definition evaluated on the imported reference's own Encoder / Predictor /
+    Joint modules (models.py:105-187)."""
+    from . import beam
+
+    cfg = weights.CONFIGS[name]
+    ref = build_reference(cfg)
+    audio = weights.make_audio(n_utt, n_samples, audio_seed)
+    out = {"config": name, "weight_seed": WEIGHT_SEED, "audio_seed": audio_seed, "n_utt": n_utt, "n_samples": n_samples,
+           "max_iters": max_iters, "widths": np.asarray(widths, dtype=np.int32)}
+    predict, joint_logits = beam.reference_callables(ref)
+    for b in range(n_utt):
+        feats = ref_features_offline(torch.from_numpy(audio[b:b + 1]), cfg)[0]
+        with torch.no_grad():
+            enc = ref.encoder(feats[None])[0]
+            greedy = ref.decode_greedy(feats, max_iters=max_iters)[0]
+        for W in widths:
+            r = beam.beam_search(enc, predict, joint_logits, ref.bos, ref.blank, W, max_iters)
+            out[f"tokens_w{W}_{b}"] = np.asarray(r.tokens, dtype=np.int32)
+            out[f"score_w{W}_{b}"] = np.float64(r.score)
+            out[f"nbest_scores_w{W}_{b}"] = np.asarray([s for _, s in r.nbest], dtype=np.float64)
+            out[f"min_margin_w{W}_{b}"] = np.float64(r.min_margin)
+            print(f"[{name} beam W={W}] utt {b}: T={enc.shape[0]} tokens={len(r.tokens)} (greedy {len(greedy)}, equal={list(greedy) == r.tokens}) "
+                  f"score={r.score:.4f} min cut margin={r.min_margin:.2e}")
+    return out
+
+
 LM_WEIGHT_SEED = 4321
 
 
@@ -296,6 +324,9 @@ def main():
         "ref_offline": lambda: offline_fixture("ref", n_utt=1, n_samples=48000, audio_seed=25),
         "cfg4_offline": lambda: offline_fixture("cfg4", n_utt=1, n_samples=32000, audio_seed=26),
         "cfg4_b8": lambda: offline_fixture("cfg4", n_utt=8, n_samples=160000, audio_seed=27),   # BASELINE configs[3] shape, >= 10 s
+        "tiny_beam": lambda: beam_fixture("tiny", widths=(1, 2, 4, 8), n_utt=3, n_samples=32000, audio_seed=41),
+        "cfg2_beam": lambda: beam_fixture("cfg2", widths=(4,), n_utt=2, n_samples=48000, audio_seed=43),
+        "cfg4_beam": lambda: beam_fixture("cfg4", widths=(4, 8), n_utt=2, n_samples=40000, audio_seed=45),
         "cfg1_demo": lambda: demo_fixture("ref"),
         "tiny_lm": lambda: lm_fixture("tiny", "tiny", n_utt=3, n_samples=40000, audio_seed=21, n_chunks=40, stream_seed=22),
         "tiny_lm_untied": lambda: lm_fixture("tiny", "tiny_untied", n_utt=2, n_samples=40000, audio_seed=31, n_chunks=30, stream_seed=32),

@@ -153,3 +153,40 @@ def test_resample_restatement_matches_torchaudio(orig):
     got = O.resample(x, orig, 16000)
     assert got.shape == ref.shape
     np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["tiny_beam", "cfg2_beam"])
+def test_beam_search_definition_on_oracle_modules_matches_reference_modules(name):
+    """Beam search is PARITY-UNPINNED in the reference (it has none).  oracle/beam.py defines it; the fixtures hold that
+    definition evaluated on the imported reference's Encoder / Predictor / Joint -- here the same function runs on the
+    oracle's restated modules."""
+    from oracle import beam
+
+    g = load_golden(name)
+    cfg, orc = _model(g)
+    audio = weights.make_audio(int(g["n_utt"]), int(g["n_samples"]), int(g["audio_seed"]))
+    predict, joint_logits = beam.oracle_callables(orc)
+    for b in range(int(g["n_utt"])):
+        feats = O.features_offline(torch.from_numpy(audio[b:b + 1]), cfg)[0]
+        enc, _ = orc.encoder(feats[None], None, "aten")
+        for W in g["widths"].tolist():
+            r = beam.beam_search(enc[0], predict, joint_logits, orc.bos, orc.blank, W, int(g["max_iters"]))
+            assert abs(r.score - float(g[f"score_w{W}_{b}"])) < 2e-3
+            if float(g[f"min_margin_w{W}_{b}"]) > 1e-4:     # away from ties the hypotheses are identical
+                assert r.tokens == g[f"tokens_w{W}_{b}"].tolist()
+
+
+def test_qint8_lm_study_fixture_is_consistent():
+    """The reference serves its LM dynamically quantised (lm.py:97, utils.py:197-210); this repo fuses the fp32 LM.
+    oracle/lm_quant_study.py ran the imported reference both ways on the cfg2_lm inputs: the recorded distance is the
+    number INTEGRATION.md quotes."""
+    import difflib
+
+    g, q = load_golden("cfg2_lm"), load_golden("cfg2_lm_qint8")
+    tot = 0
+    for b in range(int(q["n_utt"])):
+        a, c = g[f"tokens_{b}"].tolist(), q[f"tokens_qint8_{b}"].tolist()
+        same = sum(m.size for m in difflib.SequenceMatcher(a=a, b=c, autojunk=False).get_matching_blocks())
+        assert max(len(a), len(c)) - same == int(q[f"n_diff_{b}"])
+        tot += int(q[f"n_diff_{b}"])
+    assert tot + int(q["n_diff_stream"]) == int(q["n_diff_total"]) <= 2
