@@ -278,6 +278,19 @@ int32_t rnnt_b200_stream_reset(rnnt_b200_stream s, int32_t slot);
 int32_t rnnt_b200_stream_reset_state(rnnt_b200_stream s, int32_t slot);
 int32_t rnnt_b200_stream_close(rnnt_b200_stream s);
 
+
+/* ---- beam search ------------------------------------------------------------------------------- */
+
+/* Batched RNN-T beam search over encoder output (BASELINE.json configs[3], [4]).  NOT in the reference
+ * (libreasr/lib/models.py has greedy decoding only; :8 is an unused PriorityQueue import): the algorithm is the
+ * breadth-first, iteration-capped search defined by oracle/beam.py on the reference's Predictor / Joint
+ * (models.py:116-187), keeping decode_greedy's max_iters rule (models.py:369).  enc [B,T,H] device, lens_T [B] or NULL;
+ * width in [1, 8]; writes the best hypothesis of every utterance: tokens_out [B,U_cap] (U_cap >= max_iters*T),
+ * ntok_out [B], score_out [B] (fp64 log-probability, nullable) -- all device pointers.  gemm_mode 1 only. */
+int32_t rnnt_b200_decode_beam(rnnt_b200_handle h, const float* enc, const int32_t* lens_T, int32_t B, int32_t T, int32_t width,
+                              int32_t max_iters, int32_t* tokens_out, int32_t U_cap, int32_t* ntok_out, double* score_out,
+                              void* stream);
+
 /* ---- self test -------------------------------------------------------------------------------- */
 
 /* Runs the library's own GEMM (the contraction behind the LSTM gate and joint projections)

@@ -77,6 +77,9 @@ struct rnnt_b200_handle_s {
   // decode_tc2.cu (cluster split-K decode): row tiles of one cluster, TR = 32 / V/32 / 96
   uint8_t *W1p_img2 = nullptr, *W2_img2 = nullptr, *K1_img2 = nullptr, *R_img2[2] = {nullptr, nullptr};
   bool dec_tc2_ok = false;
+  // beam search (beam.cu): 256-row-tile weight images for gemm_tc.cu, built at the first call; workspaces
+  uint8_t *bm_w1p = nullptr, *bm_w2 = nullptr, *bm_k1 = nullptr, *bm_r[2] = {nullptr, nullptr};
+  DevBuf bm_state, bm_meta, bm_aimg, bm_f32;
   uint8_t* R_img[kMaxPredLayers] = {nullptr, nullptr, nullptr, nullptr};
   uint8_t* K_img[kMaxPredLayers] = {nullptr, nullptr, nullptr, nullptr};
   DevBuf dimg;                         // decode activation operand images
@@ -956,14 +959,40 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
       a.state_c_out = state_c ? state_c + (size_t)l * B * H : nullptr;
       a.barrier = h->gbar.as<unsigned int>();
       a.T = T; a.B = B; a.H = H;
+      static const int dsm_async = [] { const char* e = getenv("RNNT_DSM_ASYNC"); return e ? atoi(e) : 1; }();
+      a.dsm_async = dsm_async;
       static const bool dbg_on2 = getenv("RNNT_LSTM_DBG") != nullptr;
       unsigned long long* dbg = nullptr;
+      unsigned long long* dbg_all = nullptr;
       if (dbg_on2 && l == 0) {
         CK(cudaMalloc((void**)&dbg, (size_t)T * 32));
         CK(cudaMemset(dbg, 0, (size_t)T * 32));
+        CK(cudaMalloc((void**)&dbg_all, (size_t)pl2.grid * T * 16));
+        CK(cudaMemset(dbg_all, 0, (size_t)pl2.grid * T * 16));
         a.dbg = dbg;
+        a.dbg_all = dbg_all;
       }
       LAUNCH(1, launch_lstm_layer_tc2(a, pl2, st));
+      if (dbg_all) {
+        std::vector<unsigned long long> ha((size_t)pl2.grid * T * 2);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(ha.data(), dbg_all, ha.size() * 8, cudaMemcpyDeviceToHost));
+        cudaFree(dbg_all);
+        double sp_pub = 0, sp_red = 0, first_to_last = 0;
+        for (int t = 1; t < T; ++t) {
+          unsigned long long mn = ~0ull, mx = 0, mn2 = ~0ull, mx2 = 0;
+          for (int c2 = 0; c2 < pl2.grid; ++c2) {
+            const unsigned long long a0 = ha[((size_t)c2 * T + t) * 2], a1 = ha[((size_t)c2 * T + t) * 2 + 1];
+            mn = std::min(mn, a0); mx = std::max(mx, a0); mn2 = std::min(mn2, a1); mx2 = std::max(mx2, a1);
+          }
+          sp_pub += (double)(mx - mn); sp_red += (double)(mx2 - mn2);
+          unsigned long long pm = 0;
+          for (int c2 = 0; c2 < pl2.grid; ++c2) pm = std::max(pm, ha[((size_t)c2 * T + t - 1) * 2]);
+          first_to_last += (double)(mn2 - pm);   // last publish of step t-1 -> first CTA with complete tiles at step t
+        }
+        fprintf(stderr, "[lstm_tc2 skew] avg ns over %d CTAs: spread of publish times %.0f | spread of tiles-complete times %.0f | last publish(t-1) -> first tiles-complete(t) %.0f\n",
+                pl2.grid, sp_pub / (T - 1), sp_red / (T - 1), first_to_last / (T - 1));
+      }
       if (dbg) {
         std::vector<unsigned long long> hb((size_t)T * 4);
         CK(cudaStreamSynchronize(st));
@@ -1185,6 +1214,8 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     t.tokens = tokens_out; t.U_cap = U_cap; t.ntok = ntok_out; t.neg_logp = neg_logp_out; t.iters = iters_out;
     t.trace = trace_logp; t.trace_cap = trace_logp ? trace_cap : 0;
     t.barrier = h->gbar.as<unsigned int>();
+    static const int dsm_async2 = [] { const char* e = getenv("RNNT_DSM_ASYNC"); return e ? atoi(e) : 1; }();
+    t.dsm_async = dsm_async2;
     static const bool ddbg2 = getenv("RNNT_DEC_DBG") != nullptr;
     unsigned long long* dbg = nullptr;
     const int dcap = 8192;
@@ -1465,6 +1496,113 @@ int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, c
   CK(cudaMemcpyAsync(ntok_host, h->t_ntok.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   if (neg_logp_host) CK(cudaMemcpyAsync(neg_logp_host, h->t_nlp.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return RNNT_B200_OK;
+}
+
+
+// ---------------- beam search (beam.cu) ----------------
+namespace {
+int ensure_beam_weights(rnnt_b200_handle h, cudaStream_t st) {
+  if (h->bm_w1p) return RNNT_B200_OK;
+  const rnnt_b200_config& c = h->cfg;
+  const int H = c.hidden_sz, J = c.joint_sz, V = c.vocab_sz;
+  auto mk = [&](uint8_t** out, size_t bytes) -> cudaError_t {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    h->weight_allocs.push_back(p);
+    *out = (uint8_t*)p;
+    return cudaSuccess;
+  };
+  float* tmp = nullptr;
+  CK(cudaMalloc((void**)&tmp, (size_t)std::max(3 * H, V) * std::max(H, J) * 4));
+  CK(mk(&h->bm_w1p, gemm_tc_w_image_bytes(J, H)));
+  LAUNCH(1, launch_to_image(h->W1, 2 * H, J, H, 256, h->bm_w1p, st));                       // pred half of joint.0: first H columns
+  CK(mk(&h->bm_w2, gemm_tc_w_image_bytes(V, J)));
+  LAUNCH(1, launch_transpose(h->dw.W2_t, V, tmp, J, V, st));                                 // [J][V] -> [V][J]
+  LAUNCH(1, launch_to_image(tmp, J, V, J, 256, h->bm_w2, st));
+  for (int l = 0; l < 2; ++l) {
+    CK(mk(&h->bm_r[l], gemm_tc_w_image_bytes(3 * H, H)));
+    LAUNCH(1, launch_transpose(h->dw.Rt[l], 3 * H, tmp, H, 3 * H, st));                      // [H][3H] -> [3H interleaved][H]
+    LAUNCH(1, launch_to_image(tmp, H, 3 * H, H, 256, h->bm_r[l], st));
+  }
+  CK(mk(&h->bm_k1, gemm_tc_w_image_bytes(3 * H, H)));
+  LAUNCH(1, launch_transpose(h->dw.Kt[1], 3 * H, tmp, H, 3 * H, st));
+  LAUNCH(1, launch_to_image(tmp, H, 3 * H, H, 256, h->bm_k1, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(tmp);
+  return RNNT_B200_OK;
+}
+}  // namespace
+
+int32_t rnnt_b200_decode_beam(rnnt_b200_handle h, const float* enc, const int32_t* lens_T, int32_t B, int32_t T, int32_t width,
+                              int32_t max_iters, int32_t* tokens_out, int32_t U_cap, int32_t* ntok_out, double* score_out,
+                              void* stream) {
+  if (int r = check_ready(h)) return r;
+  const rnnt_b200_config& c = h->cfg;
+  if (!enc || !tokens_out || !ntok_out || B < 1 || T < 1) return fail(h, RNNT_B200_ERR_INVALID, "decode_beam: bad arguments");
+  if (width < 1 || width > 8 || max_iters < 1 || max_iters > 16) return fail(h, RNNT_B200_ERR_INVALID, "decode_beam: width must be in [1, 8], max_iters in [1, 16]");
+  if ((int64_t)U_cap < (int64_t)max_iters * T) return fail(h, RNNT_B200_ERR_INVALID, "decode_beam: U_cap < max_iters*T");
+  if (c.gemm_mode != RNNT_B200_GEMM_TC_FP16X3) return fail(h, RNNT_B200_ERR_INVALID, "decode_beam: needs gemm_mode 1 (tcgen05)");
+  if (c.pred_layers != 2 || c.vocab_sz > 4096 || (c.hidden_sz % 64) || (c.joint_sz % 64))
+    return fail(h, RNNT_B200_ERR_INVALID, "decode_beam: unsupported shape (two predictor layers, vocab <= 4096, H and J multiples of 64)");
+  if (c.lm_layers > 0) return fail(h, RNNT_B200_ERR_INVALID, "decode_beam: LM fusion is not part of the beam search");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = c.hidden_sz, J = c.joint_sz, V = c.vocab_sz, W = width;
+  {   // utterances are independent: bound the rows per pass
+    const int cap = std::max(1, 1024 / W);
+    if (B > cap) {
+      for (int b0 = 0; b0 < B; b0 += cap) {
+        const int nb = std::min(cap, B - b0);
+        if (int r = rnnt_b200_decode_beam(h, enc + (size_t)b0 * T * H, lens_T ? lens_T + b0 : nullptr, nb, T, width, max_iters,
+                                          tokens_out + (size_t)b0 * U_cap, U_cap, ntok_out + b0, score_out ? score_out + b0 : nullptr, stream))
+          return r;
+      }
+      return RNNT_B200_OK;
+    }
+  }
+  if (int r = ensure_beam_weights(h, st)) return r;
+  const int R = B * W, NG = max_iters + 2;
+  const int64_t M = (int64_t)B * T;
+  if (int r = ensure_decode_ws(h, B, T, 0)) return r;
+  // hoisted encoder half of the joint's first Linear (as decode_greedy)
+  CK(h->a_img.ensure(gemm_tc_a_image_bytes(M, H)));
+  LAUNCH(1, launch_to_image(enc, H, M, H, 128, h->a_img.as<uint8_t>(), st));
+  LAUNCH(1, launch_gemm_tc(h->a_img.as<uint8_t>(), h->W1e_img, h->dw.b1, h->ep.as<float>(), J, M, J, H, st));
+  // workspaces
+  const int leave_cap = W * (max_iters + 1), node_cap = 1 + T * max_iters * W + W;
+  CK(h->bm_state.ensure((size_t)3 * NG * R * H * 4));
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_hyp = take((size_t)NG * R * sizeof(BeamHyp)), o_leave = take((size_t)B * leave_cap * sizeof(BeamLeave)), o_nl = take((size_t)B * 4),
+               o_np = take((size_t)B * node_cap * 4), o_nt = take((size_t)B * node_cap * 4), o_nn = take((size_t)B * 4), o_cv = take((size_t)R * W * 4),
+               o_ci = take((size_t)R * W * 4), o_lb = take((size_t)R * 4), o_sr = take((size_t)R * 4), o_stok = take((size_t)R * 4), o_cs = take((size_t)R * 4);
+  CK(h->bm_meta.ensure(off));
+  uint8_t* mb = h->bm_meta.as<uint8_t>();
+  CK(h->bm_aimg.ensure(gemm_tc_a_image_bytes(R, std::max(H, J))));
+  size_t fo = 0;
+  auto takef = [&](size_t n) { const size_t o = fo; fo += (n + 63) & ~(size_t)63; return o; };
+  const size_t f_pp = takef((size_t)R * J), f_lg = takef((size_t)R * V), f_rec = takef((size_t)R * 3 * H), f_kin = takef((size_t)R * 3 * H), f_x1 = takef((size_t)R * H);
+  CK(h->bm_f32.ensure(fo * 4));
+  float* fb = h->bm_f32.as<float>();
+  BeamArgs a;
+  memset(&a, 0, sizeof(a));
+  a.w = h->dw; a.ep = h->ep.as<float>(); a.lens_T = lens_T; a.B = B; a.T = T; a.W = W; a.n_gen = NG;
+  a.state = h->bm_state.as<float>();
+  a.hyp = reinterpret_cast<BeamHyp*>(mb + o_hyp);
+  a.leave = reinterpret_cast<BeamLeave*>(mb + o_leave); a.leave_cap = leave_cap; a.n_leave = reinterpret_cast<int*>(mb + o_nl);
+  a.node_parent = reinterpret_cast<int*>(mb + o_np); a.node_token = reinterpret_cast<int*>(mb + o_nt); a.node_cap = node_cap;
+  a.n_nodes = reinterpret_cast<int*>(mb + o_nn);
+  a.cand_val = reinterpret_cast<float*>(mb + o_cv); a.cand_idx = reinterpret_cast<int*>(mb + o_ci); a.lp_blank = reinterpret_cast<float*>(mb + o_lb);
+  a.sel_row = reinterpret_cast<int*>(mb + o_sr); a.sel_tok = reinterpret_cast<int*>(mb + o_stok); a.copy_src = reinterpret_cast<int*>(mb + o_cs);
+  BeamBuffers bf;
+  bf.a_img = h->bm_aimg.as<uint8_t>();
+  bf.w1p_img = h->bm_w1p; bf.w2_img = h->bm_w2; bf.k1_img = h->bm_k1; bf.r_img[0] = h->bm_r[0]; bf.r_img[1] = h->bm_r[1];
+  bf.pp = fb + f_pp; bf.logits = fb + f_lg; bf.rec = fb + f_rec; bf.kin = fb + f_kin; bf.x1 = fb + f_x1;
+  int launches = 0;
+  cudaError_t e = launch_beam_search(a, bf, max_iters, tokens_out, U_cap, ntok_out, score_out, &launches, st);
+  if (e != cudaSuccess) return fail_cuda(h, e, "decode_beam");
+  h->launches += launches;
   return RNNT_B200_OK;
 }
 

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 128);
-      mbar_init(&pbar[i], 16);
+      mbar_init(&pbar[i], p.dsm_async ? 4 : 16);   // async: one arming arrive per epilogue warp; sync: 4 CTAs x 4 warps
       mbar_init(&pfree[i], 16);
     }
     mbar_init(w2full, 1);
@@ -218,13 +218,18 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
       const unsigned j = job++;
       const int ab = (int)(j & 1u);
       const unsigned n = j >> 1;
+      // async mode: every epilogue warp arms a quarter of the job's bytes (4 sources x rp rows x 32 x 4 B in total): the phase
+      // cannot complete before all four warps have entered the job, so no warp can be lapped by the barrier
+      if (p.dsm_async && lane == 0) mbar_arrive_expect_tx(&pbar[ab], (uint32_t)(D2_NB * rp * 4));
       mbar_wait(&tfull[ab], n & 1u);
       tc_fence_after();
       const int r = (M == 64) ? q * 16 + lane : q * 32 + lane;
       const bool mine = (M == 64 ? lane < 16 : true) && r < rows;
       const int dst_rank = mine ? r / rp : 0, lrow = mine ? r % rp : 0;
       const uint32_t dst = mapa(P_u32 + (uint32_t)((((ab * D2_CL + rank) * D2_NB) * D2_RP + lrow) * 4), (uint32_t)dst_rank);
-      mbar_wait_cluster(&pfree[ab], (n & 1u) ^ 1u);   // the owners have consumed the tiles of job j - 2
+      const uint32_t rbar = mapa(smem_u32(&pbar[ab]), (uint32_t)dst_rank);
+      if (p.dsm_async) mbar_wait_cluster_relaxed(&pfree[ab], (n & 1u) ^ 1u);   // the owners have consumed the tiles of job j - 2
+      else mbar_wait_cluster(&pfree[ab], (n & 1u) ^ 1u);
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         float d0[16], d1[16], d2[16];
@@ -234,22 +239,34 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
         tmem_ld16(tc + 64, d2);     // W_lo * h_hi (x 2^11)
         tmem_ld_wait();
         if (mine) {
+          if (p.dsm_async) {
 #pragma unroll
-          for (int b = 0; b < 16; ++b) st_cluster_f32(dst + (uint32_t)((hf * 16 + b) * D2_RP * 4), fmaf(d1[b] + d2[b], kLoInv, d0[b]));
+            for (int b = 0; b < 16; ++b) st_async_f32(dst + (uint32_t)((hf * 16 + b) * D2_RP * 4), fmaf(d1[b] + d2[b], kLoInv, d0[b]), rbar);
+          } else {
+#pragma unroll
+            for (int b = 0; b < 16; ++b) st_cluster_f32(dst + (uint32_t)((hf * 16 + b) * D2_RP * 4), fmaf(d1[b] + d2[b], kLoInv, d0[b]));
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[ab]);
-      __syncwarp();
-      if (lane < D2_CL) mbar_arrive_cluster(mapa(smem_u32(&pbar[ab]), (uint32_t)lane));
-      mbar_wait_cluster(&pbar[ab], n & 1u);
+      if (p.dsm_async) {
+        mbar_wait(&pbar[ab], n & 1u);
+      } else {
+        __syncwarp();
+        if (lane < D2_CL) mbar_arrive_cluster(mapa(smem_u32(&pbar[ab]), (uint32_t)lane));
+        mbar_wait_cluster(&pbar[ab], n & 1u);
+      }
       return P + (size_t)((ab * D2_CL) * D2_NB + fb) * D2_RP;   // + src * 32 * 24 ; this thread's batch row
     };
     // all reads of the partial tiles of the job just finalised are done: hand the buffers back to the senders
     auto release_job = [&]() {
       const int ab = (int)((job - 1) & 1u);
       __syncwarp();
-      if (lane < D2_CL) mbar_arrive_cluster(mapa(smem_u32(&pfree[ab]), (uint32_t)lane));
+      if (lane < D2_CL) {
+        if (p.dsm_async) mbar_arrive_cluster_relaxed(mapa(smem_u32(&pfree[ab]), (uint32_t)lane));   // (the values read are already consumed: program order suffices)
+        else mbar_arrive_cluster(mapa(smem_u32(&pfree[ab]), (uint32_t)lane));
+      }
     };
     auto sum2 = [&](const float* pr, int off, float* o, int nfl) {   // o[i] = sum over the 4 sources, nfl in {2, 4, 6}
 #pragma unroll
@@ -459,12 +476,13 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
           }
           c.emit[bb] = emit;
         }
-        named_bar_sync(1, 128);
-        if (et == 0) {
-          int ae = 0, aa = 0;
-          for (int i = 0; i < B; ++i) { ae |= c.emit[i]; aa |= c.active[i]; }
-          c.flags[0] = ae; c.flags[1] = aa;
-          mbar_arrive(ctlbar);
+        if (warp == 0) {   // B <= 32: the whole control state lives in warp 0's lanes
+          const unsigned ae = __ballot_sync(0xffffffffu, et < B && c.emit[et] != 0);
+          const unsigned aa = __ballot_sync(0xffffffffu, et < B && c.active[et] != 0);
+          if (lane == 0) {
+            c.flags[0] = ae != 0u; c.flags[1] = aa != 0u;
+            mbar_arrive(ctlbar);
+          }
         }
         named_bar_sync(1, 128);
       }
@@ -508,9 +526,10 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
       const uint32_t tag = (n >> 1) & 1u;
       const uint8_t* src = img_ptr(img, n) + slice_off + (size_t)lt * 16;
       uint4 r[16];
-      poll_chunks<16>(src, 2048, 16, tag, r);
+      poll_issue<16>(src, 16, tag, r);
 #pragma unroll
       for (int kb = 0; kb < D2_KS; ++kb, ++ga) {
+        poll_validate_kb<16>(src, kb, tag, r);
         const int s = (int)(ga % D2_AST);
         mbar_wait(&aempty[s], ((ga / D2_AST) & 1u) ^ 1u);
         uint8_t* dst = aring + (size_t)s * 8192 + (size_t)lt * 16;
@@ -624,41 +643,56 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
     }
   } else {
     // ======================================= weight streamer =======================================
+    // The streamed matrices are consumed in a fixed cyclic order whatever the emission pattern is -- (BOS run: R0, R1, K1,)
+    // then R0, W1p, R1, K1, R0, W1p, ... -- so the streamer never waits for the flags of a step to know WHAT comes next:
+    // it keeps the 3-stage ring full (K1's first 72 KB are resident before the rule that needs them has even run) and
+    // only watches the control barrier to learn when the loop ends.
     unsigned gw = 0;
-    auto stream = [&](const uint8_t* wimg, int TR) {   // this CTA's K slice of its cluster's row tile: 4 k-blocks of TR x 256 B
-      const uint32_t kbb = (uint32_t)TR * 256u;
-      const uint8_t* src = wimg + img_tile_offset(cl, rank * D2_KS, 0, D2_K / 64, TR);
-      for (int kb = 0; kb < D2_KS; ++kb, ++gw) {
-        const int s = (int)(gw % D2_WST);
-        mbar_wait(&wempty[s], ((gw / D2_WST) & 1u) ^ 1u);
+    int seq = p.use_state_in ? 3 : 0;   // position in  R0 R1 K1 | R0 W1p R1 K1 | R0 W1p R1 K1 ...
+    int kb = 0, step = 0;
+    bool done = false, finishing = false;   // finishing: the loop has ended with an emission, the last K1 still has to be delivered
+    int k1_needed = p.use_state_in ? 0 : 1, k1_issued = 0;   // K1 matrices the MMA warp will consume in total / fully streamed so far
+    while (!done) {
+      const int s = (int)(gw % D2_WST);
+      if (mbar_try_wait(&wempty[s], ((gw / D2_WST) & 1u) ^ 1u)) {
+        const int m = seq < 3 ? seq : (seq - 3) % 4;                 // which matrix
+        const uint8_t* wimg;
+        int TR;
+        if (seq < 3) { wimg = m == 0 ? p.r_img[0] : (m == 1 ? p.r_img[1] : p.k1_img); TR = 96; }
+        else if (m == 0) { wimg = p.r_img[0]; TR = 96; }
+        else if (m == 1) { wimg = p.w1p_img; TR = 32; }
+        else if (m == 2) { wimg = p.r_img[1]; TR = 96; }
+        else { wimg = p.k1_img; TR = 96; }
+        const uint32_t kbb = (uint32_t)TR * 256u;
         if (elect_one()) {
           mbar_arrive_expect_tx(&wfull[s], kbb);
-          tma_bulk_g2s(wring + (size_t)s * D2_WSTAGE, src + (size_t)kb * kbb, kbb, &wfull[s]);
+          tma_bulk_g2s(wring + (size_t)s * D2_WSTAGE, wimg + img_tile_offset(cl, rank * D2_KS + kb, 0, D2_K / 64, TR), kbb, &wfull[s]);
         }
         __syncwarp();
+        ++gw;
+        if (++kb == D2_KS) {
+          kb = 0;
+          const bool was_k1 = seq == 2 || seq == 6;
+          ++seq;
+          if (seq >= 7) seq = 3;
+          if (was_k1) ++k1_issued;
+          if (finishing && k1_issued >= k1_needed) done = true;
+        }
+      } else if (!finishing && mbar_try_wait(ctlbar, step & 1)) {
+        const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ctlack);
+        ++step;
+        if (any_emit) ++k1_needed;
+        if (!any_active) {
+          // the other roles still run the predictor of a final emission (JK1): its K1 must be delivered in full
+          if (k1_issued >= k1_needed) done = true;
+          else finishing = true;
+        }
       }
-    };
-    if (!p.use_state_in) {
-      stream(p.r_img[0], 96);
-      stream(p.r_img[1], 96);
-      stream(p.k1_img, 96);
     }
-    bool pending = true, any_upd = true;
-    for (int step = 0;; ++step) {
-      if (pending) stream(p.r_img[0], 96);
-      if (any_upd) stream(p.w1p_img, 32);
-      if (pending) { stream(p.r_img[1], 96); pending = false; }
-      mbar_wait(ctlbar, step & 1);
-      const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ctlack);
-      if (any_emit) {
-        stream(p.k1_img, 96);
-        pending = true;
-      }
-      any_upd = any_emit;
-      if (!any_active) break;
-    }
+    // every copy that was issued has to land before the CTA may go (stages fetched ahead of a loop that ended)
+    for (unsigned g = gw > D2_WST ? gw - D2_WST : 0; g < gw; ++g) mbar_wait(&wfull[g % D2_WST], (g / D2_WST) & 1u);
   }
   tc_fence_before();
   __syncthreads();

@@ -9,6 +9,8 @@
 // samples are non-zero), the CTA then writes the X = n_mels*n_stack floats of the row with
 // one coalesced pass.  Audio is read once per frame (25% of frames are
 // shared by two rows and recomputed: the kernel is FFT-, not HBM-bound).
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace rnnt {
@@ -19,7 +21,10 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-__global__ void __launch_bounds__(kFrontendMaxWarps * 32)
+// MINB = CTAs per SM the register allocation must allow (1: ~125 registers, one 10-warp CTA per SM = 16 % of the warp slots;
+// 2: <= 102 registers so that two CTAs share an SM and hide each other's FFT latency)
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 mel_stack_kernel(FrontendArgs p) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -201,10 +206,18 @@ size_t frontend_smem_bytes(int n_stack, int n_mels) {
 cudaError_t launch_mel_stack(const FrontendArgs& a, int B, cudaStream_t st) {
   if (a.n_stack > kFrontendMaxWarps) return cudaErrorInvalidValue;
   const size_t smem = frontend_smem_bytes(a.n_stack, a.n_mels);
-  cudaError_t e = cudaFuncSetAttribute(mel_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static const int occ = [] { const char* e = getenv("RNNT_FE_OCC"); return e ? atoi(e) : 2; }();
   dim3 grid(a.T_out, B);
-  mel_stack_kernel<<<grid, a.n_stack * 32, smem, st>>>(a);
+  cudaError_t e;
+  if (occ >= 2 && a.n_stack * 32 <= 320) {
+    e = cudaFuncSetAttribute(mel_stack_kernel<320, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mel_stack_kernel<320, 2><<<grid, a.n_stack * 32, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(mel_stack_kernel<kFrontendMaxWarps * 32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mel_stack_kernel<kFrontendMaxWarps * 32, 1><<<grid, a.n_stack * 32, smem, st>>>(a);
+  }
   return cudaGetLastError();
 }
 

@@ -107,8 +107,10 @@ struct LstmTc2Args {
   float* state_h_out; float* state_c_out;
   unsigned int* barrier;     // one launch-start counter, zero at launch
   unsigned long long* dbg;   // optional [T][4] globaltimer stamps of CTA 0, or nullptr
+  unsigned long long* dbg_all;   // optional [grid][T][2] (publish, tiles complete) stamps of every CTA: skew diagnosis
   int T, B, H;
   int KS, KB;                // filled from the plan by the launcher
+  int dsm_async;             // partial tiles through st.async + complete_tx (1) or st.shared::cluster + release arrive (0)
 };
 cudaError_t configure_lstm_tc2();
 bool lstm_tc2_plan(int H, int B, int sms, LstmTc2Plan* pl);
@@ -294,6 +296,7 @@ struct DecodeTc2Args {
   int32_t* tokens; int U_cap; int32_t* ntok; double* neg_logp; uint8_t* iters; float* trace; int trace_cap;
   unsigned int* barrier;           // launch-start counter, zero at launch
   unsigned long long* dbg; int dbg_cap;
+  int dsm_async;                   // partial tiles through st.async + complete_tx (1) or st.shared::cluster + release arrive (0)
 };
 cudaError_t configure_decode_tc2();
 bool decode_tc2_plan(int H, int J, int V, int Lp, int B, int sms, int lm_layers);
@@ -301,6 +304,30 @@ size_t decode_tc2_image_bytes();   // one buffer of one activation image
 size_t decode_tc2_keys_bytes();
 int decode_tc2_part_ctas();
 cudaError_t launch_decode_tc2(const DecodeTc2Args& a, cudaStream_t st);
+
+// ---------------- beam.cu (batched RNN-T beam search; algorithm defined by oracle/beam.py) ----------------
+struct BeamHyp { double score; unsigned long long hash; int node; int valid; };
+struct BeamLeave { double score; unsigned long long hash; int node; int gen; int slot; };
+struct BeamArgs {
+  DecodeWeights w;
+  const float* ep;             // [B][T][J] encoder half of the joint incl. b1
+  const int32_t* lens_T;
+  int B, T, W, n_gen;          // n_gen = max_iters + 2 generation buffers
+  float* state;                // [3 (h0, h1, g)][n_gen][B*W][H]
+  BeamHyp* hyp;                // [n_gen][B*W]
+  BeamLeave* leave; int leave_cap; int* n_leave;        // [B][leave_cap], [B]
+  int* node_parent; int* node_token; int node_cap; int* n_nodes;   // per-utterance token trie
+  float* cand_val; int* cand_idx; float* lp_blank;      // [B*W][W], [B*W][W], [B*W]
+  int* sel_row; int* sel_tok;  // [B*W] parent row / token of the rows of the generation being built
+  int* copy_src;               // [B*W]
+};
+struct BeamBuffers {
+  uint8_t* a_img;              // activation operand image (128-row tiles) for up to B*W rows x max(H, J)
+  const uint8_t *w1p_img, *w2_img, *k1_img, *r_img[2];   // 256-row-tile weight images (gemm_tc.cu)
+  float *pp, *logits, *rec, *kin, *x1;
+};
+cudaError_t launch_beam_search(const BeamArgs& a, const BeamBuffers& bf, int max_iters, int32_t* tokens, int U_cap, int32_t* ntok, double* score,
+                               int* launches, cudaStream_t st);
 
 // standalone predictor step / joint (same phase code, one launch per phase)
 struct PredictArgs {

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 128);
-      mbar_init(&pbar[i], L2_CL);
+      mbar_init(&pbar[i], L2_CL);   // sync mode: one remote arrive per source CTA; async mode: one arming arrive per epilogue warp
     }
     mbar_init(wfull, 1);
     fence_mbar_init();
@@ -132,6 +132,9 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
         xv0 = xr[0];
         xv1 = xr[1];
       }
+      // async mode: every epilogue warp arms a quarter of the step's bytes, so the phase cannot complete (and the barrier cannot
+      // run a phase ahead of a lagging warp) before all four warps have entered the step
+      if (p.dsm_async && lane == 0) mbar_arrive_expect_tx(&pbar[ab], (uint32_t)(L2_NB * 32 * 4));
       mbar_wait(&tfull[ab], (t >> 1) & 1);
       tc_fence_after();
       if (p.dbg && blockIdx.x == 0 && et == 0) p.dbg[t * 4 + 1] = gtimer();
@@ -146,13 +149,24 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
         mbar_arrive(&tempty[ab]);
         // my gate row's 32 batch values -> CTA q's partial tile [ab][src = rank][b][row = lane]
         const uint32_t dst = mapa(P_u32 + (uint32_t)(((ab * L2_CL + rank) * L2_NB) * 128 + lane * 4), (uint32_t)q);
+        if (p.dsm_async) {   // the bytes are counted on the owner's mbarrier: no fence on either side
+          const uint32_t rbar = mapa(smem_u32(&pbar[ab]), (uint32_t)q);
 #pragma unroll
-        for (int b = 0; b < 32; ++b) st_cluster_f32(dst + (uint32_t)b * 128u, fmaf(d1[b] + d2[b], kLoInv, d0[b]));
+          for (int b = 0; b < 32; ++b) st_async_f32(dst + (uint32_t)b * 128u, fmaf(d1[b] + d2[b], kLoInv, d0[b]), rbar);
+        } else {
+#pragma unroll
+          for (int b = 0; b < 32; ++b) st_cluster_f32(dst + (uint32_t)b * 128u, fmaf(d1[b] + d2[b], kLoInv, d0[b]));
+        }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&pbar[ab]), (uint32_t)q));
-      mbar_wait_cluster(&pbar[ab], (t >> 1) & 1);
+      if (p.dsm_async) {
+        mbar_wait(&pbar[ab], (t >> 1) & 1);
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&pbar[ab]), (uint32_t)q));
+        mbar_wait_cluster(&pbar[ab], (t >> 1) & 1);
+      }
       if (p.dbg && blockIdx.x == 0 && et == 0) p.dbg[t * 4 + 2] = gtimer();
+      if (p.dbg_all && et == 0) p.dbg_all[((size_t)blockIdx.x * T + t) * 2 + 1] = gtimer();
       {
         float acc[8];
         const float* pr = P + (size_t)((ab * L2_CL) * L2_NB + fb) * 32 + fw * 8;
@@ -184,6 +198,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
       // h_t gates the next step: publish first; the BatchNorm(h_t) outputs follow off the critical path
       publish(p.x_img[(t + 1) & 1], h[0], h[1], (uint32_t)(((t + 1) >> 1) & 1));
       if (p.dbg && blockIdx.x == 0 && et == 0) p.dbg[t * 4 + 3] = gtimer();
+      if (p.dbg_all && et == 0) p.dbg_all[((size_t)blockIdx.x * T + t) * 2] = gtimer();
       if (valid) {
         const float y0 = h[0] * bsc[0] + bsh[0], y1 = h[1] * bsc[1] + bsh[1];
         if (p.y) *reinterpret_cast<float2*>(p.y + row * H + unit) = make_float2(y0, y1);
@@ -214,10 +229,11 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
       const uint32_t tag = (uint32_t)((t >> 1) & 1);
       const uint8_t* src = p.x_img[t & 1] + slice_off + (size_t)lt * 16;
       uint4 r[L2_MAX_KS * 4];
-      poll_chunks<L2_MAX_KS * 4>(src, 2048, NL, tag, r);
+      poll_issue<L2_MAX_KS * 4>(src, NL, tag, r);
 #pragma unroll
       for (int kb = 0; kb < L2_MAX_KS; ++kb) {
         if (kb < KS) {
+          poll_validate_kb<L2_MAX_KS * 4>(src, kb, tag, r);
           if (t > 0) mbar_wait(&hempty[kb], (t - 1) & 1);   // the MMAs of step t-1 have finished reading this k-block
 #pragma unroll
           for (int j = 0; j < 4; ++j) {

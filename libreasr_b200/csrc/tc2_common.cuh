@@ -98,31 +98,55 @@ __device__ __forceinline__ void split_tag(float x, bool tagged, uint32_t tag, ui
 __device__ __forceinline__ bool chunk_tag_ok(const uint4& r, uint32_t tag) { return ((r.w >> 16) & 1u) == tag; }
 __device__ __forceinline__ void chunk_strip_tag(uint4& r) { r.w &= 0xFFFEFFFFu; }
 
-// Polls N tagged chunks (src + i * stride, i < n) until every one carries `tag`.  The warp first spins, converged, on
-// chunk 0 only (one coalesced request per round trip: nothing else can be valid before it is worth looking), then
-// issues all the remaining loads back to back and re-issues only the stale ones, again in parallel rounds -- a
-// serial "load, check, reload" chain would cost one L2 round trip per chunk.
+// Tagged-chunk fetch of NKB k-blocks x 4 chunks per thread (chunk i at src + i * 2048).  The warp spins, converged, on
+// chunk 0 until ANY lane sees the new tag (one coalesced request per round trip: nothing is worth loading earlier), then
+// issues every load back to back; `poll_validate_kb` afterwards re-reads only the stale chunks of one k-block, in
+// parallel rounds, so the first k-blocks can be handed to the MMA while the stragglers of the later ones are in flight.
 template <int N>
-__device__ __forceinline__ void poll_chunks(const uint8_t* src, size_t stride, int n, uint32_t tag, uint4 (&r)[N]) {
+__device__ __forceinline__ void poll_issue(const uint8_t* src, int n, uint32_t tag, uint4 (&r)[N]) {
   for (;;) {
     r[0] = ld_relaxed_v4(src);
-    if (__all_sync(0xffffffffu, chunk_tag_ok(r[0], tag))) break;
+    if (__any_sync(0xffffffffu, chunk_tag_ok(r[0], tag))) break;
   }
 #pragma unroll
   for (int i = 1; i < N; ++i)
-    if (i < n) r[i] = ld_relaxed_v4(src + (size_t)i * stride);
-  uint32_t bad = 0;
+    if (i < n) r[i] = ld_relaxed_v4(src + (size_t)i * 2048);
+}
+template <int N>
+__device__ __forceinline__ void poll_validate_kb(const uint8_t* src, int kb, uint32_t tag, uint4 (&r)[N]) {
+  for (;;) {
+    uint32_t bad = 0;
 #pragma unroll
-  for (int i = 1; i < N; ++i)
-    if (i < n && !chunk_tag_ok(r[i], tag)) bad |= 1u << i;
-  while (__any_sync(0xffffffffu, bad != 0u)) {
+    for (int j = 0; j < 4; ++j)
+      if (!chunk_tag_ok(r[kb * 4 + j], tag)) bad |= 1u << j;
+    if (!__any_sync(0xffffffffu, bad != 0u)) break;
 #pragma unroll
-    for (int i = 1; i < N; ++i)
-      if ((bad >> i) & 1u) r[i] = ld_relaxed_v4(src + (size_t)i * stride);
-#pragma unroll
-    for (int i = 1; i < N; ++i)
-      if (((bad >> i) & 1u) && chunk_tag_ok(r[i], tag)) bad &= ~(1u << i);
+    for (int j = 0; j < 4; ++j)
+      if ((bad >> j) & 1u) r[kb * 4 + j] = ld_relaxed_v4(src + (size_t)(kb * 4 + j) * 2048);
   }
+}
+
+// ---- distributed-shared-memory partial tiles without fences ----
+// st.async delivers the value and counts its bytes on the RECEIVER's mbarrier (complete_tx), like a TMA copy: the
+// receiver arms the barrier with the byte count of a job (arrive.expect_tx) and waits for the phase -- no release fence
+// on the sender (mbarrier.arrive.release.cluster lowers to MEMBAR.ALL.GPU), no acquire + L1 invalidate on the receiver.
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(remote_addr), "f"(v), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
 }
 
 }  // namespace

@@ -314,6 +314,30 @@ class Engine:
                 "state": (ph, po) if ph is not None else None}
 
     # ---- whole path --------------------------------------------------------------------------------
+    def decode_beam(self, enc, lens_T=None, width=4, max_iters=3):
+        """Beam search over encoder output [B,T,H] (not in the reference; algorithm: oracle/beam.py).  Returns the best
+        hypothesis per utterance: dict(tokens [B,U], ntok [B], score [B] fp64 log-probability)."""
+        enc = self._f32(enc)
+        B, T, H = enc.shape
+        U = max_iters * max(T, 1)
+        lens_T = self._i32(lens_T)
+        tokens = torch.zeros(B, U, dtype=torch.int32, device=self.device)
+        ntok = torch.zeros(B, dtype=torch.int32, device=self.device)
+        score = torch.zeros(B, dtype=torch.float64, device=self.device)
+        self._ck(self.lib.rnnt_b200_decode_beam(self._h, _ptr(enc), _ptr(lens_T), B, T, int(width), int(max_iters), _ptr(tokens), U,
+                                                _ptr(ntok), _ptr(score), self._stream()))
+        return {"tokens": tokens, "ntok": ntok, "score": score}
+
+    def transcribe_beam(self, audio, lens=None, width=4, max_iters=3):
+        """Device-resident audio [B, n] -> features -> encoder -> beam search."""
+        audio = self._f32(audio)
+        feats = self.features(audio, lens)
+        lens_T = None
+        if lens is not None:
+            lens_T = torch.clamp((self._i32(lens).to(torch.int64) // self.cfg.hop_length + 1 - self.cfg.n_stack) // self.cfg.downsample + 1, min=0).to(torch.int32)
+        enc, _ = self.encode(feats, lens_T)
+        return self.decode_beam(enc, lens_T, width, max_iters)
+
     def transcribe(self, audio, lens=None, max_iters=3):
         """Device-resident audio [B, n] -> dict(tokens, ntok, neg_logp, iters) device tensors."""
         audio = self._f32(audio)

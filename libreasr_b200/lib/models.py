@@ -300,6 +300,20 @@ class Transducer(nn.Module):
             extra["outs"] = [o[None, None, None] for o in r["trace"][0, :n_eval]]
         return self.lang.denumericalize(y_seq), float(r["neg_logp"][0]), metrics, extra
 
+    def decode_beam(self, x, width=4, max_iters=3):
+        """Beam search for one utterance x [T,X(,1)] -> (text, score).  The reference has no beam search (models.py:8 is
+        an unused PriorityQueue import); the algorithm is the one defined in oracle/beam.py on the reference's own
+        Predictor / Joint, keeping ``decode_greedy``'s max_iters rule."""
+        eng = self.engine()
+        x = x.to(eng.device, torch.float32)
+        if x.dim() == 2:
+            x = x[:, :, None]
+        x = x[None].reshape(1, x.size(0), -1)
+        enc, _ = eng.encode(x)
+        r = eng.decode_beam(enc, None, width=width, max_iters=max_iters)
+        y_seq = tokens_to_lists(r["tokens"], r["ntok"])[0]
+        return self.lang.denumericalize(y_seq), float(r["score"][0])
+
     def transcribe_stream(self, stream, denumericalizer, max_iters=10, alpha=0.3, theta=1.0):
         """Generator over chunks of shape [T_c, X(,1)] or None (models.py:457-577): yields
         (all tokens so far, denumericalizer(tokens of this chunk), reset_fn).  One LM fuser lives for the whole
