@@ -1187,7 +1187,8 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
       decode_tc2_plan(H, J, c.vocab_sz, c.pred_layers, B, h->sm_count, c.lm_layers)) {
     // cluster split-K decode (decode_tc2.cu): up to 32 utterances per launch
     const size_t one = decode_tc2_image_bytes();
-    CK(h->dimg.ensure(one * 10));
+    const int nimg = decode_tc2_images();
+    CK(h->dimg.ensure(one * 2 * nimg));
     const int max_steps = max_iters * T + 2;
     const int nBp = decode_tc2_part_ctas();
     CK(h->dpart.ensure((size_t)max_steps * nBp * 32 * 8));
@@ -1204,7 +1205,9 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     memset(&t, 0, sizeof(t));
     t.w = h->dw;
     t.w1p_img = h->W1p_img2; t.w2_img = h->W2_img2; t.k1_img = h->K1_img2; t.r_img[0] = h->R_img2[0]; t.r_img[1] = h->R_img2[1];
-    for (int i = 0; i < 5; ++i) t.img[i] = h->dimg.as<uint8_t>() + (size_t)(2 * i) * one;
+    for (int i = 0; i < nimg; ++i) t.img[i] = h->dimg.as<uint8_t>() + (size_t)(2 * i) * one;
+    static const int n_spec = [] { const char* e = getenv("RNNT_DEC_SPEC"); return e ? atoi(e) : 2; }();
+    t.n_spec = std::max(1, std::min(n_spec, decode_tc2_max_spec()));
     t.img_stride = one;
     t.keys = h->dkeys.as<unsigned long long>();
     t.n_eval = reinterpret_cast<int*>(h->dkeys.as<uint8_t>() + decode_tc2_keys_bytes());

@@ -49,14 +49,15 @@ constexpr int D2_WSTAGE = 24576;
 constexpr int D2_RP = 24;         // row stride of a partial tile (max rows finalised per CTA)
 constexpr int D2_K = 1024;        // H = J
 
-enum { IMG_G = 0, IMG_Z = 1, IMG_X = 2, IMG_H0 = 3, IMG_H1 = 4, IMG_N = 5 };
+constexpr int D2_MAXS = 2;        // joint evaluations per utterance and lock-step (speculative look-ahead frames)
+enum { IMG_G = 0, IMG_X = 1, IMG_H0 = 2, IMG_H1 = 3, IMG_Z0 = 4, IMG_N = 4 + D2_MAXS };
 enum { JOB_A = 0, JOB_B = 1, JOB_K1 = 2, JOB_R0 = 3, JOB_R1 = 4 };
 
 struct Ctrl2 {
   int t[D2_NB], it[D2_NB], ntok[D2_NB], tok[D2_NB], n_eval[D2_NB], len[D2_NB], am[D2_NB];
   unsigned char active[D2_NB], emit[D2_NB];
   int flags[2];                                  // any_emit, any_active of the current step
-  unsigned long long kred[8][D2_NB];             // partial maxima of the key table
+  unsigned long long kred[D2_MAXS][8][D2_NB];    // partial maxima of the key table, per look-ahead frame
 };
 
 __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args p) {
@@ -156,7 +157,10 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
       gval[0] = p.pred_out[(size_t)fb * H + unit];
       gval[1] = p.pred_out[(size_t)fb * H + unit + 1];
     }
-    unsigned nw[IMG_N] = {0, 0, 0, 0, 0};   // writes issued so far per image
+    unsigned nw[IMG_N];                     // writes issued so far per image
+#pragma unroll
+    for (int i = 0; i < IMG_N; ++i) nw[i] = 0;
+    const int NS = p.n_spec;
     unsigned nkeys = 0;                     // key-table writes so far
     // 8 consecutive k (the two values of the 4 lanes of a batch row) -> one hi and one lo 16-byte chunk, tagged
     auto publish = [&](int img, float v0, float v1) {
@@ -188,15 +192,15 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
         st_relaxed_v4(p.img[IMG_H0] + p.img_stride + off, one.x, one.y, one.z, one.w);
         st_relaxed_v4(p.img[IMG_H1] + p.img_stride + off, one.x, one.y, one.z, one.w);
         for (int bf = 0; bf < 2; ++bf) {
-          st_relaxed_v4(p.img[IMG_Z] + (size_t)bf * p.img_stride + off, one.x, one.y, one.z, one.w);
           st_relaxed_v4(p.img[IMG_X] + (size_t)bf * p.img_stride + off, one.x, one.y, one.z, one.w);
+#pragma unroll
+          for (int zs = 0; zs < D2_MAXS; ++zs)
+            if (zs < NS) st_relaxed_v4(p.img[IMG_Z0 + zs] + (size_t)bf * p.img_stride + off, one.x, one.y, one.z, one.w);
         }
       }
-      // key table [2][128 cta][32 b] u64: tag 1 (bit 0) everywhere
-      if (et < 32) {
-        p.keys[(size_t)cta * D2_NB + et] = 1ull;
-        p.keys[(size_t)(D2_G + cta) * D2_NB + et] = 1ull;
-      }
+      // key table [2][NS][128 cta][32 b] u64: tag 1 (bit 0) everywhere
+      if (et < 32)
+        for (int i = 0; i < 2 * NS; ++i) p.keys[((size_t)i * D2_G + cta) * D2_NB + et] = 1ull;
       __threadfence();
       named_bar_sync(1, 128);
       if (et == 0) {
@@ -341,115 +345,144 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
     for (int step = 0;; ++step) {
       if (pending) epi_rec(0);
       // ---------------- phase A: pp and z ----------------
+      // Look-ahead: z is formed for the current frame AND the next NS - 1 frames of every utterance (same predictor
+      // state: valid as long as the earlier evaluations of this step come out blank, which ~75 % do), so the rule below can
+      // consume up to NS joint evaluations per lock-step.  Every evaluation is the one the sequential loop would make.
       {
         const bool act = bvalid && c.active[fb] != 0;
-        float2 epv = make_float2(0.f, 0.f);
-        if (act) epv = *reinterpret_cast<const float2*>(p.ep + ((size_t)fb * T + c.t[fb]) * J + unit);
+        float2 epv[D2_MAXS];
+        bool vs[D2_MAXS];
+#pragma unroll
+        for (int zs = 0; zs < D2_MAXS; ++zs) {
+          vs[zs] = zs < NS && act && c.t[fb] + zs < c.len[fb];
+          epv[zs] = make_float2(0.f, 0.f);
+          if (vs[zs]) epv[zs] = *reinterpret_cast<const float2*>(p.ep + ((size_t)fb * T + c.t[fb] + zs) * J + unit);
+        }
         if (any_upd) {
           const float* pr = reduce_job(64, 32, 8);
           sum2(pr, fw * 2, pp, 2);
           release_job();
         }
-        publish(IMG_Z, act ? tanhf(pp[0] + epv.x) : 0.f, act ? tanhf(pp[1] + epv.y) : 0.f);
+#pragma unroll
+        for (int zs = 0; zs < D2_MAXS; ++zs)
+          if (zs < NS) publish(IMG_Z0 + zs, vs[zs] ? tanhf(pp[0] + epv[zs].x) : 0.f, vs[zs] ? tanhf(pp[1] + epv[zs].y) : 0.f);
       }
       stamp(0);
       if (pending) { epi_rec(1); pending = false; }
-      // ---------------- phase B: logits of this CTA's vocabulary rows, arg max exchange ----------------
+      // ---------------- phase B: logits of this CTA's vocabulary rows (one job per look-ahead frame), arg max exchange ----------------
       {
         float b2v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) b2v[i] = (i < rptB) ? w.b2[vB0 + fw * rptB + i] : 0.f;
-        const float* pr = reduce_job(64, RB, rpB);
-        float lv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int s = 0; s < D2_CL; ++s) {
-          const float* ps = pr + (size_t)s * D2_NB * D2_RP + fw * rptB;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < rptB) lv[i] = (s == 0 ? b2v[i] : lv[i]) + ps[i];
-        }
-        release_job();
-        const bool act = bvalid && c.active[fb] != 0;
-        float m = -INFINITY, s = 0.f;
-        int am = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < rptB && lv[i] > m) { m = lv[i]; am = vB0 + fw * rptB + i; }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < rptB) s += expf(lv[i] - m);
-        if (p.trace && act && c.n_eval[fb] < p.trace_cap) {
-          float* tr = p.trace + ((size_t)fb * p.trace_cap + c.n_eval[fb]) * V + vB0 + fw * rptB;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < rptB) tr[i] = lv[i];
-        }
-        // the 4 lanes of a batch row hold ascending vocabulary slices: strict > keeps the first maximum (torch.max)
-#pragma unroll
-        for (int o = 1; o < 4; o <<= 1) {
-          const float m2 = __shfl_down_sync(0xffffffffu, m, o), s2 = __shfl_down_sync(0xffffffffu, s, o);
-          const int am2 = __shfl_down_sync(0xffffffffu, am, o);
-          if ((fw & (2 * o - 1)) == 0) {
-            if (m2 > m) { s = s * expf(m - m2) + s2; m = m2; am = am2; }
-            else s += s2 * expf(m2 - m);
-          }
-        }
+        unsigned long long keys[D2_MAXS];
         const unsigned nk = nkeys++;
         const uint32_t ktag = (nk >> 1) & 1u;
-        unsigned long long key = (unsigned long long)ktag;
-        if (act && step < p.max_steps) {
-          unsigned u = __float_as_uint(m);
-          u ^= (u & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u;
-          key = ((unsigned long long)u << 32) | (unsigned long long)(((0x7FFFFFFFu - (unsigned)am) << 1) | ktag);
-          if (fw == 0) *reinterpret_cast<float2*>(p.part + (((size_t)step * D2_G + cta) * D2_NB + fb) * 2) = make_float2(m, s);
+#pragma unroll
+        for (int zs = 0; zs < D2_MAXS; ++zs) {
+          keys[zs] = (unsigned long long)ktag;
+          if (zs < NS) {
+            const float* pr = reduce_job(64, RB, rpB);
+            float lv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int sr = 0; sr < D2_CL; ++sr) {
+              const float* ps = pr + (size_t)sr * D2_NB * D2_RP + fw * rptB;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i < rptB) lv[i] = (sr == 0 ? b2v[i] : lv[i]) + ps[i];
+            }
+            release_job();
+            const bool vz = bvalid && c.active[fb] != 0 && c.t[fb] + zs < c.len[fb];
+            const int e = c.n_eval[fb] + zs;     // index of this evaluation in the utterance's sequence
+            float m = -INFINITY, sx = 0.f;
+            int am = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < rptB && lv[i] > m) { m = lv[i]; am = vB0 + fw * rptB + i; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < rptB) sx += expf(lv[i] - m);
+            if (p.trace && vz && e < p.trace_cap) {
+              float* tr = p.trace + ((size_t)fb * p.trace_cap + e) * V + vB0 + fw * rptB;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i < rptB) tr[i] = lv[i];
+            }
+            // the 4 lanes of a batch row hold ascending vocabulary slices: strict > keeps the first maximum (torch.max)
+#pragma unroll
+            for (int o = 1; o < 4; o <<= 1) {
+              const float m2 = __shfl_down_sync(0xffffffffu, m, o), s2 = __shfl_down_sync(0xffffffffu, sx, o);
+              const int am2 = __shfl_down_sync(0xffffffffu, am, o);
+              if ((fw & (2 * o - 1)) == 0) {
+                if (m2 > m) { sx = sx * expf(m - m2) + s2; m = m2; am = am2; }
+                else sx += s2 * expf(m2 - m);
+              }
+            }
+            if (vz && e < p.max_steps) {
+              unsigned u = __float_as_uint(m);
+              u ^= (u & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u;
+              keys[zs] = ((unsigned long long)u << 32) | (unsigned long long)(((0x7FFFFFFFu - (unsigned)am) << 1) | ktag);
+              if (fw == 0) *reinterpret_cast<float2*>(p.part + (((size_t)e * D2_G + cta) * D2_NB + fb) * 2) = make_float2(m, sx);
+            }
+          }
         }
-        const unsigned long long key2 = __shfl_down_sync(0xffffffffu, key, 4);   // batch row fb + 1 (same warp: fb even)
-        unsigned long long* ktab = p.keys + (size_t)(nk & 1u) * D2_G * D2_NB;
-        if (fw == 0 && (fb & 1) == 0)
-          st_relaxed_v4(ktab + (size_t)cta * D2_NB + fb, (uint32_t)key, (uint32_t)(key >> 32), (uint32_t)key2, (uint32_t)(key2 >> 32));
+        unsigned long long* ktab = p.keys + (size_t)(nk & 1u) * NS * D2_G * D2_NB;
+#pragma unroll
+        for (int zs = 0; zs < D2_MAXS; ++zs) {
+          if (zs < NS) {
+            const unsigned long long key2 = __shfl_down_sync(0xffffffffu, keys[zs], 4);   // batch row fb + 1 (same warp: fb even)
+            if (fw == 0 && (fb & 1) == 0)
+              st_relaxed_v4(ktab + ((size_t)zs * D2_G + cta) * D2_NB + fb, (uint32_t)keys[zs], (uint32_t)(keys[zs] >> 32), (uint32_t)key2, (uint32_t)(key2 >> 32));
+          }
+        }
         stamp(1);
-        // every CTA reduces the whole table: thread -> batch pair et % 16, CTAs [16 (et / 16), +16)
+        // every CTA reduces the whole table: thread -> batch pair et % 16, CTAs [16 (et / 16), +16), one look-ahead frame after the other
         {
           const int bp = et & 15, g = et >> 4;
           const unsigned long long* src = ktab + (size_t)(g * 16) * D2_NB + 2 * bp;
-          uint4 r[16];
+#pragma unroll 1
+          for (int zs = 0; zs < NS; ++zs) {
+            const unsigned long long* sz = src + (size_t)zs * D2_G * D2_NB;
+            uint4 r[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = ld_relaxed_v4(src + (size_t)i * D2_NB);
-          uint32_t bad = 0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if ((r[i].x & 1u) != ktag || (r[i].z & 1u) != ktag) bad |= 1u << i;
-          while (__any_sync(0xffffffffu, bad != 0u)) {   // stale entries are re-read in parallel rounds
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if ((bad >> i) & 1u) r[i] = ld_relaxed_v4(src + (size_t)i * D2_NB);
+            for (int i = 0; i < 16; ++i) r[i] = ld_relaxed_v4(sz + (size_t)i * D2_NB);
+            uint32_t bad = 0;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (((bad >> i) & 1u) && (r[i].x & 1u) == ktag && (r[i].z & 1u) == ktag) bad &= ~(1u << i);
-          }
-          unsigned long long k0 = 0ull, k1 = 0ull;
+              if ((r[i].x & 1u) != ktag || (r[i].z & 1u) != ktag) bad |= 1u << i;
+            while (__any_sync(0xffffffffu, bad != 0u)) {   // stale entries are re-read in parallel rounds
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const unsigned long long a = ((unsigned long long)r[i].y << 32) | r[i].x, b = ((unsigned long long)r[i].w << 32) | r[i].z;
-            k0 = a > k0 ? a : k0;
-            k1 = b > k1 ? b : k1;
+              for (int i = 0; i < 16; ++i)
+                if ((bad >> i) & 1u) r[i] = ld_relaxed_v4(sz + (size_t)i * D2_NB);
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (((bad >> i) & 1u) && (r[i].x & 1u) == ktag && (r[i].z & 1u) == ktag) bad &= ~(1u << i);
+            }
+            unsigned long long k0 = 0ull, k1 = 0ull;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const unsigned long long a = ((unsigned long long)r[i].y << 32) | r[i].x, b = ((unsigned long long)r[i].w << 32) | r[i].z;
+              k0 = a > k0 ? a : k0;
+              k1 = b > k1 ? b : k1;
+            }
+            c.kred[zs][g][2 * bp] = k0;
+            c.kred[zs][g][2 * bp + 1] = k1;
           }
-          c.kred[g][2 * bp] = k0;
-          c.kred[g][2 * bp + 1] = k1;
         }
         named_bar_sync(1, 128);
         stamp(2);
       }
       // ---------------- R: greedy rule (models.py:408-437), identical in every CTA ----------------
+      // consumes the look-ahead evaluations in order: a blank moves on to the next frame (whose evaluation is already there),
+      // the first non-blank ends the step for the utterance (its predictor state changes)
       {
         if (step > 0) mbar_wait(ctlack, (step - 1) & 1);
         if (et < B) {
           const int bb = et;
           unsigned char emit = 0;
-          if (c.active[bb]) {
+          for (int zs = 0; zs < NS && c.active[bb] && !emit; ++zs) {
             unsigned long long key = 0ull;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) key = c.kred[g][bb] > key ? c.kred[g][bb] : key;
+            for (int g = 0; g < 8; ++g) key = c.kred[zs][g][bb] > key ? c.kred[zs][g][bb] : key;
             const int am2 = (int)(0x7FFFFFFFu - (unsigned)((key & 0xFFFFFFFFull) >> 1));
             const int t = c.t[bb];
             c.n_eval[bb] += 1;
@@ -513,7 +546,10 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
   } else if (warp < 8) {
     // ======================================= loaders =======================================
     const int lt = (warp - 4) * 32 + lane;
-    unsigned nw[IMG_N] = {1, 0, 0, 1, 1};   // writes that precede the point reached in the job sequence
+    unsigned nw[IMG_N];                     // writes that precede the point reached in the job sequence
+#pragma unroll
+    for (int i = 0; i < IMG_N; ++i) nw[i] = (i == IMG_G || i == IMG_H0 || i == IMG_H1) ? 1u : 0u;
+    const int NS = p.n_spec;
     unsigned ga = 0;                        // k-block stages filled so far
     if (lane == 0) {
       while (ld_acquire_u32(p.barrier) < (unsigned)D2_G) {
@@ -553,9 +589,13 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
     for (int step = 0;; ++step) {
       if (pending) fetch(IMG_H0);
       if (any_upd) fetch(IMG_G);
-      nw[IMG_Z]++;
+#pragma unroll
+      for (int zs = 0; zs < D2_MAXS; ++zs)
+        if (zs < NS) nw[IMG_Z0 + zs]++;
       if (pending) { fetch(IMG_H1); pending = false; }
-      fetch(IMG_Z);
+#pragma unroll
+      for (int zs = 0; zs < D2_MAXS; ++zs)
+        if (zs < NS) fetch(IMG_Z0 + zs);
       mbar_wait(ctlbar, step & 1);
       const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
       __syncwarp();
@@ -629,7 +669,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
       if (pending) run_job(128, 96, false);
       if (any_upd) run_job(64, 32, false);
       if (pending) { run_job(128, 96, false); pending = false; }
-      run_job(64, RB, true);
+      for (int zs = 0; zs < p.n_spec; ++zs) run_job(64, RB, true);
       mbar_wait(ctlbar, step & 1);
       const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
       __syncwarp();
@@ -737,7 +777,9 @@ bool decode_tc2_plan(int H, int J, int V, int Lp, int B, int sms, int lm_layers)
 }
 
 size_t decode_tc2_image_bytes() { return (size_t)(D2_K / 64) * 8192; }        // one buffer of one activation image
-size_t decode_tc2_keys_bytes() { return (size_t)2 * D2_G * D2_NB * 8; }
+size_t decode_tc2_keys_bytes() { return (size_t)2 * D2_MAXS * D2_G * D2_NB * 8; }
+int decode_tc2_images() { return IMG_N; }
+int decode_tc2_max_spec() { return D2_MAXS; }
 int decode_tc2_part_ctas() { return D2_G; }
 
 cudaError_t launch_decode_tc2(const DecodeTc2Args& a, cudaStream_t st) {

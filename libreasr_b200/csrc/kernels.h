@@ -282,7 +282,8 @@ struct DecodeTc2Args {
   const uint8_t* w2_img;
   const uint8_t* k1_img;
   const uint8_t* r_img[2];
-  uint8_t* img[5];                 // tagged activation images g, z, BN(h0'), h0', h1': 2 buffers of img_stride bytes each
+  uint8_t* img[8];                 // tagged activation images g, BN(h0'), h0', h1', z of look-ahead frame 0, 1, ..: 2 buffers of img_stride bytes each
+  int n_spec;                      // joint evaluations per utterance and lock-step (1 = none speculative)
   size_t img_stride;
   unsigned long long* keys;        // [2][128 CTAs][32] packed (logit, index, tag) arg-max keys
   const float* ep;                 // [B][T][J] encoder half of the joint incl. b1
@@ -303,6 +304,8 @@ bool decode_tc2_plan(int H, int J, int V, int Lp, int B, int sms, int lm_layers)
 size_t decode_tc2_image_bytes();   // one buffer of one activation image
 size_t decode_tc2_keys_bytes();
 int decode_tc2_part_ctas();
+int decode_tc2_images();
+int decode_tc2_max_spec();
 cudaError_t launch_decode_tc2(const DecodeTc2Args& a, cudaStream_t st);
 
 // ---------------- beam.cu (batched RNN-T beam search; algorithm defined by oracle/beam.py) ----------------
