@@ -266,6 +266,8 @@ int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, c
 typedef struct rnnt_b200_stream_s* rnnt_b200_stream;
 int32_t rnnt_b200_stream_open(rnnt_b200_handle h, int32_t n_streams, int32_t chunk_samples, int32_t n_window,
                               int32_t n_buffer, int32_t max_iters, rnnt_b200_stream* out);
+/* Buffer lifetime: a HOST `chunks` buffer (chunks_on_host = 1) may be reused as soon as the call returns -- every return path
+ * has waited for the copy out of it.  rnnt_b200_destroy() refuses (ERR_STATE) while sessions opened on the handle exist. */
 int32_t rnnt_b200_stream_push(rnnt_b200_stream s, const float* chunks, int32_t chunks_on_host, const uint8_t* active_host,
                               int32_t* tokens_host_out, int32_t U_cap, int32_t* ntok_host_out,
                               int32_t* advanced_out, void* stream);

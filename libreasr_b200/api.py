@@ -27,8 +27,13 @@ class LibreASR:
 
     def __init__(self, model, denumericalize=None):
         self.model = model
-        self.engine = model.engine()
         self.denumericalize = denumericalize or (lambda ids: list(ids))
+
+    @property
+    def engine(self):
+        """Fetched from the model on every use: `m.lm = ...`, `load_state_dict` or `.to()` rebuild the engine, a cached
+        reference would point at a destroyed handle."""
+        return self.model.engine()
 
     # offline: ASRServicer.Transcribe (api-server.py:64-80) for one or many utterances
     def transcribe(self, audio, lens=None, max_iters=3, sr=16000):
@@ -82,6 +87,7 @@ class StreamBatch:
         with torch.cuda.device(engine.device):
             engine._ck(engine.lib.rnnt_b200_stream_open(engine._h, n_streams, self.chunk, BUFFER_N_FRAMES, n_buffer, max_iters,
                                                         C.byref(self._s)))
+        engine._register_session(self)
         self.U = max_iters * n_buffer
         self._tok = torch.zeros(n_streams, self.U, dtype=torch.int32).pin_memory()
         self._ntok = torch.zeros(n_streams, dtype=torch.int32).pin_memory()

@@ -54,6 +54,7 @@ struct rnnt_b200_handle_s {
   bool finalized = false;
   int sm_count = 0, coop_blocks = 0;
   int64_t launches = 0;
+  int open_streams = 0;                // streaming sessions that reference this handle (destroy refuses while > 0)
   std::vector<void*> weight_allocs;
   // frontend
   float* window = nullptr;
@@ -306,6 +307,8 @@ int32_t rnnt_b200_create(const rnnt_b200_config* cfg, rnnt_b200_handle* out) {
 
 int32_t rnnt_b200_destroy(rnnt_b200_handle h) {
   if (!h) return RNNT_B200_OK;
+  if (h->open_streams > 0)
+    return fail(h, RNNT_B200_ERR_STATE, "destroy: " + std::to_string(h->open_streams) + " streaming session(s) still reference this handle; close them first");
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
   for (void* p : h->weight_allocs) cudaFree(p);
@@ -1621,6 +1624,7 @@ struct rnnt_b200_stream_s {
   DevBuf bos_h, bos_out;  // predictor state / output after feeding BOS from the learnable state (reset_predictor, models.py:484-489)
   DevBuf ctl;             // device copy of the per-tick control words: pos[B] | lens_T[B]
   int32_t* ctl_host = nullptr;   // pinned staging for `ctl`
+  bool counted = false;          // registered in h->open_streams
 };
 
 namespace {
@@ -1702,6 +1706,8 @@ int32_t rnnt_b200_stream_open(rnnt_b200_handle h, int32_t B, int32_t chunk, int3
   for (int b = 0; b < B; ++b)
     if (int r = stream_reset_slot_impl(s, b, nullptr)) { rnnt_b200_stream_close(s); return r; }
   CK(cudaStreamSynchronize(nullptr));
+  h->open_streams += 1;
+  s->counted = true;
   *out = s;
   return RNNT_B200_OK;
 }
@@ -1729,6 +1735,7 @@ int32_t rnnt_b200_stream_close(rnnt_b200_stream s) {
                     &s->enc_out, &s->tokens, &s->ntok, &s->lm, &s->bos_h, &s->bos_out, &s->ctl})
     b->release();
   if (s->ctl_host) cudaFreeHost(s->ctl_host);
+  if (s->counted) s->h->open_streams -= 1;
   delete s;
   return RNNT_B200_OK;
 }
@@ -1770,12 +1777,14 @@ int32_t rnnt_b200_stream_push(rnnt_b200_stream s, const float* chunks, int32_t o
   float* wnew = s->win[s->cur ^ 1].as<float>();
   LAUNCH(1, launch_slide_window(wold, wnew, chunks_dev, B, (int)W, ck, mask, st));
   s->cur ^= 1;
-  if (!any_row) return RNNT_B200_OK;
+  // a host chunk buffer may be reused by the caller as soon as this call returns: on the paths that do not end in the
+  // stream synchronisation below, wait for the copy out of it here
+  if (!any_row) { if (on_host) CK(cudaStreamSynchronize(st)); return RNNT_B200_OK; }
   CK(cudaMemcpyAsync(s->ctl.p, s->ctl_host, (size_t)2 * B * 4, cudaMemcpyHostToDevice, st));
   // stream transforms -> one stacked row per stream, appended to its Buffer (transforms.py:326-342,463-471)
   if (int r = rnnt_b200_features_stream(h, wnew, B, (int64_t)W, s->row.as<float>(), stream)) return r;
   LAUNCH(1, launch_store_rows(s->row.as<float>(), s->rows.as<float>(), s->ctl.as<int32_t>(), B, (int)X, s->n_buffer, st));
-  if (!any_ready) return RNNT_B200_OK;
+  if (!any_ready) { if (on_host) CK(cudaStreamSynchronize(st)); return RNNT_B200_OK; }
   if (!tokens_host || !ntok_host || U_cap < U) return fail(h, RNNT_B200_ERR_INVALID, "stream_push: token outputs missing or U_cap < max_iters * n_buffer");
   // Transducer.transcribe_stream, one chunk of n_buffer encoder steps for the streams whose Buffer filled (models.py:503-571);
   // the others take part with zero frames (state untouched)

@@ -120,9 +120,24 @@ class Engine:
 
     # ---- lifecycle ------------------------------------------------------------------
     def close(self):
+        """Destroys the handle.  Streaming sessions opened on it are closed first (the C ABI refuses to destroy a handle that
+        sessions still reference), so a StreamBatch can never outlive the engine it points into."""
+        for ref in list(getattr(self, "_sessions", ())):
+            sb = ref()
+            if sb is not None:
+                sb.close()
+        self._sessions = []
         if getattr(self, "_h", None) and self._h.value:
             self.lib.rnnt_b200_destroy(self._h)
             self._h = C.c_void_p(0)
+
+    def _register_session(self, sb):
+        import weakref
+
+        if not hasattr(self, "_sessions"):
+            self._sessions = []
+        self._sessions = [r for r in self._sessions if r() is not None]
+        self._sessions.append(weakref.ref(sb))
 
     def __del__(self):
         try:

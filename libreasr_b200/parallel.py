@@ -109,30 +109,28 @@ def scatter_audio_blocks(audio: Optional[torch.Tensor], n_items: int, n_samples:
     lo, hi = shard_bounds(n_items, world, rank)
     local = torch.empty(hi - lo, n_samples, dtype=torch.float32, device=device)
     parts = []
+    n_blocks = -(-(shard_bounds(n_items, world, 0)[1]) // block) if n_items else 0   # rank 0 owns the (joint) largest shard
     if rank == src:
         reqs = []
-        k = 0
-        while True:
-            any_left = False
+        for k in range(n_blocks):   # one batched group of sends per round: block k of every rank
+            ops = []
             for r in range(world):
                 a, b = shard_bounds(n_items, world, r)
                 s0, s1 = a + k * block, min(b, a + (k + 1) * block)
                 if s0 >= s1:
                     continue
-                any_left = True
                 if r == src:
                     local[s0 - a:s1 - a].copy_(audio[s0:s1])
                 else:
-                    reqs.append(dist.isend(audio[s0:s1], dst=r))
-            if not any_left:
-                break
-            k += 1
+                    ops.append(dist.P2POp(dist.isend, audio[s0:s1], r))
+            if ops:
+                reqs += dist.batch_isend_irecv(ops)
         for b0 in range(0, hi - lo, block):
             parts.append((local[b0:min(hi - lo, b0 + block)], None))
         return parts, reqs
     for b0 in range(0, hi - lo, block):
         sl = local[b0:min(hi - lo, b0 + block)]
-        parts.append((sl, dist.irecv(sl, src=src)))
+        parts.append((sl, dist.batch_isend_irecv([dist.P2POp(dist.irecv, sl, src)])[0]))
     return parts, []
 
 

@@ -240,9 +240,10 @@ class StreamScheduler:
     def tick(self):
         """Takes at most one pending frame per live slot and advances those streams by one chunk."""
         active = [False] * self.B
-        with self._mu:
+        with self._mu:   # one consistent snapshot: which slots are live, which are new connections, and THEIR queues
             live = list(self._live)
             fresh, self._fresh = self._fresh, [False] * self.B
+            inq, outq = list(self._inq), list(self._outq)
         resets = [b for b in range(self.B) if live[b] and fresh[b]]   # new connections: full reset (window, Buffer, state)
         state_resets = []                                              # reset_fn requests: model state only (models.py:480-500)
         closing = []
@@ -251,7 +252,7 @@ class StreamScheduler:
                 continue
             while True:
                 try:
-                    item = self._inq[b].get_nowait()
+                    item = inq[b].get_nowait()
                 except queue.Empty:
                     break
                 if item is None:                      # reset request from the transcript logic
@@ -282,7 +283,7 @@ class StreamScheduler:
                 # the session reports [] for streams that did not run, which the transcript logic must not count as a step
                 if active[b] and live[b] and self._ran(b):
                     self._all[b] = self._all[b] + list(new[b])
-                    self._outq[b].put((list(self._all[b]), list(new[b])))
+                    outq[b].put((list(self._all[b]), list(new[b])))
         return True
 
     def _ran(self, b):
@@ -290,10 +291,18 @@ class StreamScheduler:
         return True if ran is None else bool(ran[b])
 
     def run(self, stop: threading.Event, idle_s=0.002):
-        while not stop.is_set():
-            if not self.tick():
-                self._wake.wait(idle_s)
-                self._wake.clear()
+        """Scheduler loop.  A failing tick must not leave the connected clients blocked on their result queues: every
+        live slot is disconnected (end-of-stream marker) and the error is kept in ``self.error`` and re-raised."""
+        try:
+            while not stop.is_set():
+                if not self.tick():
+                    self._wake.wait(idle_s)
+                    self._wake.clear()
+        except Exception as e:  # noqa: BLE001
+            self.error = e
+            for b in range(self.B):
+                self.disconnect(b)
+            raise
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ def test_nccl_sharded_tokens_equal_single_gpu_tokens():
         pytest.skip("needs >= 2 GPUs")
     world = 2 if n < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tools", "nccl_shard_check.py"), "--n", "70"]
+           "--master-port", "29517", os.path.join(ROOT, "tools", "nccl_shard_check.py"), "--utterances", "70"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]

@@ -152,3 +152,34 @@ def test_stream_session_mid_stream_state_reset_matches_reference_fixture():
     assert [t for y in yields for t in y] == g["tokens_all"].tolist()
     assert other == _oracle_stream_tokens(orc, cfg, a, n_chunks)       # stream 1: no reset
     assert other != yields
+
+
+def test_checkpoint_bundle_then_decode(tmp_path):
+    """Row f4: libreasr-model-<lang>.tar.gz (fastai `{"model", "opt"}` dict inside `<lang>/model.pth`, model_utils.py:20-95)
+    -> load_asr_model -> the tokens of the `tiny_offline` reference fixture."""
+    from libreasr_b200.lib import model_utils as MU
+    from libreasr_b200.lib.models import Transducer
+
+    g = load_golden("tiny_offline")
+    cfg = weights.CONFIGS["tiny"]
+    sd = {k: torch.as_tensor(v) for k, v in weights.make_state_dict(cfg, int(g["weight_seed"])).items()}
+
+    def fresh():
+        return Transducer(cfg.feature_sz, cfg.embed_sz, cfg.vocab_sz, cfg.hidden_sz, cfg.out_sz, cfg.joint_sz, Lang(),
+                          encoder_kwargs={"num_layers": cfg.enc_layers}, predictor_kwargs={"num_layers": cfg.pred_layers})
+    src = fresh()
+    src.load_state_dict(sd, strict=True)
+    dest = tmp_path / "tmp"
+    (dest / "xx").mkdir(parents=True)
+    torch.save({"model": src.state_dict(), "opt": {}}, dest / "xx" / "model.pth")
+    (dest / "xx" / "tokenizer.yttm-model").write_bytes(b"\x00")
+    arc = tmp_path / "libreasr-model-xx.tar.gz"
+    MU.save_asr_model("xx", path_archive=arc, path_dest=dest)
+    MU.extract_tars([str(arc)], path_dest=tmp_path / "out")
+    m = MU.load_asr_model(fresh(), "xx", Lang(), device="cuda:0", path_dest=tmp_path / "out")
+    audio = weights.make_audio(int(g["n_utt"]), int(g["n_samples"]), int(g["audio_seed"]))
+    for b in range(int(g["n_utt"])):
+        feats = m.engine().features(torch.from_numpy(audio[b:b + 1]).cuda())[0]
+        toks = m.decode_greedy(feats.unsqueeze(-1), max_iters=int(g["max_iters"]))[0]
+        assert toks == g[f"tokens_{b}"].tolist()
+    m._drop_engine()

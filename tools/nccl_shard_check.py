@@ -1,6 +1,6 @@
 """Run under torchrun (NCCL, one rank per GPU): N-GPU sharded transcription == 1-GPU transcription.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 tools/nccl_shard_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 tools/nccl_shard_check.py --utterances 70
 
 Rank 0 holds `--n` utterances (cfg2 model, ragged lengths optional); they go through
 libreasr_b200.parallel.transcribe_sharded three ways -- contiguous blocks, length-balanced dealing and the
@@ -24,7 +24,7 @@ from libreasr_b200.engine import Engine, EngineConfig, tokens_to_lists  # noqa: 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=70)
+    ap.add_argument("--utterances", type=int, default=70)
     ap.add_argument("--seconds", type=float, default=3.0)
     ap.add_argument("--config", default="cfg2")
     a = ap.parse_args()
@@ -41,26 +41,26 @@ def main():
     n = int(a.seconds * 16000)
     audio = lens = want = None
     if rank == 0:
-        audio = torch.from_numpy(synth.make_audio(a.n, n, seed=151)).to(dev)
-        lens = torch.tensor([n - 800 * (i % 23) for i in range(a.n)], dtype=torch.int32, device=dev)
+        audio = torch.from_numpy(synth.make_audio(a.utterances, n, seed=151)).to(dev)
+        lens = torch.tensor([n - 800 * (i % 23) for i in range(a.utterances)], dtype=torch.int32, device=dev)
         r = eng.transcribe(audio, lens, 3)
         want = tokens_to_lists(r["tokens"], r["ntok"])
         r2 = eng.transcribe(audio, None, 3)
         want_full = tokens_to_lists(r2["tokens"], r2["ntok"])
     res = {}
-    got = parallel.transcribe_sharded(eng, audio, lens, a.n, n, max_iters=3)
+    got = parallel.transcribe_sharded(eng, audio, lens, a.utterances, n, max_iters=3)
     if rank == 0:
         res["contiguous_ragged"] = got == want
-    got = parallel.transcribe_sharded(eng, audio, lens, a.n, n, max_iters=3, balance=True)
+    got = parallel.transcribe_sharded(eng, audio, lens, a.utterances, n, max_iters=3, balance=True)
     if rank == 0:
         res["balanced_ragged"] = got == want
-    got = parallel.transcribe_sharded(eng, audio, None, a.n, n, max_iters=3, block=16)
+    got = parallel.transcribe_sharded(eng, audio, None, a.utterances, n, max_iters=3, block=16)
     if rank == 0:
         res["block_pipelined"] = got == want_full
     ok = True
     if rank == 0:
         ok = all(res.values())
-        print(json.dumps({"world": world, "n_utterances": a.n, "tokens_total": sum(len(t) for t in want), "checks": res, "ok": ok}), flush=True)
+        print(json.dumps({"world": world, "n_utterances": a.utterances, "tokens_total": sum(len(t) for t in want), "checks": res, "ok": ok}), flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)
     dist.barrier()
