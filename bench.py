@@ -403,8 +403,9 @@ def run_product(args):
                     "frac": round(a / peak_t, 5), "ms_per_step": round(ms, 4), "launches_per_step": launches,
                     "algorithmic_flops_per_step": int(flops)}
         lstm_name = ("lstm_layer_tc2_kernel" if lstm_v == "2" else "lstm_layer_tc_kernel") if tc else "lstm_step_kernel"
+        dec_name = ("decode_tc2_kernel" if os.environ.get("RNNT_DEC_V", "2") == "2" else "decode_tc_kernel") if tc else "decode_greedy_kernel"
         per_kernel = [
-            tens("decode_tc_kernel" if tc else "decode_greedy_kernel", work["decode_flops"], stage["decode"], 1),
+            tens(dec_name, work["decode_flops"], stage["decode"], 1),
             tens(lstm_name, rec_flops, rec_ms, L if tc else L * T),
             tens("gemm_tc_f16x3_kernel" if tc else "gemm_nt_f32_kernel", hoist_flops, max(stage["encoder_input_gemms"], 1e-6), L),
             {"kernel": "mel_stack_kernel", "bound": "hbm", "achieved": round(fe_bytes / (stage["features"] * 1e-3) / 1e9, 1),

@@ -968,8 +968,8 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
       unsigned long long* dbg = nullptr;
       unsigned long long* dbg_all = nullptr;
       if (dbg_on2 && l == 0) {
-        CK(cudaMalloc((void**)&dbg, (size_t)T * 32));
-        CK(cudaMemset(dbg, 0, (size_t)T * 32));
+        CK(cudaMalloc((void**)&dbg, (size_t)T * 32 + 128));
+        CK(cudaMemset(dbg, 0, (size_t)T * 32 + 128));
         CK(cudaMalloc((void**)&dbg_all, (size_t)pl2.grid * T * 16));
         CK(cudaMemset(dbg_all, 0, (size_t)pl2.grid * T * 16));
         a.dbg = dbg;
@@ -997,10 +997,15 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
                 pl2.grid, sp_pub / (T - 1), sp_red / (T - 1), first_to_last / (T - 1));
       }
       if (dbg) {
-        std::vector<unsigned long long> hb((size_t)T * 4);
+        std::vector<unsigned long long> hb((size_t)T * 4 + 16);
         CK(cudaStreamSynchronize(st));
-        CK(cudaMemcpy(hb.data(), dbg, (size_t)T * 32, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hb.data(), dbg, (size_t)T * 32 + 128, cudaMemcpyDeviceToHost));
         cudaFree(dbg);
+        fprintf(stderr, "[lstm_tc2 epilogue cycles/step, CTA 0 thread 0] wait accumulators %.0f | TMEM drain %.0f | scatter issue %.0f | wait tiles %.0f | tile sums %.0f | cell %.0f | publish %.0f | BN outputs %.0f\n",
+                (double)hb[(size_t)T * 4 + 0] / T, (double)hb[(size_t)T * 4 + 1] / T, (double)hb[(size_t)T * 4 + 2] / T, (double)hb[(size_t)T * 4 + 3] / T,
+                (double)hb[(size_t)T * 4 + 4] / T, (double)hb[(size_t)T * 4 + 5] / T, (double)hb[(size_t)T * 4 + 6] / T, (double)hb[(size_t)T * 4 + 7] / T);
+        fprintf(stderr, "[lstm_tc2 loader cycles/step, CTA 0 thread 0] first chunk visible %.0f | k-block 0 valid %.0f | k-blocks 1-3 valid %.0f | stores+fence+arrive %.0f\n",
+                (double)hb[(size_t)T * 4 + 8] / T, (double)hb[(size_t)T * 4 + 9] / T, (double)hb[(size_t)T * 4 + 10] / T, (double)hb[(size_t)T * 4 + 11] / T);
         double ld = 0, mma = 0, red = 0, fin = 0;
         for (int t = 1; t < T; ++t) {
           ld += (double)(hb[t * 4 + 0] - hb[(t - 1) * 4 + 3]);   // previous publish -> K slice of h landed in smem

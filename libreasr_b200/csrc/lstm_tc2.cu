@@ -26,6 +26,8 @@
 //   warps 0-3  epilogue: TMEM -> fold -> DSMEM scatter; then finalise 8 units x 32 rows; publish h_t; y outputs
 //   warps 4-7  loaders: poll/validate the K-slice of h_{t-1} (32 KB), store to smem, fence.proxy.async, arrive
 //   warp  8    MMA issuer (one elected lane), accumulators double-buffered in TMEM
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 #include "tc2_common.cuh"
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < L2_MAX_KS; ++i) {
-      mbar_init(&hfull[i], 128);
+      mbar_init(&hfull[i], 4);   // one arrive per loader warp
       mbar_init(&hempty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -122,7 +124,10 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
     if (et == 0) red_release_add(p.barrier, 1u);   // once per launch: stale chunks of an earlier launch cannot be mistaken for h_{-1}
 
     const uint32_t P_u32 = smem_u32(P);
+    long long cyc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // tuning aid (CTA 0, thread 0): cycles per epilogue segment, summed over the steps
+    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && et == 0;
     for (int t = 0; t < T; ++t) {
+      long long c0 = prof ? clock64() : 0;
       const int ab = t & 1;
       const int64_t row = (int64_t)fb * T + t;
       const bool upd = valid && t < len;
@@ -138,6 +143,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
       mbar_wait(&tfull[ab], (t >> 1) & 1);
       tc_fence_after();
       if (p.dbg && blockIdx.x == 0 && et == 0) p.dbg[t * 4 + 1] = gtimer();
+      if (prof) { const long long c1 = clock64(); cyc[0] += c1 - c0; c0 = c1; }   // waiting for the accumulators
       {
         float d0[32], d1[32], d2[32];
         const uint32_t tc = tl + (uint32_t)(ab * 128);
@@ -147,6 +153,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&tempty[ab]);
+        if (prof) { const long long c1 = clock64(); cyc[1] += c1 - c0; c0 = c1; }   // TMEM drain
         // my gate row's 32 batch values -> CTA q's partial tile [ab][src = rank][b][row = lane]
         const uint32_t dst = mapa(P_u32 + (uint32_t)(((ab * L2_CL + rank) * L2_NB) * 128 + lane * 4), (uint32_t)q);
         if (p.dsm_async) {   // the bytes are counted on the owner's mbarrier: no fence on either side
@@ -158,6 +165,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
           for (int b = 0; b < 32; ++b) st_cluster_f32(dst + (uint32_t)b * 128u, fmaf(d1[b] + d2[b], kLoInv, d0[b]));
         }
       }
+      if (prof) { const long long c1 = clock64(); cyc[2] += c1 - c0; c0 = c1; }   // scatter issue
       if (p.dsm_async) {
         mbar_wait(&pbar[ab], (t >> 1) & 1);
       } else {
@@ -167,6 +175,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
       }
       if (p.dbg && blockIdx.x == 0 && et == 0) p.dbg[t * 4 + 2] = gtimer();
       if (p.dbg_all && et == 0) p.dbg_all[((size_t)blockIdx.x * T + t) * 2 + 1] = gtimer();
+      if (prof) { const long long c1 = clock64(); cyc[3] += c1 - c0; c0 = c1; }   // waiting for the four partial tiles
       {
         float acc[8];
         const float* pr = P + (size_t)((ab * L2_CL) * L2_NB + fb) * 32 + fw * 8;
@@ -180,23 +189,26 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
             acc[0] += u0.x; acc[1] += u0.y; acc[2] += u0.z; acc[3] += u0.w; acc[4] += u1.x; acc[5] += u1.y; acc[6] += u1.z; acc[7] += u1.w;
           }
         }
+        if (prof) { const long long c1 = clock64(); cyc[4] += c1 - c0; c0 = c1; }   // tile sums (LDS)
         if (upd) {
           {
             const float vi = acc[0] + xv0.x, vf = acc[1] + xv0.y, vg = acc[2] + xv0.z, vo = acc[3] + xv0.w;
-            const float cn = sigmoidf_acc(vf) * c[0] + sigmoidf_acc(vi) * tanhf(vg);
+            const float cn = sigmoid_fast(vf) * c[0] + sigmoid_fast(vi) * tanh_fast(vg);
             c[0] = cn;
-            h[0] = sigmoidf_acc(vo) * tanhf(cn);
+            h[0] = sigmoid_fast(vo) * tanh_fast(cn);
           }
           {
             const float vi = acc[4] + xv1.x, vf = acc[5] + xv1.y, vg = acc[6] + xv1.z, vo = acc[7] + xv1.w;
-            const float cn = sigmoidf_acc(vf) * c[1] + sigmoidf_acc(vi) * tanhf(vg);
+            const float cn = sigmoid_fast(vf) * c[1] + sigmoid_fast(vi) * tanh_fast(vg);
             c[1] = cn;
-            h[1] = sigmoidf_acc(vo) * tanhf(cn);
+            h[1] = sigmoid_fast(vo) * tanh_fast(cn);
           }
         }
       }
+      if (prof) { const long long c1 = clock64(); cyc[5] += c1 - c0; c0 = c1; }   // cell
       // h_t gates the next step: publish first; the BatchNorm(h_t) outputs follow off the critical path
       publish(p.x_img[(t + 1) & 1], h[0], h[1], (uint32_t)(((t + 1) >> 1) & 1));
+      if (prof) { const long long c1 = clock64(); cyc[6] += c1 - c0; c0 = c1; }   // publish
       if (p.dbg && blockIdx.x == 0 && et == 0) p.dbg[t * 4 + 3] = gtimer();
       if (p.dbg_all && et == 0) p.dbg_all[((size_t)blockIdx.x * T + t) * 2] = gtimer();
       if (valid) {
@@ -211,7 +223,10 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
           *reinterpret_cast<uint32_t*>(hi + 128 * 128) = l0 | (l1 << 16);
         }
       }
+      if (prof) { const long long c1 = clock64(); cyc[7] += c1 - c0; }   // BatchNorm outputs
     }
+    if (prof)
+      for (int i = 0; i < 8; ++i) p.dbg[(size_t)T * 4 + i] = (unsigned long long)cyc[i];
     if (valid) {
       if (p.state_h_out) *reinterpret_cast<float2*>(p.state_h_out + (size_t)fb * H + unit) = make_float2(h[0], h[1]);
       if (p.state_c_out) *reinterpret_cast<float2*>(p.state_c_out + (size_t)fb * H + unit) = make_float2(c[0], c[1]);
@@ -225,15 +240,20 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
       }
     }
     __syncwarp();
+    long long lcyc[4] = {0, 0, 0, 0};
+    const bool lprof = p.dbg != nullptr && blockIdx.x == 0 && lt == 0;
     for (int t = 0; t < T; ++t) {
       const uint32_t tag = (uint32_t)((t >> 1) & 1);
       const uint8_t* src = p.x_img[t & 1] + slice_off + (size_t)lt * 16;
       uint4 r[L2_MAX_KS * 4];
+      long long lc0 = lprof ? clock64() : 0;
       poll_issue<L2_MAX_KS * 4>(src, NL, tag, r);
+      if (lprof) { const long long c1 = clock64(); lcyc[0] += c1 - lc0; lc0 = c1; }   // until the first chunk of h_{t-1} shows up
 #pragma unroll
       for (int kb = 0; kb < L2_MAX_KS; ++kb) {
         if (kb < KS) {
           poll_validate_kb<L2_MAX_KS * 4>(src, kb, tag, r);
+          if (lprof) { const long long c1 = clock64(); lcyc[1 + (kb > 0)] += c1 - lc0; lc0 = c1; }   // k-block 0 complete | the others
           if (t > 0) mbar_wait(&hempty[kb], (t - 1) & 1);   // the MMAs of step t-1 have finished reading this k-block
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -242,11 +262,15 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
             *reinterpret_cast<uint4*>(hs + (size_t)i * 2048 + (size_t)lt * 16) = r[i];
           }
           fence_proxy_async_smem();
-          mbar_arrive(&hfull[kb]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&hfull[kb]);
+          if (lprof) { const long long c1 = clock64(); lcyc[3] += c1 - lc0; lc0 = c1; }   // stores + fence + arrive
         }
       }
       if (p.dbg && blockIdx.x == 0 && lt == 0) p.dbg[t * 4 + 0] = gtimer();
     }
+    if (lprof)
+      for (int i = 0; i < 4; ++i) p.dbg[(size_t)T * 4 + 8 + i] = (unsigned long long)lcyc[i];
   } else {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
@@ -338,7 +362,10 @@ cudaError_t launch_lstm_layer_tc2(const LstmTc2Args& a, const LstmTc2Plan& pl, c
   at[1].id = cudaLaunchAttributeCooperative;
   at[1].val.cooperative = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 2;
+  // profilers cannot replay a cooperative cluster launch: RNNT_NO_COOP=1 drops the co-residency check of the launch
+  // (the plan has verified with cudaOccupancyMaxActiveClusters that all clusters fit; only use on an otherwise idle GPU)
+  static const bool no_coop = [] { const char* e = getenv("RNNT_NO_COOP"); return e && e[0] == '1'; }();
+  cfg.numAttrs = no_coop ? 1 : 2;
   return cudaLaunchKernelEx(&cfg, lstm_layer_tc2_kernel, args);
 }
 

@@ -104,10 +104,14 @@ __device__ __forceinline__ void chunk_strip_tag(uint4& r) { r.w &= 0xFFFEFFFFu; 
 // parallel rounds, so the first k-blocks can be handed to the MMA while the stragglers of the later ones are in flight.
 template <int N>
 __device__ __forceinline__ void poll_issue(const uint8_t* src, int n, uint32_t tag, uint4 (&r)[N]) {
+  // lanes 0-7 = the eight chunks (eight producer CTAs) of one 128-byte line: one sector request per producer and round trip
+  const bool poller = (threadIdx.x & 31) < 8;
+  r[0] = make_uint4(0u, 0u, 0u, (tag ^ 1u) << 16);
   for (;;) {
-    r[0] = ld_relaxed_v4(src);
-    if (__any_sync(0xffffffffu, chunk_tag_ok(r[0], tag))) break;
+    if (poller) r[0] = ld_relaxed_v4(src);
+    if (__any_sync(0xffffffffu, poller && chunk_tag_ok(r[0], tag))) break;
   }
+  if (!poller) r[0] = ld_relaxed_v4(src);
 #pragma unroll
   for (int i = 1; i < N; ++i)
     if (i < n) r[i] = ld_relaxed_v4(src + (size_t)i * 2048);
@@ -125,6 +129,12 @@ __device__ __forceinline__ void poll_validate_kb(const uint8_t* src, int kb, uin
       if ((bad >> j) & 1u) r[kb * 4 + j] = ld_relaxed_v4(src + (size_t)(kb * 4 + j) * 2048);
   }
 }
+
+// Gate non-linearities of the cluster kernels' cells: one ex2.approx and one rcp.approx each.  Absolute error ~1e-7
+// (the outputs live in (-1, 1): that is fp32 epsilon), against ~250 dependent instructions for the libm versions on the
+// single warp per scheduler that sits on the recurrent chain.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
 // ---- distributed-shared-memory partial tiles without fences ----
 // st.async delivers the value and counts its bytes on the RECEIVER's mbarrier (complete_tx), like a TMA copy: the
