@@ -51,7 +51,7 @@ constexpr int D2_WSTAGE = 24576;
 constexpr int D2_RP = 24;         // row stride of a partial tile (max rows finalised per CTA)
 constexpr int D2_K = 1024;        // H = J
 
-constexpr int D2_MAXS = 3;        // joint evaluations per utterance and lock-step (speculative look-ahead frames)
+constexpr int D2_MAXS = 2;        // joint evaluations per utterance and lock-step (speculative look-ahead frames)
 enum { IMG_G = 0, IMG_X = 1, IMG_H0 = 2, IMG_H1 = 3, IMG_Z0 = 4, IMG_N = 4 + D2_MAXS };
 enum { JOB_A = 0, JOB_B = 1, JOB_K1 = 2, JOB_R0 = 3, JOB_R1 = 4 };
 
@@ -60,6 +60,7 @@ struct Ctrl2 {
   unsigned char active[D2_NB], emit[D2_NB];
   int flags[2];                                  // any_emit, any_active of the current step
   unsigned long long kred[D2_MAXS][8][D2_NB];    // partial maxima of the key table, per look-ahead frame
+  unsigned long long kbuf[D2_CL][D2_MAXS][D2_NB]; // cluster leader: the four CTAs' keys of a step (written through DSMEM)
 };
 
 __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args p) {
@@ -91,7 +92,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
   uint64_t* w2full = pfree + 2;
   uint64_t* ctlbar = w2full + 1;          // flags of a step published
   uint64_t* ctlack = ctlbar + 1;          // ... and read by the 6 GEMM-side warps
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(ctlack + 1);
+  uint64_t* kbar = ctlack + 1;            // cluster leader: the keys of a step have arrived (transaction bytes)
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(kbar + 1);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < D2_AST; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
     mbar_init(w2full, 1);
     mbar_init(ctlbar, 1);
     mbar_init(ctlack, 6);
+    mbar_init(kbar, 4);   // armed by the four epilogue warps of the leader
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc(tptr, 256);
@@ -200,9 +203,9 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
             if (zs < NS) st_relaxed_v4(p.img[IMG_Z0 + zs] + (size_t)bf * p.img_stride + off, one.x, one.y, one.z, one.w);
         }
       }
-      // key table [2][NS][128 cta][32 b] u64: tag 1 (bit 0) everywhere
-      if (et < 32)
-        for (int i = 0; i < 2 * NS; ++i) p.keys[((size_t)i * D2_G + cta) * D2_NB + et] = 1ull;
+      // key table [2][NS][32 clusters][32 b] u64 (written by the cluster leaders): tag 1 (bit 0) everywhere
+      if (et < 32 && rank == 0)
+        for (int i = 0; i < 2 * NS; ++i) p.keys[((size_t)i * D2_NCL + cl) * D2_NB + et] = 1ull;
       __threadfence();
       named_bar_sync(1, 128);
       if (et == 0) {
@@ -220,7 +223,12 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
     };
     // Drain the accumulators of the current job, scatter this warp's rows to their owner CTAs, wait for the four
     // partial tiles of the rows this CTA owns.  M: MMA M of the job, rows: valid rows of the cluster, rp: rows per owner.
-    auto reduce_job = [&](int M, int rows, int rp) -> const float* {
+    // A GEMM job's epilogue in two halves so that consecutive jobs can overlap their waits:
+    //   send_job: drain the accumulators of the next job, scatter this warp's rows to their owner CTAs      -> job index j
+    //   wait_job: the four partial tiles of the rows this CTA owns have arrived                              -> this thread's batch row
+    //   release_job: all reads of those tiles are done, hand the buffer back to the senders
+    // M: MMA M of the job, rows: valid rows of the cluster, rp: rows per owner.
+    auto send_job = [&](int M, int rows, int rp) -> unsigned {
       const unsigned j = job++;
       const int ab = (int)(j & 1u);
       const unsigned n = j >> 1;
@@ -256,18 +264,20 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
       }
       tc_fence_before();
       mbar_arrive(&tempty[ab]);
-      if (p.dsm_async) {
-        mbar_wait(&pbar[ab], n & 1u);
-      } else {
+      if (!p.dsm_async) {
         __syncwarp();
         if (lane < D2_CL) mbar_arrive_cluster(mapa(smem_u32(&pbar[ab]), (uint32_t)lane));
-        mbar_wait_cluster(&pbar[ab], n & 1u);
       }
+      return j;
+    };
+    auto wait_job = [&](unsigned j) -> const float* {
+      const int ab = (int)(j & 1u);
+      if (p.dsm_async) mbar_wait(&pbar[ab], (j >> 1) & 1u);
+      else mbar_wait_cluster(&pbar[ab], (j >> 1) & 1u);
       return P + (size_t)((ab * D2_CL) * D2_NB + fb) * D2_RP;   // + src * 32 * 24 ; this thread's batch row
     };
-    // all reads of the partial tiles of the job just finalised are done: hand the buffers back to the senders
-    auto release_job = [&]() {
-      const int ab = (int)((job - 1) & 1u);
+    auto release_job = [&](unsigned j) {
+      const int ab = (int)(j & 1u);
       __syncwarp();
       if (lane < D2_CL) {
         if (p.dsm_async) mbar_arrive_cluster_relaxed(mapa(smem_u32(&pfree[ab]), (uint32_t)lane));   // (the values read are already consumed: program order suffices)
@@ -289,9 +299,9 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
     };
     // speculative recurrent product of predictor layer l -> registers
     auto epi_rec = [&](int l) {
-      const float* pr = reduce_job(128, 96, 24);
-      sum2(pr, fw * 6, rec[l], 6);
-      release_job();
+      const unsigned j = send_job(128, 96, 24);
+      sum2(wait_job(j), fw * 6, rec[l], 6);
+      release_job(j);
     };
     // predictor layer l (GRU cell + BatchNorm eval, haste/nbrc.py:46-56); vx = input pre-activations incl. bias
     auto gru_cell = [&](int l, const float (&vx)[6]) {
@@ -324,10 +334,10 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
       float kb[6];
 #pragma unroll
       for (int i = 0; i < 6; ++i) kb[i] = w.kbias[1][(size_t)unit * 3 + i];
-      const float* pr = reduce_job(128, 96, 24);
+      const unsigned j = send_job(128, 96, 24);
       float vx[6];
-      sum2(pr, fw * 6, vx, 6);
-      release_job();
+      sum2(wait_job(j), fw * 6, vx, 6);
+      release_job(j);
 #pragma unroll
       for (int i = 0; i < 6; ++i) vx[i] += kb[i];
       gru_cell(1, vx);
@@ -361,9 +371,9 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
           if (vs[zs]) epv[zs] = *reinterpret_cast<const float2*>(p.ep + ((size_t)fb * T + c.t[fb] + zs) * J + unit);
         }
         if (any_upd) {
-          const float* pr = reduce_job(64, 32, 8);
-          sum2(pr, fw * 2, pp, 2);
-          release_job();
+          const unsigned j = send_job(64, 32, 8);
+          sum2(wait_job(j), fw * 2, pp, 2);
+          release_job(j);
         }
 #pragma unroll
         for (int zs = 0; zs < D2_MAXS; ++zs)
@@ -379,11 +389,17 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
         unsigned long long keys[D2_MAXS];
         const unsigned nk = nkeys++;
         const uint32_t ktag = (nk >> 1) & 1u;
+        // two look-ahead frames: both scatters go out before either wait (the two jobs use the two tile buffers)
+        unsigned jb[D2_MAXS];
+#pragma unroll
+        for (int zs = 0; zs < D2_MAXS; ++zs)
+          if (zs < NS && zs < 2) jb[zs] = send_job(64, RB, rpB);
 #pragma unroll
         for (int zs = 0; zs < D2_MAXS; ++zs) {
           keys[zs] = (unsigned long long)ktag;
           if (zs < NS) {
-            const float* pr = reduce_job(64, RB, rpB);
+            if (zs >= 2) jb[zs] = send_job(64, RB, rpB);   // a third frame reuses the first frame's buffer: only after its release
+            const float* pr = wait_job(jb[zs]);
             float lv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
             for (int sr = 0; sr < D2_CL; ++sr) {
@@ -392,7 +408,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
               for (int i = 0; i < 4; ++i)
                 if (i < rptB) lv[i] = (sr == 0 ? b2v[i] : lv[i]) + ps[i];
             }
-            release_job();
+            release_job(jb[zs]);
             const bool vz = bvalid && c.active[fb] != 0 && c.t[fb] + zs < c.len[fb];
             const int e = c.n_eval[fb] + zs;     // index of this evaluation in the utterance's sequence
             float m = -INFINITY, sx = 0.f;
@@ -427,48 +443,72 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
             }
           }
         }
-        unsigned long long* ktab = p.keys + (size_t)(nk & 1u) * NS * D2_G * D2_NB;
+        // Arg-max exchange in two hops: every CTA hands its keys to the cluster leader through DSMEM (st.async, 117 ns), the
+        // leader folds the four and publishes ONE tagged entry per (frame, utterance pair); every CTA then reads the 32-cluster
+        // table of all look-ahead frames in a single pass (8 chunks per thread at two frames).
+        unsigned long long* ktab = p.keys + (size_t)(nk & 1u) * NS * D2_NCL * D2_NB;
+        if (rank == 0 && lane == 0) mbar_arrive_expect_tx(kbar, (uint32_t)(D2_NB * NS * 8));   // a quarter of 4 CTAs x 32 x NS keys
+        {
+          const uint32_t kb_remote = mapa(smem_u32(&c.kbuf[rank][0][fb]), 0u), kbar_remote = mapa(smem_u32(kbar), 0u);
 #pragma unroll
-        for (int zs = 0; zs < D2_MAXS; ++zs) {
-          if (zs < NS) {
-            const unsigned long long key2 = __shfl_down_sync(0xffffffffu, keys[zs], 4);   // batch row fb + 1 (same warp: fb even)
-            if (fw == 0 && (fb & 1) == 0)
-              st_relaxed_v4(ktab + ((size_t)zs * D2_G + cta) * D2_NB + fb, (uint32_t)keys[zs], (uint32_t)(keys[zs] >> 32), (uint32_t)key2, (uint32_t)(key2 >> 32));
+          for (int zs = 0; zs < D2_MAXS; ++zs)
+            if (zs < NS && fw == 0) st_async_b64(kb_remote + (uint32_t)(zs * D2_NB * 8), keys[zs], kbar_remote);
+        }
+        if (rank == 0) {
+          mbar_wait(kbar, nk & 1u);
+          const int kb_b = et & 31, kb_z = et >> 5;
+          unsigned long long kk = (unsigned long long)ktag;
+          if (kb_z < NS) {
+#pragma unroll
+            for (int sr = 0; sr < D2_CL; ++sr) kk = c.kbuf[sr][kb_z][kb_b] > kk ? c.kbuf[sr][kb_z][kb_b] : kk;
           }
+          const unsigned long long kk2 = __shfl_down_sync(0xffffffffu, kk, 1);
+          if (kb_z < NS && (kb_b & 1) == 0)
+            st_relaxed_v4(ktab + ((size_t)kb_z * D2_NCL + cl) * D2_NB + kb_b, (uint32_t)kk, (uint32_t)(kk >> 32), (uint32_t)kk2, (uint32_t)(kk2 >> 32));
         }
         stamp(1);
-        // every CTA reduces the whole table: thread -> batch pair et % 16, CTAs [16 (et / 16), +16), one look-ahead frame after the other
+        // thread -> batch pair et % 16, clusters {et / 16 + 8 i}; all frames requested before the first is validated
         {
           const int bp = et & 15, g = et >> 4;
-          const unsigned long long* src = ktab + (size_t)(g * 16) * D2_NB + 2 * bp;
-#pragma unroll 1
-          for (int zs = 0; zs < NS; ++zs) {
-            const unsigned long long* sz = src + (size_t)zs * D2_G * D2_NB;
-            uint4 r[16];
+          const unsigned long long* src = ktab + (size_t)g * D2_NB + 2 * bp;
+          uint4 r[D2_MAXS][4];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = ld_relaxed_v4(sz + (size_t)i * D2_NB);
+          for (int zs = 0; zs < D2_MAXS; ++zs)
+            if (zs < NS) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) r[zs][i] = ld_relaxed_v4(src + ((size_t)zs * D2_NCL + 8 * i) * D2_NB);
+            }
+          for (;;) {
             uint32_t bad = 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if ((r[i].x & 1u) != ktag || (r[i].z & 1u) != ktag) bad |= 1u << i;
-            while (__any_sync(0xffffffffu, bad != 0u)) {   // stale entries are re-read in parallel rounds
+            for (int zs = 0; zs < D2_MAXS; ++zs)
+              if (zs < NS) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if ((bad >> i) & 1u) r[i] = ld_relaxed_v4(sz + (size_t)i * D2_NB);
+                for (int i = 0; i < 4; ++i)
+                  if ((r[zs][i].x & 1u) != ktag || (r[zs][i].z & 1u) != ktag) bad |= 1u << (zs * 4 + i);
+              }
+            if (!__any_sync(0xffffffffu, bad != 0u)) break;
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (((bad >> i) & 1u) && (r[i].x & 1u) == ktag && (r[i].z & 1u) == ktag) bad &= ~(1u << i);
-            }
-            unsigned long long k0 = 0ull, k1 = 0ull;
+            for (int zs = 0; zs < D2_MAXS; ++zs)
+              if (zs < NS) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const unsigned long long a = ((unsigned long long)r[i].y << 32) | r[i].x, b = ((unsigned long long)r[i].w << 32) | r[i].z;
-              k0 = a > k0 ? a : k0;
-              k1 = b > k1 ? b : k1;
-            }
-            c.kred[zs][g][2 * bp] = k0;
-            c.kred[zs][g][2 * bp + 1] = k1;
+                for (int i = 0; i < 4; ++i)
+                  if ((bad >> (zs * 4 + i)) & 1u) r[zs][i] = ld_relaxed_v4(src + ((size_t)zs * D2_NCL + 8 * i) * D2_NB);
+              }
           }
+#pragma unroll
+          for (int zs = 0; zs < D2_MAXS; ++zs)
+            if (zs < NS) {
+              unsigned long long k0 = 0ull, k1 = 0ull;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const unsigned long long a = ((unsigned long long)r[zs][i].y << 32) | r[zs][i].x, b = ((unsigned long long)r[zs][i].w << 32) | r[zs][i].z;
+                k0 = a > k0 ? a : k0;
+                k1 = b > k1 ? b : k1;
+              }
+              c.kred[zs][g][2 * bp] = k0;
+              c.kred[zs][g][2 * bp + 1] = k1;
+            }
         }
         named_bar_sync(1, 128);
         stamp(2);
@@ -780,7 +820,7 @@ bool decode_tc2_plan(int H, int J, int V, int Lp, int B, int sms, int lm_layers)
 }
 
 size_t decode_tc2_image_bytes() { return (size_t)(D2_K / 64) * 8192; }        // one buffer of one activation image
-size_t decode_tc2_keys_bytes() { return (size_t)2 * D2_MAXS * D2_G * D2_NB * 8; }
+size_t decode_tc2_keys_bytes() { return (size_t)2 * D2_MAXS * D2_NCL * D2_NB * 8; }
 int decode_tc2_images() { return IMG_N; }
 int decode_tc2_max_spec() { return D2_MAXS; }
 int decode_tc2_part_ctas() { return D2_G; }
