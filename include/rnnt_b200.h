@@ -306,6 +306,9 @@ int32_t rnnt_b200_selftest_gemm(rnnt_b200_handle h, const float* A_dev, const fl
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t rnnt_b200_kernel_launches(rnnt_b200_handle h);
+/* Launches of the fp32 cooperative decode kernel so far (gemm_mode 0, or a gemm_mode 1 call that could not take a tcgen05
+ * kernel: a registered LM state blob with more than 64 streams).  Tests assert that the tensor-core path was the one that ran. */
+int64_t rnnt_b200_fp32_decode_launches(rnnt_b200_handle h);
 
 /* Device time (ms) the most recent transcribe*() spent per stage, measured with CUDA
  * events on `stream`: out[0]=features, [1]=encoder total (LayerNorm + hoisted input GEMMs +

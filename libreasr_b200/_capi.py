@@ -65,6 +65,7 @@ SIGNATURES = {
     "rnnt_b200_stream_close": (_i32, [_vp]),
     "rnnt_b200_selftest_gemm": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "rnnt_b200_kernel_launches": (_i64, [_vp]),
+    "rnnt_b200_fp32_decode_launches": (_i64, [_vp]),
     "rnnt_b200_set_profiling": (_i32, [_vp, _i32]),
     "rnnt_b200_stage_times_ms": (_i32, [_vp, _vp]),
 }

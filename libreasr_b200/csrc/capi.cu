@@ -54,7 +54,8 @@ struct rnnt_b200_handle_s {
   bool finalized = false;
   int sm_count = 0, coop_blocks = 0;
   int64_t launches = 0;
-  int open_streams = 0;                // streaming sessions that reference this handle (destroy refuses while > 0)
+  int open_streams = 0;
+  int64_t fp32_decode_launches = 0;    // launches of the fp32 cooperative decode kernel (the slow twin of the tcgen05 kernels)                // streaming sessions that reference this handle (destroy refuses while > 0)
   std::vector<void*> weight_allocs;
   // frontend
   float* window = nullptr;
@@ -894,8 +895,18 @@ int32_t rnnt_b200_resample(rnnt_b200_handle h, const float* audio, int32_t B, in
   return RNNT_B200_OK;
 }
 
+static int32_t encode_impl(rnnt_b200_handle h, const float* feats, const int32_t* lens_T, int32_t B, int32_t T, float* state_h,
+                           float* state_c, int32_t use_state_in, float* enc_out, void* stream, int state_ld);
+
 int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* lens_T, int32_t B, int32_t T, float* state_h,
                          float* state_c, int32_t use_state_in, float* enc_out, void* stream) {
+  return encode_impl(h, feats, lens_T, B, T, state_h, state_c, use_state_in, enc_out, stream, B);
+}
+
+// state_ld: batch stride of state_h / state_c per layer ([L][state_ld][H]); = B for a whole call, the full stream count for a
+// sub-batch of a stateful call (whose rows come first from the pointers passed)
+static int32_t encode_impl(rnnt_b200_handle h, const float* feats, const int32_t* lens_T, int32_t B, int32_t T, float* state_h,
+                           float* state_c, int32_t use_state_in, float* enc_out, void* stream, int state_ld) {
   if (int r = check_ready(h)) return r;
   const rnnt_b200_config& c = h->cfg;
   if (!feats || !enc_out || B < 1 || T < 1) return fail(h, RNNT_B200_ERR_INVALID, "encode: bad arguments");
@@ -903,15 +914,21 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
   if ((state_h == nullptr) != (state_c == nullptr)) return fail(h, RNNT_B200_ERR_INVALID, "encode: state_h and state_c must both be given");
   cudaStream_t st = (cudaStream_t)stream;
   const int H = c.hidden_sz, X = c.n_mels * c.n_stack, Bp = bp_of(B);
-  static const int sub32 = [] { const char* e = getenv("RNNT_SUB32"); return e ? atoi(e) : 0; }();
+  // Sub-batch policy (RNNT_SUB32: -1 default, 0 never, 1 always): stateless offline batches run as 32-row sub-batches of the
+  // cluster split-K kernel (measured: 64 utterances 50.0k x real-time vs 44.6k in one 64-row launch of the round-1 kernel, 256
+  // utterances equal); streaming ticks (T = 2, carried state) are faster in one wide launch of the round-1 kernel (8.7k vs 8.0k x)
+  static const int sub32 = [] { const char* e = getenv("RNNT_SUB32"); return e ? atoi(e) : -1; }();
   static const int lstm_v0 = [] { const char* e = getenv("RNNT_LSTM_V"); return e ? atoi(e) : 2; }();
-  const int enc_cap = (sub32 && lstm_v0 == 2 && h->lstm_tc2_ok) ? 32 : 128;   // the cluster split-K kernel takes 32 rows per launch
-  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->lstm_tc_ok && B > enc_cap && !state_h) {
-    // independent utterances: stateless batches beyond the persistent LSTM kernel's capacity run as sub-batches
+  const bool want32 = sub32 == 1 || (sub32 == -1 && !state_h);
+  const int enc_cap = (want32 && lstm_v0 == 2 && h->lstm_tc2_ok) ? 32 : 128;   // the cluster split-K kernel takes 32 rows per launch
+  if (c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->lstm_tc_ok && B > enc_cap) {
+    // independent utterances / streams: batches beyond the persistent LSTM kernel's capacity run as sub-batches; the state
+    // [L][state_ld][H] is sliced by rows (every layer passes its own base pointer to the kernel)
     for (int b0 = 0; b0 < B; b0 += enc_cap) {
       const int nb = std::min(enc_cap, B - b0);
-      const int r = rnnt_b200_encode(h, feats + (size_t)b0 * T * X, lens_T ? lens_T + b0 : nullptr, nb, T, nullptr, nullptr, 0,
-                                     enc_out + (size_t)b0 * T * H, stream);
+      const int r = encode_impl(h, feats + (size_t)b0 * T * X, lens_T ? lens_T + b0 : nullptr, nb, T,
+                                state_h ? state_h + (size_t)b0 * H : nullptr, state_c ? state_c + (size_t)b0 * H : nullptr, use_state_in,
+                                enc_out + (size_t)b0 * T * H, stream, state_ld);
       if (r) return r;
     }
     return RNNT_B200_OK;
@@ -956,14 +973,16 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
       a.xp = h->xp.as<float>(); a.bn_scale = L.bn_scale; a.bn_shift = L.bn_shift;
       a.y = y; a.y_img = (l == c.enc_layers - 1) ? nullptr : h->a_img.as<uint8_t>();
       a.lens_T = lens_T; a.h_init_vec = L.h0; a.c_init_vec = L.c0;
-      a.state_h_in = use_state_in ? state_h + (size_t)l * B * H : nullptr;
-      a.state_c_in = use_state_in ? state_c + (size_t)l * B * H : nullptr;
-      a.state_h_out = state_h ? state_h + (size_t)l * B * H : nullptr;
-      a.state_c_out = state_c ? state_c + (size_t)l * B * H : nullptr;
+      a.state_h_in = use_state_in ? state_h + (size_t)l * state_ld * H : nullptr;
+      a.state_c_in = use_state_in ? state_c + (size_t)l * state_ld * H : nullptr;
+      a.state_h_out = state_h ? state_h + (size_t)l * state_ld * H : nullptr;
+      a.state_c_out = state_c ? state_c + (size_t)l * state_ld * H : nullptr;
       a.barrier = h->gbar.as<unsigned int>();
       a.T = T; a.B = B; a.H = H;
       static const int dsm_async = [] { const char* e = getenv("RNNT_DSM_ASYNC"); return e ? atoi(e) : 1; }();
       a.dsm_async = dsm_async;
+      static const int trig = [] { const char* e = getenv("RNNT_TRIG"); return e ? atoi(e) : 3; }();
+      a.trig_lanes = std::max(1, std::min(trig, 8));
       static const bool dbg_on2 = getenv("RNNT_LSTM_DBG") != nullptr;
       unsigned long long* dbg = nullptr;
       unsigned long long* dbg_all = nullptr;
@@ -1031,10 +1050,10 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
       a.xp = h->xp.as<float>(); a.bn_scale = L.bn_scale; a.bn_shift = L.bn_shift;
       a.y = y; a.y_img = (l == c.enc_layers - 1) ? nullptr : h->a_img.as<uint8_t>();
       a.lens_T = lens_T; a.h_init_vec = L.h0; a.c_init_vec = L.c0;
-      a.state_h_in = use_state_in ? state_h + (size_t)l * B * H : nullptr;
-      a.state_c_in = use_state_in ? state_c + (size_t)l * B * H : nullptr;
-      a.state_h_out = state_h ? state_h + (size_t)l * B * H : nullptr;
-      a.state_c_out = state_c ? state_c + (size_t)l * B * H : nullptr;
+      a.state_h_in = use_state_in ? state_h + (size_t)l * state_ld * H : nullptr;
+      a.state_c_in = use_state_in ? state_c + (size_t)l * state_ld * H : nullptr;
+      a.state_h_out = state_h ? state_h + (size_t)l * state_ld * H : nullptr;
+      a.state_c_out = state_c ? state_c + (size_t)l * state_ld * H : nullptr;
       a.barrier = h->gbar.as<unsigned int>();
       a.T = T; a.B = B; a.H = H;
       static const bool dbg_on = getenv("RNNT_LSTM_DBG") != nullptr;
@@ -1063,8 +1082,8 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
       continue;
     }
     if (use_state_in) {
-      LAUNCH(1, launch_state_to_T(state_h + (size_t)l * B * H, h->ehT[0].as<float>(), B, Bp, H, st));
-      LAUNCH(1, launch_state_to_T(state_c + (size_t)l * B * H, h->ecT.as<float>(), B, Bp, H, st));
+      LAUNCH(1, launch_state_to_T(state_h + (size_t)l * state_ld * H, h->ehT[0].as<float>(), B, Bp, H, st));
+      LAUNCH(1, launch_state_to_T(state_c + (size_t)l * state_ld * H, h->ecT.as<float>(), B, Bp, H, st));
     } else {
       LAUNCH(1, launch_state_broadcast_T(L.h0, h->ehT[0].as<float>(), B, Bp, H, st));
       LAUNCH(1, launch_state_broadcast_T(L.c0, h->ecT.as<float>(), B, Bp, H, st));
@@ -1079,8 +1098,8 @@ int32_t rnnt_b200_encode(rnnt_b200_handle h, const float* feats, const int32_t* 
       LAUNCH(1, launch_lstm_step(a, st));
     }
     if (state_h) {
-      LAUNCH(1, launch_state_from_T(h->ehT[T & 1].as<float>(), state_h + (size_t)l * B * H, B, Bp, H, st));
-      LAUNCH(1, launch_state_from_T(h->ecT.as<float>(), state_c + (size_t)l * B * H, B, Bp, H, st));
+      LAUNCH(1, launch_state_from_T(h->ehT[T & 1].as<float>(), state_h + (size_t)l * state_ld * H, B, Bp, H, st));
+      LAUNCH(1, launch_state_from_T(h->ecT.as<float>(), state_c + (size_t)l * state_ld * H, B, Bp, H, st));
     }
   }
   if (h->ev) cudaEventRecord(h->ev[1], st);
@@ -1130,10 +1149,25 @@ int32_t rnnt_b200_joint(rnnt_b200_handle h, const float* h_pred, const float* h_
   return RNNT_B200_OK;
 }
 
+static int32_t decode_greedy_impl(rnnt_b200_handle h, const float* enc, const int32_t* lens_T, int32_t B, int32_t T,
+                                  int32_t max_iters, float* pred_state_h, float* pred_out, int32_t use_state_in,
+                                  int32_t* tokens_out, int32_t U_cap, int32_t* ntok_out, double* neg_logp_out,
+                                  uint8_t* iters_out, float* trace_logp, int32_t trace_cap, void* stream, int state_ld);
+
 int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int32_t* lens_T, int32_t B, int32_t T,
                                 int32_t max_iters, float* pred_state_h, float* pred_out, int32_t use_state_in,
                                 int32_t* tokens_out, int32_t U_cap, int32_t* ntok_out, double* neg_logp_out,
                                 uint8_t* iters_out, float* trace_logp, int32_t trace_cap, void* stream) {
+  return decode_greedy_impl(h, enc, lens_T, B, T, max_iters, pred_state_h, pred_out, use_state_in, tokens_out, U_cap, ntok_out, neg_logp_out,
+                            iters_out, trace_logp, trace_cap, stream, B);
+}
+
+// state_ld: batch stride of pred_state_h per layer ([Lp][state_ld][H]); = B for a whole call, the full stream count when this call
+// is a sub-batch of a stateful call (the rows of the sub-batch come first from the pointer passed)
+static int32_t decode_greedy_impl(rnnt_b200_handle h, const float* enc, const int32_t* lens_T, int32_t B, int32_t T,
+                                  int32_t max_iters, float* pred_state_h, float* pred_out, int32_t use_state_in,
+                                  int32_t* tokens_out, int32_t U_cap, int32_t* ntok_out, double* neg_logp_out,
+                                  uint8_t* iters_out, float* trace_logp, int32_t trace_cap, void* stream, int state_ld) {
   if (int r = check_ready(h)) return r;
   const rnnt_b200_config& c = h->cfg;
   if (!enc || !tokens_out || !ntok_out || B < 1 || T < 1 || max_iters < 1 || max_iters > 255)
@@ -1154,21 +1188,29 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
           !decode_tc_plan(c.hidden_sz, c.joint_sz, c.vocab_sz, c.pred_layers, std::min(B, 64), h->sm_count, &probe, c.lm_layers, c.lm_hidden_sz) &&
           decode_tc_plan(c.hidden_sz, c.joint_sz, c.vocab_sz, c.pred_layers, 32, h->sm_count, &probe, c.lm_layers, c.lm_hidden_sz))
         cap = 32;
-      static const int sub32d = [] { const char* e = getenv("RNNT_SUB32"); return e ? atoi(e) : 0; }();
+      static const int sub32d = [] { const char* e = getenv("RNNT_SUB32"); return e ? atoi(e) : -1; }();
       static const int dec_v0 = [] { const char* e = getenv("RNNT_DEC_V"); return e ? atoi(e) : 2; }();
-      if (sub32d && dec_v0 == 2 && h->dec_tc2_ok && !h->lm_blob) cap = 32;   // the cluster split-K decode kernel takes 32 utterances
+      const bool stateless = !(pred_state_h || pred_out || use_state_in || h->lm_blob);
+      if ((sub32d == 1 || (sub32d == -1 && stateless)) && dec_v0 == 2 && h->dec_tc2_ok && !h->lm_blob &&
+          decode_tc2_plan(c.hidden_sz, c.joint_sz, c.vocab_sz, c.pred_layers, 32, h->sm_count, c.lm_layers))
+        cap = 32;   // the cluster split-K decode kernel takes 32 utterances (same policy as the encoder, see rnnt_b200_encode)
     }
     const bool stateful = pred_state_h || pred_out || use_state_in || h->lm_blob;
     if (stateful && B > kDecodeMaxBatch)
       return fail(h, RNNT_B200_ERR_INVALID, "decode_greedy: stateful calls are limited to " + std::to_string(kDecodeMaxBatch) + " streams per call");
-    // (a stateful call beyond the tcgen05 kernel's capacity falls through to the fp32 cooperative kernel below)
-    if (B > cap && !stateful) {
+    // The predictor state [Lp][state_ld][H] / [B][H] is sliceable by rows (the kernels take the layer stride), so stateful
+    // (streaming) calls beyond the tcgen05 kernels' capacity run as sub-batches as well; only the fused LM's feature-major state blob
+    // is not sliceable: with a registered LM blob a wide call still falls through to the fp32 cooperative kernel below.
+    const bool tc_path = c.gemm_mode == RNNT_B200_GEMM_TC_FP16X3 && h->dec_tc_ok;
+    if (B > cap && (!stateful || (tc_path && !h->lm_blob))) {
+      const int H0 = c.hidden_sz;
       for (int b0 = 0; b0 < B; b0 += cap) {
         const int nb = std::min(cap, B - b0);
-        const int r = rnnt_b200_decode_greedy(h, enc + (size_t)b0 * T * c.hidden_sz, lens_T ? lens_T + b0 : nullptr, nb, T, max_iters,
-                                              nullptr, nullptr, 0, tokens_out + (size_t)b0 * U_cap, U_cap, ntok_out + b0,
-                                              neg_logp_out ? neg_logp_out + b0 : nullptr, iters_out ? iters_out + (size_t)b0 * T : nullptr,
-                                              trace_logp ? trace_logp + (size_t)b0 * trace_cap * c.vocab_sz : nullptr, trace_cap, stream);
+        const int r = decode_greedy_impl(h, enc + (size_t)b0 * T * H0, lens_T ? lens_T + b0 : nullptr, nb, T, max_iters,
+                                         pred_state_h ? pred_state_h + (size_t)b0 * H0 : nullptr, pred_out ? pred_out + (size_t)b0 * H0 : nullptr,
+                                         use_state_in, tokens_out + (size_t)b0 * U_cap, U_cap, ntok_out + b0,
+                                         neg_logp_out ? neg_logp_out + b0 : nullptr, iters_out ? iters_out + (size_t)b0 * T : nullptr,
+                                         trace_logp ? trace_logp + (size_t)b0 * trace_cap * c.vocab_sz : nullptr, trace_cap, stream, state_ld);
         if (r) return r;
       }
       return RNNT_B200_OK;
@@ -1221,7 +1263,7 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     t.n_eval = reinterpret_cast<int*>(h->dkeys.as<uint8_t>() + decode_tc2_keys_bytes());
     t.ep = h->ep.as<float>(); t.lens_T = lens_T; t.B = B; t.T = T; t.max_iters = max_iters; t.use_state_in = use_state_in;
     t.part = h->dpart.as<float>(); t.trace_lse = h->dlse.as<float>(); t.max_steps = max_steps;
-    t.state_h = pred_state_h; t.pred_out = pred_out;
+    t.state_h = pred_state_h; t.pred_out = pred_out; t.state_ld = state_ld;
     t.tokens = tokens_out; t.U_cap = U_cap; t.ntok = ntok_out; t.neg_logp = neg_logp_out; t.iters = iters_out;
     t.trace = trace_logp; t.trace_cap = trace_logp ? trace_cap : 0;
     t.barrier = h->gbar.as<unsigned int>();
@@ -1288,7 +1330,7 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     t.keys = h->dkeys.as<unsigned long long>();
     t.n_eval = reinterpret_cast<int*>(h->dkeys.as<uint8_t>() + (size_t)max_steps * dpl.Bq * 8);
     t.max_steps = max_steps;
-    t.state_h = pred_state_h; t.pred_out = pred_out;
+    t.state_h = pred_state_h; t.pred_out = pred_out; t.state_ld = state_ld;
     t.tokens = tokens_out; t.U_cap = U_cap; t.ntok = ntok_out; t.neg_logp = neg_logp_out; t.iters = iters_out;
     t.trace = trace_logp; t.trace_cap = trace_logp ? trace_cap : 0;
     t.barrier = h->gbar.as<unsigned int>();
@@ -1394,6 +1436,7 @@ int32_t rnnt_b200_decode_greedy(rnnt_b200_handle h, const float* enc, const int3
     a.fpart = h->lm_fpart.as<float>();
   }
   LAUNCH(1, launch_decode(a, h->coop_blocks, st));
+  h->fp32_decode_launches += 1;
   if (pred_state_h)
     for (int l = 0; l < c.pred_layers; ++l)
       LAUNCH(1, launch_state_from_T(a.hT[l][0], pred_state_h + (size_t)l * B * H, B, Bp, H, st));
@@ -1841,6 +1884,7 @@ int32_t rnnt_b200_selftest_gemm(rnnt_b200_handle h, const float* A, const float*
 }
 
 int64_t rnnt_b200_kernel_launches(rnnt_b200_handle h) { return h ? h->launches : -1; }
+int64_t rnnt_b200_fp32_decode_launches(rnnt_b200_handle h) { return h ? h->fp32_decode_launches : -1; }
 
 int32_t rnnt_b200_set_profiling(rnnt_b200_handle h, int32_t enable) {
   if (!h) return RNNT_B200_ERR_INVALID;

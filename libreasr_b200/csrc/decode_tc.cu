@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
 #pragma unroll
       for (int i = 0; i < DT_MAX_RPT; ++i)
         hst[l][i] = (l < Lp && i < upt && bvalid)
-                        ? (p.use_state_in ? p.state_h[((size_t)l * B + b) * H + unit0 + i] : w.h0[l][unit0 + i]) : 0.f;
+                        ? (p.use_state_in ? p.state_h[((size_t)l * p.state_ld + b) * H + unit0 + i] : w.h0[l][unit0 + i]) : 0.f;
     auto store_act = [&](uint8_t* img, int k0, int n, const float* v) {   // n consecutive k of batch row b
 #pragma unroll
       for (int j0 = 0; j0 < DT_MAX_RPT; j0 += 4) {
@@ -983,7 +983,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tc_kernel(DecodeTcArgs p
         for (int l = 0; l < Lp; ++l)
 #pragma unroll
           for (int i = 0; i < DT_MAX_RPT; ++i)
-            if (i < upt) p.state_h[((size_t)l * B + b) * H + unit0 + i] = hst[l][i];
+            if (i < upt) p.state_h[((size_t)l * p.state_ld + b) * H + unit0 + i] = hst[l][i];
       if (p.pred_out)
 #pragma unroll
         for (int i = 0; i < DT_MAX_RPT; ++i)

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
     for (int l = 0; l < 2; ++l)
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        hst[l][i] = (bvalid && p.use_state_in) ? p.state_h[((size_t)l * B + fb) * H + unit + i] : w.h0[l][unit + i];
+        hst[l][i] = (bvalid && p.use_state_in) ? p.state_h[((size_t)l * p.state_ld + fb) * H + unit + i] : w.h0[l][unit + i];
         bsc[l][i] = w.bn_scale[l][unit + i];
         bsh[l][i] = w.bn_shift[l][unit + i];
       }
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
       if (p.state_h)
 #pragma unroll
         for (int l = 0; l < 2; ++l)
-          *reinterpret_cast<float2*>(p.state_h + ((size_t)l * B + fb) * H + unit) = make_float2(hst[l][0], hst[l][1]);
+          *reinterpret_cast<float2*>(p.state_h + ((size_t)l * p.state_ld + fb) * H + unit) = make_float2(hst[l][0], hst[l][1]);
       if (p.pred_out) *reinterpret_cast<float2*>(p.pred_out + (size_t)fb * H + unit) = make_float2(gval[0], gval[1]);
     }
   } else if (warp < 8) {

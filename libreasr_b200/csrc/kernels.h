@@ -111,6 +111,7 @@ struct LstmTc2Args {
   int T, B, H;
   int KS, KB;                // filled from the plan by the launcher
   int dsm_async;             // partial tiles through st.async + complete_tx (1) or st.shared::cluster + release arrive (0)
+  int trig_lanes;            // producers (of 8) whose chunk must be visible before the bulk load of a K slice is issued
 };
 cudaError_t configure_lstm_tc2();
 bool lstm_tc2_plan(int H, int B, int sms, LstmTc2Plan* pl);
@@ -262,7 +263,8 @@ struct DecodeTcArgs {
   int* n_eval;                     // [B] evaluations per utterance (out)
   int max_steps;
   float* trace_lse;
-  float* state_h; float* pred_out; // [Lp][B][H], [B][H] in/out (nullable unless use_state_in)
+  float* state_h; float* pred_out; // [Lp][state_ld][H] (rows of this launch first), [B][H] in/out (nullable unless use_state_in)
+  int state_ld;                    // batch stride of state_h per layer (= B unless the launch is a slice of a larger state)
   int32_t* tokens; int U_cap; int32_t* ntok; double* neg_logp; uint8_t* iters; float* trace; int trace_cap;
   unsigned int* barrier;           // grid phase counter, zero at launch
   unsigned long long* dbg; int dbg_cap;   // optional (time, tag) trail of CTA 0 (tuning aid)
@@ -293,7 +295,8 @@ struct DecodeTc2Args {
   int* n_eval;                     // [B]
   int max_steps;
   float* trace_lse;
-  float* state_h; float* pred_out; // [2][B][H], [B][H] in/out (nullable unless use_state_in)
+  float* state_h; float* pred_out; // [2][state_ld][H] (rows of this launch first), [B][H] in/out (nullable unless use_state_in)
+  int state_ld;                    // batch stride of state_h per layer
   int32_t* tokens; int U_cap; int32_t* ntok; double* neg_logp; uint8_t* iters; float* trace; int trace_cap;
   unsigned int* barrier;           // launch-start counter, zero at launch
   unsigned long long* dbg; int dbg_cap;

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_layer_tc2_kernel(LstmTc2Ar
       const uint8_t* src = p.x_img[t & 1] + slice_off + (size_t)lt * 16;
       uint4 r[L2_MAX_KS * 4];
       long long lc0 = lprof ? clock64() : 0;
-      poll_issue<L2_MAX_KS * 4>(src, NL, tag, r);
+      poll_issue<L2_MAX_KS * 4>(src, NL, tag, r, p.trig_lanes);
       if (lprof) { const long long c1 = clock64(); lcyc[0] += c1 - lc0; lc0 = c1; }   // until the first chunk of h_{t-1} shows up
 #pragma unroll
       for (int kb = 0; kb < L2_MAX_KS; ++kb) {

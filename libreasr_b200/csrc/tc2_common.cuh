@@ -103,13 +103,13 @@ __device__ __forceinline__ void chunk_strip_tag(uint4& r) { r.w &= 0xFFFEFFFFu; 
 // issues every load back to back; `poll_validate_kb` afterwards re-reads only the stale chunks of one k-block, in
 // parallel rounds, so the first k-blocks can be handed to the MMA while the stragglers of the later ones are in flight.
 template <int N>
-__device__ __forceinline__ void poll_issue(const uint8_t* src, int n, uint32_t tag, uint4 (&r)[N]) {
+__device__ __forceinline__ void poll_issue(const uint8_t* src, int n, uint32_t tag, uint4 (&r)[N], int min_valid = 1) {
   // lanes 0-7 = the eight chunks (eight producer CTAs) of one 128-byte line: one sector request per producer and round trip
   const bool poller = (threadIdx.x & 31) < 8;
   r[0] = make_uint4(0u, 0u, 0u, (tag ^ 1u) << 16);
   for (;;) {
     if (poller) r[0] = ld_relaxed_v4(src);
-    if (__any_sync(0xffffffffu, poller && chunk_tag_ok(r[0], tag))) break;
+    if (__popc(__ballot_sync(0xffffffffu, poller && chunk_tag_ok(r[0], tag))) >= min_valid) break;   // min_valid of the 8 producers have published
   }
   if (!poller) r[0] = ld_relaxed_v4(src);
 #pragma unroll

@@ -403,6 +403,10 @@ class Engine:
     def kernel_launches(self):
         return int(self.lib.rnnt_b200_kernel_launches(self._h))
 
+    def fp32_decode_launches(self):
+        """Launches of the fp32 cooperative decode kernel (the slow twin): 0 on the tensor-core path."""
+        return int(self.lib.rnnt_b200_fp32_decode_launches(self._h))
+
     def set_profiling(self, on):
         self._ck(self.lib.rnnt_b200_set_profiling(self._h, 1 if on else 0))
 

@@ -538,13 +538,15 @@ def test_lm_fusion_wide_batches_match_oracle(B):
 
 
 def test_stream_session_beyond_64_streams():
-    """70 lock-step streams: more than the tcgen05 decode kernel's 64, so the stateful decode falls through to the fp32
-    cooperative kernel while the encoder stays on its own path; spot-checked streams equal the oracle."""
+    """70 lock-step streams: more than one launch of the tcgen05 decode kernel takes (64), so the stateful decode runs as two
+    sub-batches over row slices of the predictor state -- the fp32 cooperative kernel is never launched in gemm_mode 1;
+    spot-checked streams equal the oracle."""
     from libreasr_b200.api import StreamBatch
 
     cfg, sd, m, orc = model_for("tiny")
     S, n_chunks = 70, 14
     audio = weights.make_audio(S, n_chunks * CHUNK, seed=73)
+    f32_before = m.engine().fp32_decode_launches()
     sb = StreamBatch(m.engine(), S, max_iters=10)
     ticks = [[] for _ in range(S)]
     for j in range(n_chunks):
@@ -553,7 +555,9 @@ def test_stream_session_beyond_64_streams():
             for b in range(S):
                 ticks[b].append(new[b])
     sb.close()
-    for b in (0, 33, 64, 69):
+    if GEMM_MODE == 1:
+        assert m.engine().fp32_decode_launches() == f32_before      # the tensor-core kernels served every tick
+    for b in (0, 33, 63, 64, 69):
         assert ticks[b] == _oracle_stream_tokens(orc, cfg, audio[b], n_chunks), f"stream {b}"
 
 
