@@ -293,6 +293,23 @@ int32_t rnnt_b200_decode_beam(rnnt_b200_handle h, const float* enc, const int32_
                               int32_t max_iters, int32_t* tokens_out, int32_t U_cap, int32_t* ntok_out, double* score_out,
                               void* stream);
 
+
+/* ---- training-time forward: joint lattice + RNN-T loss (eval mode, no gradients) ---------------------- */
+
+/* Transducer.forward (libreasr/lib/models.py:308-359) in eval mode and the loss get_loss_func("rnnt") computes from its
+ * output (libreasr/lib/loss.py:72-110 -> warp_rnnt.rnnt_loss(..., average_frames=False); restated from its definition,
+ * oracle/rnnt_loss.py).  feats [N,T,X] (what the transform pipeline yields), lens_T [N] encoder steps or NULL,
+ * labels [N,Umax] int32 (padded), label_lens [N].  The predictor is teacher-forced over cat(bos, labels) (U = Umax+1
+ * positions).  loss_out [N] fp64 = -log p(labels | audio) per sequence; lattice_out (nullable) [N,T,U,V] = the
+ * log_softmax lattice forward() returns (positions beyond (lens_T, label_lens) hold the values of the padded
+ * computation).  All pointers device; N <= 256; gemm_mode 1. */
+int32_t rnnt_b200_forward_loss(rnnt_b200_handle h, const float* feats, const int32_t* lens_T, const int32_t* labels,
+                               const int32_t* label_lens, int32_t N, int32_t T, int32_t Umax, float* lattice_out,
+                               double* loss_out, void* stream);
+/* The loss alone from a given log-probability lattice [N,T,U,V] (what the reference's _loss_func receives as `inp`). */
+int32_t rnnt_b200_rnnt_loss(rnnt_b200_handle h, const float* lattice, const int32_t* lens_T, const int32_t* labels,
+                            const int32_t* label_lens, int32_t N, int32_t T, int32_t U, double* loss_out, void* stream);
+
 /* ---- self test -------------------------------------------------------------------------------- */
 
 /* Runs the library's own GEMM (the contraction behind the LSTM gate and joint projections)

@@ -60,6 +60,8 @@ SIGNATURES = {
     "rnnt_b200_stream_open": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
     "rnnt_b200_stream_push": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _vp, C.POINTER(_i32), _vp]),
     "rnnt_b200_decode_beam": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "rnnt_b200_forward_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "rnnt_b200_rnnt_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "rnnt_b200_stream_reset": (_i32, [_vp, _i32]),
     "rnnt_b200_stream_reset_state": (_i32, [_vp, _i32]),
     "rnnt_b200_stream_close": (_i32, [_vp]),

@@ -82,6 +82,7 @@ struct rnnt_b200_handle_s {
   // beam search (beam.cu): 256-row-tile weight images for gemm_tc.cu, built at the first call; workspaces
   uint8_t *bm_w1p = nullptr, *bm_w2 = nullptr, *bm_k1 = nullptr, *bm_r[2] = {nullptr, nullptr};
   DevBuf bm_state, bm_meta, bm_aimg, bm_f32;
+  DevBuf lt_f32, lt_i32, lt_enc;       // lattice.cu workspaces (training-time forward + loss)
   uint8_t* R_img[kMaxPredLayers] = {nullptr, nullptr, nullptr, nullptr};
   uint8_t* K_img[kMaxPredLayers] = {nullptr, nullptr, nullptr, nullptr};
   DevBuf dimg;                         // decode activation operand images
@@ -1657,6 +1658,74 @@ int32_t rnnt_b200_decode_beam(rnnt_b200_handle h, const float* enc, const int32_
   cudaError_t e = launch_beam_search(a, bf, max_iters, tokens_out, U_cap, ntok_out, score_out, &launches, st);
   if (e != cudaSuccess) return fail_cuda(h, e, "decode_beam");
   h->launches += launches;
+  return RNNT_B200_OK;
+}
+
+// ---------------- training-time forward: joint lattice + RNN-T loss (lattice.cu) ----------------
+int32_t rnnt_b200_rnnt_loss(rnnt_b200_handle h, const float* lattice, const int32_t* lens_T, const int32_t* labels,
+                            const int32_t* label_lens, int32_t N, int32_t T, int32_t U, double* loss_out, void* stream) {
+  if (int r = check_ready(h)) return r;
+  if (!lattice || !labels || !label_lens || !loss_out || N < 1 || T < 1 || U < 1) return fail(h, RNNT_B200_ERR_INVALID, "rnnt_loss: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = (int64_t)N * T * U;
+  CK(h->lt_f32.ensure((size_t)rows * 2 * 4));
+  float* lpb = h->lt_f32.as<float>();
+  float* lpl = lpb + rows;
+  LAUNCH(1, launch_lattice_gather(lattice, rows, h->cfg.vocab_sz, labels, T, U, U - 1, h->cfg.blank, lpb, lpl, st));
+  LAUNCH(1, launch_rnnt_alpha(lpb, lpl, lens_T, label_lens, N, T, U, loss_out, st));
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_forward_loss(rnnt_b200_handle h, const float* feats, const int32_t* lens_T, const int32_t* labels,
+                               const int32_t* label_lens, int32_t N, int32_t T, int32_t Umax, float* lattice_out,
+                               double* loss_out, void* stream) {
+  if (int r = check_ready(h)) return r;
+  const rnnt_b200_config& c = h->cfg;
+  if (!feats || !labels || !label_lens || !loss_out || N < 1 || N > kDecodeMaxBatch || T < 1 || Umax < 1)
+    return fail(h, RNNT_B200_ERR_INVALID, "forward_loss: bad arguments (1 <= N <= 256)");
+  if (c.gemm_mode != RNNT_B200_GEMM_TC_FP16X3) return fail(h, RNNT_B200_ERR_INVALID, "forward_loss: needs gemm_mode 1 (tcgen05)");
+  if ((c.hidden_sz % 64) || (c.joint_sz % 64)) return fail(h, RNNT_B200_ERR_INVALID, "forward_loss: H and J must be multiples of 64");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = c.hidden_sz, J = c.joint_sz, V = c.vocab_sz, U = Umax + 1;
+  if (int r = ensure_beam_weights(h, st)) return r;     // 256-row-tile images of W1p / W2 for gemm_tc.cu
+  // encoder (models.py:318-320), then the encoder half of the joint's first Linear for all frames
+  CK(h->lt_enc.ensure((size_t)N * T * H * 4));
+  float* enc = h->lt_enc.as<float>();
+  if (int r = rnnt_b200_encode(h, feats, lens_T, N, T, nullptr, nullptr, 0, enc, stream)) return r;
+  const int64_t M = (int64_t)N * T;
+  if (int r = ensure_decode_ws(h, N, T, 0)) return r;
+  CK(h->a_img.ensure(gemm_tc_a_image_bytes(M, H)));
+  LAUNCH(1, launch_to_image(enc, H, M, H, 128, h->a_img.as<uint8_t>(), st));
+  LAUNCH(1, launch_gemm_tc(h->a_img.as<uint8_t>(), h->W1e_img, h->dw.b1, h->ep.as<float>(), J, M, J, H, st));
+  // workspaces: g_all [N*U][H] | pp_all [N*U][J] | lpb, lpl [N*T*U] | logits chunk [CH][V] | predictor state, step output
+  const int64_t rows = (int64_t)N * T * U;
+  const int CH = 8192;
+  size_t fo = 0;
+  auto takef = [&](size_t n) { const size_t o = fo; fo += (n + 63) & ~(size_t)63; return o; };
+  const size_t f_g = takef((size_t)N * U * H), f_pp = takef((size_t)N * U * J), f_lpb = takef((size_t)rows), f_lpl = takef((size_t)rows),
+               f_lg = takef((size_t)CH * V), f_st = takef((size_t)c.pred_layers * N * H), f_out = takef((size_t)N * H);
+  CK(h->lt_f32.ensure(fo * 4));
+  float* fb = h->lt_f32.as<float>();
+  CK(h->lt_i32.ensure((size_t)N * 4));
+  int32_t* toks = h->lt_i32.as<int32_t>();
+  // predictor, teacher-forced over cat(bos, y) (models.py:326-336): one step per label position, state carried
+  for (int u = 0; u < U; ++u) {
+    LAUNCH(1, launch_lattice_tokens(labels, N, Umax, u, c.bos, toks, st));
+    if (int r = rnnt_b200_predict(h, toks, N, fb + f_st, u > 0 ? 1 : 0, fb + f_out, stream)) return r;
+    CK(cudaMemcpy2DAsync(fb + f_g + (size_t)u * H, (size_t)U * H * 4, fb + f_out, (size_t)H * 4, (size_t)H * 4, N, cudaMemcpyDeviceToDevice, st));
+  }
+  // pred half of the joint's first Linear for every label position
+  CK(h->bm_aimg.ensure(gemm_tc_a_image_bytes(std::max<int64_t>((int64_t)N * U, CH), std::max(H, J))));
+  LAUNCH(1, launch_to_image(fb + f_g, H, (int64_t)N * U, H, 128, h->bm_aimg.as<uint8_t>(), st));
+  LAUNCH(1, launch_gemm_tc(h->bm_aimg.as<uint8_t>(), h->bm_w1p, nullptr, fb + f_pp, J, (int64_t)N * U, J, H, st));
+  // the lattice in L2-sized chunks of rows (n, t, u): z image -> logits -> (log p(blank), log p(label)) [+ log_softmax rows]
+  for (int64_t r0 = 0; r0 < rows; r0 += CH) {
+    const int nr = (int)std::min<int64_t>(CH, rows - r0);
+    LAUNCH(1, launch_lattice_z_image(fb + f_pp, h->ep.as<float>(), T, U, r0, nr, J, h->bm_aimg.as<uint8_t>(), st));
+    LAUNCH(1, launch_gemm_tc(h->bm_aimg.as<uint8_t>(), h->bm_w2, h->dw.b2, fb + f_lg, V, nr, V, J, st));
+    LAUNCH(1, launch_lattice_lse(fb + f_lg, nr, V, r0, labels, T, U, Umax, c.blank, fb + f_lpb, fb + f_lpl, lattice_out, st));
+  }
+  LAUNCH(1, launch_rnnt_alpha(fb + f_lpb, fb + f_lpl, lens_T, label_lens, N, T, U, loss_out, st));
   return RNNT_B200_OK;
 }
 

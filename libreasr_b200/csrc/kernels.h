@@ -335,6 +335,16 @@ struct BeamBuffers {
 cudaError_t launch_beam_search(const BeamArgs& a, const BeamBuffers& bf, int max_iters, int32_t* tokens, int U_cap, int32_t* ntok, double* score,
                                int* launches, cudaStream_t st);
 
+// ---------------- lattice.cu (training-time forward: joint lattice + RNN-T loss, eval mode) ----------------
+cudaError_t launch_lattice_tokens(const int32_t* labels, int N, int Umax, int u, int bos, int32_t* out, cudaStream_t st);
+cudaError_t launch_lattice_z_image(const float* pp, const float* ep, int T, int U, int64_t row0, int rows, int J, uint8_t* img, cudaStream_t st);
+cudaError_t launch_lattice_lse(const float* logits, int rows, int V, int64_t row0, const int32_t* labels, int T, int U, int Umax, int blank,
+                               float* lp_blank, float* lp_label, float* lattice_out, cudaStream_t st);
+cudaError_t launch_lattice_gather(const float* lat, int64_t rows, int V, const int32_t* labels, int T, int U, int Umax, int blank, float* lp_blank,
+                                  float* lp_label, cudaStream_t st);
+cudaError_t launch_rnnt_alpha(const float* lp_blank, const float* lp_label, const int32_t* xl, const int32_t* yl, int N, int T, int U, double* loss,
+                              cudaStream_t st);
+
 // standalone predictor step / joint (same phase code, one launch per phase)
 struct PredictArgs {
   DecodeWeights w;

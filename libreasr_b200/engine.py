@@ -329,6 +329,38 @@ class Engine:
                 "state": (ph, po) if ph is not None else None}
 
     # ---- whole path --------------------------------------------------------------------------------
+    # ---- training-time forward: joint lattice + RNN-T loss (eval mode, no gradients) ---------------------
+    def forward_loss(self, feats, lens_T, labels, label_lens, want_lattice=False):
+        """``Transducer.forward`` (models.py:308-359, eval mode) + the RNN-T loss of loss.py:72-110 on its output.
+        feats [N,T,X], lens_T [N] | None, labels [N,Umax] (padded), label_lens [N] ->
+        dict(loss [N] fp64 = -log p(labels | audio), lattice [N,T,Umax+1,V] log-probabilities | None)."""
+        feats = self._f32(feats)
+        N, T, X = feats.shape
+        if X != self.cfg.feature_sz:
+            raise ValueError(f"feature size mismatch; expected {self.cfg.feature_sz} got {X}")
+        labels = self._i32(labels)
+        Umax = labels.shape[1]
+        lens_T, label_lens = self._i32(lens_T), self._i32(label_lens)
+        loss = torch.zeros(N, dtype=torch.float64, device=self.device)
+        lat = torch.empty(N, T, Umax + 1, self.cfg.vocab_sz, device=self.device) if want_lattice else None
+        self._ck(self.lib.rnnt_b200_forward_loss(self._h, _ptr(feats), _ptr(lens_T), _ptr(labels), _ptr(label_lens), N, T, Umax,
+                                                 _ptr(lat), _ptr(loss), self._stream()))
+        return {"loss": loss, "lattice": lat}
+
+    def rnnt_loss(self, lattice, lens_T, labels, label_lens):
+        """Per-sequence RNN-T negative log-likelihood from a log-probability lattice [N,T,U,V] (U = label columns + 1)."""
+        lattice = self._f32(lattice)
+        N, T, U, V = lattice.shape
+        if V != self.cfg.vocab_sz:
+            raise ValueError("lattice vocabulary size mismatch")
+        labels = self._i32(labels)
+        if labels.shape[1] != U - 1:
+            raise ValueError(f"labels must have U - 1 = {U - 1} columns")
+        loss = torch.zeros(N, dtype=torch.float64, device=self.device)
+        self._ck(self.lib.rnnt_b200_rnnt_loss(self._h, _ptr(lattice), _ptr(self._i32(lens_T)), _ptr(labels), _ptr(self._i32(label_lens)),
+                                              N, T, U, _ptr(loss), self._stream()))
+        return loss
+
     def decode_beam(self, enc, lens_T=None, width=4, max_iters=3):
         """Beam search over encoder output [B,T,H] (not in the reference; algorithm: oracle/beam.py).  Returns the best
         hypothesis per utterance: dict(tokens [B,U], ntok [B], score [B] fp64 log-probability)."""

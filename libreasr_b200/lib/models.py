@@ -264,7 +264,19 @@ class Transducer(nn.Module):
             print(f"{name.ljust(10, ' ')} | {t:4.2f}ms")
 
     def forward(self, tpl):
-        raise NotImplementedError("training forward (models.py:308-359) is outside the built inference path")
+        """``(x, y, xl, yl)`` -> the log_softmax joint lattice [N, T, U, V] (models.py:308-359), EVAL MODE ONLY: the engine has no
+        autograd, so this serves validation / loss evaluation (``libreasr_b200.lib.loss``), not a training step.  Like the
+        reference outside training, the predictor is teacher-forced over ``cat(bos, y)`` (grab_bos, models.py:286-306)."""
+        if self.training:
+            raise NotImplementedError("Transducer.forward in training mode needs gradients; the B200 path is inference-only "
+                                      "(call .eval() for the validation-time lattice / loss)")
+        x, y, xl, yl = tpl
+        eng = self.engine()
+        x = x.to(eng.device, torch.float32)
+        x = x.reshape(x.size(0), x.size(1), -1)                      # models.py:319
+        r = eng.forward_loss(x, xl, y, yl, want_lattice=True)
+        self._last_loss = r["loss"]
+        return r["lattice"]
 
     # ---- inference (models.py:361-455) ---------------------------------------------------
     def decode(self, *args, **kwargs):

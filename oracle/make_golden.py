@@ -231,6 +231,25 @@ def beam_fixture(name, widths, n_utt, n_samples, audio_seed, max_iters=3):
     return out
 
 
+def forward_fixture(name="tiny", N=3, T=14, Umax=5, seed=51):
+    """``Transducer.forward`` (models.py:308-359) of the imported reference in eval mode: the training-time joint lattice.
+    Lengths are ragged; the lattice is compared on the valid region only."""
+    cfg = weights.CONFIGS[name]
+    ref = build_reference(cfg)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, T, cfg.feature_sz, 1, generator=g)
+    y = torch.randint(3, cfg.vocab_sz, (N, Umax), generator=g)
+    xl = torch.tensor([T, T - 3, T - 5][:N])
+    yl = torch.tensor([Umax, Umax - 2, Umax - 1][:N])
+    for n in range(N):
+        y[n, int(yl[n]):] = 0
+    with torch.no_grad():
+        lat = ref((x, y, xl, yl))
+    print(f"[{name} forward] lattice {tuple(lat.shape)}")
+    return {"config": name, "weight_seed": WEIGHT_SEED, "x": x[..., 0].numpy(), "y": y.numpy().astype(np.int32), "xl": xl.numpy().astype(np.int32),
+            "yl": yl.numpy().astype(np.int32), "lattice": lat.numpy()}
+
+
 LM_WEIGHT_SEED = 4321
 
 
@@ -319,6 +338,7 @@ def main():
         "tiny_stream": lambda: stream_fixture("tiny", n_chunks=40, audio_seed=22),
         "tiny_stream_reset": lambda: stream_fixture("tiny", n_chunks=44, audio_seed=23, reset_after=(4, 11)),
         "tiny_modules": lambda: modules_fixture("tiny"),
+        "tiny_forward": lambda: forward_fixture("tiny"),
         "cfg2_offline": lambda: offline_fixture("cfg2", n_utt=2, n_samples=80000, audio_seed=105),
         "cfg2_stream": lambda: stream_fixture("cfg2", n_chunks=50, audio_seed=47),
         "ref_offline": lambda: offline_fixture("ref", n_utt=1, n_samples=48000, audio_seed=25),

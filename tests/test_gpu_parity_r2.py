@@ -183,3 +183,49 @@ def test_checkpoint_bundle_then_decode(tmp_path):
         toks = m.decode_greedy(feats.unsqueeze(-1), max_iters=int(g["max_iters"]))[0]
         assert toks == g[f"tokens_{b}"].tolist()
     m._drop_engine()
+
+
+def test_forward_lattice_and_rnnt_loss():
+    """Row f3: Transducer.forward (models.py:308-359, eval mode) on the GPU == the imported reference's lattice (fixture
+    tiny_forward) on the valid region (2e-4), and the RNN-T loss (loss.py:72-110 -> warp_rnnt, restated in oracle/rnnt_loss.py:
+    unpinned) == the fp64 CPU recursion; a second, larger random case against the oracle end to end."""
+    from oracle import rnnt_loss as RL
+    from libreasr_b200.lib.loss import get_loss_func
+
+    g = load_golden("tiny_forward")
+    cfg, sd, m, orc = model_for("tiny")
+    m.eval()
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    xl, yl = torch.from_numpy(g["xl"]), torch.from_numpy(g["yl"])
+    lat = m((x[..., None].cuda(), y.cuda(), xl.cuda(), yl.cuda()))
+    ref = torch.from_numpy(g["lattice"])
+    assert tuple(lat.shape) == tuple(ref.shape)
+    for n in range(x.shape[0]):
+        T, U = int(xl[n]), int(yl[n]) + 1
+        assert float((lat[n, :T, :U].cpu() - ref[n, :T, :U]).abs().max()) < 2e-4
+    want = RL.rnnt_loss(ref, g["y"], g["xl"], g["yl"])
+    got = m._last_loss.cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-3)
+    loss_fn = get_loss_func("rnnt", m.engine())
+    per_seq = loss_fn(lat, (y.cuda(), yl.cuda(), xl.cuda()), reduction="none").cpu().numpy()
+    np.testing.assert_allclose(per_seq, want, atol=2e-3)
+    assert abs(float(loss_fn(lat, (y.cuda(), yl.cuda(), xl.cuda()))) - want.mean()) < 2e-3
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m((x[..., None].cuda(), y.cuda(), xl.cuda(), yl.cuda()))
+    m.eval()
+    # larger case, chunked lattice (N*T*U > one 8192-row chunk), against the oracle
+    gen = torch.Generator().manual_seed(61)
+    N, T, Umax = 5, 60, 33
+    x2 = torch.randn(N, T, cfg.feature_sz, generator=gen)
+    y2 = torch.randint(3, cfg.vocab_sz, (N, Umax), generator=gen)
+    xl2 = torch.tensor([60, 51, 60, 37, 44])
+    yl2 = torch.tensor([33, 20, 1, 17, 30])
+    for n in range(N):
+        y2[n, int(yl2[n]):] = 0
+    r = m.engine().forward_loss(x2.cuda(), xl2.cuda(), y2.cuda(), yl2.cuda(), want_lattice=True)
+    lat2 = RL.forward_lattice(orc, x2, y2, xl2.numpy(), yl2.numpy())
+    for n in range(N):
+        Tn, Un = int(xl2[n]), int(yl2[n]) + 1
+        assert float((r["lattice"][n, :Tn, :Un].cpu() - lat2[n, :Tn, :Un]).abs().max()) < 3e-4
+    np.testing.assert_allclose(r["loss"].cpu().numpy(), RL.rnnt_loss(lat2, y2.numpy(), xl2.numpy(), yl2.numpy()), atol=2e-2, rtol=1e-4)

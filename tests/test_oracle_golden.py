@@ -190,3 +190,41 @@ def test_qint8_lm_study_fixture_is_consistent():
         assert max(len(a), len(c)) - same == int(q[f"n_diff_{b}"])
         tot += int(q[f"n_diff_{b}"])
     assert tot + int(q["n_diff_stream"]) == int(q["n_diff_total"]) <= 2
+
+
+def test_forward_lattice_matches_reference_forward():
+    """Row f3: ``Transducer.forward`` (models.py:308-359, eval mode) -- the oracle's lattice equals the imported reference's on
+    the valid (t < xl, u <= yl) region; the RNN-T loss recursion (loss.py:72-110 -> warp_rnnt, restated: unpinned) gives finite
+    values that drop when the lattice favours the labels."""
+    from oracle import rnnt_loss as RL
+
+    g = load_golden("tiny_forward")
+    cfg, orc = _model(g)
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    xl, yl = g["xl"], g["yl"]
+    lat = RL.forward_lattice(orc, x, y, xl, yl)
+    ref = torch.from_numpy(g["lattice"])
+    assert lat.shape == ref.shape
+    for n in range(x.shape[0]):
+        T, U = int(xl[n]), int(yl[n]) + 1
+        np.testing.assert_allclose(lat[n, :T, :U].numpy(), ref[n, :T, :U].numpy(), atol=5e-5)
+    loss = RL.rnnt_loss(ref, g["y"], xl, yl)
+    assert np.all(np.isfinite(loss)) and np.all(loss > 0)
+    # brute force on the smallest sample: sum over all monotone alignments
+    n = int(np.argmin(xl * (yl + 1)))
+    T, U = int(xl[n]), int(yl[n])
+    lp = ref[n].double().numpy()
+    import itertools
+
+    tot = -np.inf
+    for ups in itertools.combinations(range(T + U - 1), U):     # positions of the U label emissions among T-1+U moves
+        t = u = 0
+        s = 0.0
+        for k in range(T + U - 1):
+            if k in ups:
+                s += lp[t, u, int(g["y"][n][u])]; u += 1
+            else:
+                s += lp[t, u, 0]; t += 1
+        s += lp[T - 1, U, 0]
+        tot = np.logaddexp(tot, s)
+    assert abs(-tot - loss[n]) < 1e-8
