@@ -270,6 +270,12 @@ def leg_strong(eng, dev, dist, rank, world, base_dev, sizes=(256, 512, 1024, 204
     return out
 
 
+def _trace(msg):
+    """BENCH_TRACE=1: phase markers on stderr (where did a run stall?)."""
+    if os.environ.get("BENCH_TRACE"):
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_product(args):
     from libreasr_b200 import synth
     from libreasr_b200.engine import Engine, tokens_to_lists
@@ -311,7 +317,9 @@ def run_product(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput (value) ----
+    _trace("engine ready; warm-up")
     for i in range(args.warmup):
+        _trace(f"warm-up step {i}")
         res = eng.transcribe(devb[i % N_ROTATE], max_iters=MAX_ITERS)
     barrier()
     l0 = eng.kernel_launches()
@@ -322,8 +330,12 @@ def run_product(args):
     e0.record()
     for i in range(args.steps):
         res = eng.transcribe(devb[i % N_ROTATE], max_iters=MAX_ITERS)
+        if os.environ.get("BENCH_TRACE"):
+            torch.cuda.synchronize(dev)
+            _trace(f"timed step {i} (batch {i % N_ROTATE}) done")
     e1.record()
     barrier()
+    _trace("device-resident loop done")
     sampler.end()
     ms_total = e0.elapsed_time(e1)
     stage = eng.stage_times_ms()
@@ -361,6 +373,7 @@ def run_product(args):
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     sampler.end()
+    _trace("e2e loop done")
     clocks = sampler.stop() if rank == 0 else None
 
     # max over ranks (+ every rank's own time: explains where a weak-scaling loss comes from)
@@ -437,7 +450,9 @@ def run_product(args):
                     "note": ("dependent-chain (latency) bound at batch 32 (DESIGN.md section 4): fraction = algorithmic flops / sustained bf16 tensor peak; "
                              "the 3xFP16 split issues 3 fp16 MACs per algorithmic MAC" if tc else "fp32 CUDA-core mode; fraction vs the bf16 tensor peak"),
                     "per_kernel": per_kernel}
+        _trace("cpu baseline")
         cpu = cpu_baseline(cfg, n, budget_s=args.cpu_budget)
+        _trace("cpu baseline done")
         line = {
             "metric": "streaming RTFx (audio-s/wall-s)", "value": round(value, 1), "unit": "x real-time",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),

@@ -1259,6 +1259,8 @@ static int32_t decode_greedy_impl(rnnt_b200_handle h, const float* enc, const in
     for (int i = 0; i < nimg; ++i) t.img[i] = h->dimg.as<uint8_t>() + (size_t)(2 * i) * one;
     static const int n_spec = [] { const char* e = getenv("RNNT_DEC_SPEC"); return e ? atoi(e) : 2; }();
     t.n_spec = std::max(1, std::min(n_spec, decode_tc2_max_spec()));
+    static const int dec_tune = [] { const char* e = getenv("RNNT_DEC_TUNE"); return e ? atoi(e) : 6; }();
+    t.tune = dec_tune;
     t.img_stride = one;
     t.keys = h->dkeys.as<unsigned long long>();
     t.n_eval = reinterpret_cast<int*>(h->dkeys.as<uint8_t>() + decode_tc2_keys_bytes());

@@ -317,18 +317,30 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
         }
       }
     };
-    auto phase_c0 = [&]() {
-      float vx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (bvalid && c.emit[fb]) {   // Embedding -> Linear -> kernel_0 folded into a [V][3H] table (models.py:182-183)
-        const float* row = w.table0 + (size_t)c.tok[fb] * (3 * H);
+    float vpre[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // table row of the token this thread's utterance is about to emit, fetched ahead of the rule
+    auto load_table0 = [&](int tok, float (&vx)[6]) {   // Embedding -> Linear -> kernel_0 folded into a [V][3H] table (models.py:182-183)
+      const float* row = w.table0 + (size_t)tok * (3 * H);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          vx[3 * i + 0] = row[unit + i]; vx[3 * i + 1] = row[H + unit + i]; vx[3 * i + 2] = row[2 * H + unit + i];
+      for (int i = 0; i < 2; ++i) {
+        vx[3 * i + 0] = row[unit + i]; vx[3 * i + 1] = row[H + unit + i]; vx[3 * i + 2] = row[2 * H + unit + i];
+      }
+    };
+    // tok_pre: the token whose row sits in vpre (-1: none).  The replay that produced it reads the control state without a
+    // barrier against the rule, so it is only a hint: the row is used iff it is the row of the token the rule has recorded.
+    auto phase_c0 = [&](int tok_pre) {
+      float vx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (bvalid && c.emit[fb]) {
+        if (tok_pre == c.tok[fb]) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) vx[i] = vpre[i];
+        } else {
+          load_table0(c.tok[fb], vx);
         }
       }
       gru_cell(0, vx);
-      publish(IMG_H0, hst[0][0], hst[0][1]);
+      // BN(h0') feeds JK1 on the dependent chain; h0' itself only the speculative recurrent product of the NEXT emission
       publish(IMG_X, hst[0][0] * bsc[0][0] + bsh[0][0], hst[0][1] * bsc[0][1] + bsh[0][1]);
+      publish(IMG_H0, hst[0][0], hst[0][1]);
     };
     auto phase_c1 = [&]() {
       float kb[6];
@@ -343,14 +355,14 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
       gru_cell(1, vx);
       gval[0] = hst[1][0] * bsc[1][0] + bsh[1][0];
       gval[1] = hst[1][1] * bsc[1][1] + bsh[1][1];
+      publish(IMG_G, gval[0], gval[1]);       // g feeds JA on the dependent chain, h1' only the speculative JR1
       publish(IMG_H1, hst[1][0], hst[1][1]);
-      publish(IMG_G, gval[0], gval[1]);
     };
 
     if (!p.use_state_in) {   // feed BOS from the learnable initial state (models.py:397-398)
       epi_rec(0);
       epi_rec(1);
-      phase_c0();
+      phase_c0(-1);
       phase_c1();
     }
     bool pending = true, any_upd = true;
@@ -394,55 +406,80 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
 #pragma unroll
         for (int zs = 0; zs < D2_MAXS; ++zs)
           if (zs < NS && zs < 2) jb[zs] = send_job(64, RB, rpB);
+        // first pass, on the dependent chain: the logits of my rows and their (max, arg max) -> key
+        float lv[D2_MAXS][4];
 #pragma unroll
         for (int zs = 0; zs < D2_MAXS; ++zs) {
           keys[zs] = (unsigned long long)ktag;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) lv[zs][i] = -INFINITY;
           if (zs < NS) {
             if (zs >= 2) jb[zs] = send_job(64, RB, rpB);   // a third frame reuses the first frame's buffer: only after its release
             const float* pr = wait_job(jb[zs]);
-            float lv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
             for (int sr = 0; sr < D2_CL; ++sr) {
               const float* ps = pr + (size_t)sr * D2_NB * D2_RP + fw * rptB;
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                if (i < rptB) lv[i] = (sr == 0 ? b2v[i] : lv[i]) + ps[i];
+                if (i < rptB) lv[zs][i] = (sr == 0 ? b2v[i] : lv[zs][i]) + ps[i];
             }
             release_job(jb[zs]);
             const bool vz = bvalid && c.active[fb] != 0 && c.t[fb] + zs < c.len[fb];
             const int e = c.n_eval[fb] + zs;     // index of this evaluation in the utterance's sequence
-            float m = -INFINITY, sx = 0.f;
+            float m = -INFINITY;
             int am = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              if (i < rptB && lv[i] > m) { m = lv[i]; am = vB0 + fw * rptB + i; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (i < rptB) sx += expf(lv[i] - m);
-            if (p.trace && vz && e < p.trace_cap) {
-              float* tr = p.trace + ((size_t)fb * p.trace_cap + e) * V + vB0 + fw * rptB;
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (i < rptB) tr[i] = lv[i];
-            }
+              if (i < rptB && lv[zs][i] > m) { m = lv[zs][i]; am = vB0 + fw * rptB + i; }
             // the 4 lanes of a batch row hold ascending vocabulary slices: strict > keeps the first maximum (torch.max)
 #pragma unroll
             for (int o = 1; o < 4; o <<= 1) {
-              const float m2 = __shfl_down_sync(0xffffffffu, m, o), s2 = __shfl_down_sync(0xffffffffu, sx, o);
+              const float m2 = __shfl_down_sync(0xffffffffu, m, o);
               const int am2 = __shfl_down_sync(0xffffffffu, am, o);
-              if ((fw & (2 * o - 1)) == 0) {
-                if (m2 > m) { sx = sx * expf(m - m2) + s2; m = m2; am = am2; }
-                else sx += s2 * expf(m2 - m);
-              }
+              if ((fw & (2 * o - 1)) == 0 && m2 > m) { m = m2; am = am2; }
             }
             if (vz && e < p.max_steps) {
               unsigned u = __float_as_uint(m);
               u ^= (u & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u;
               keys[zs] = ((unsigned long long)u << 32) | (unsigned long long)(((0x7FFFFFFFu - (unsigned)am) << 1) | ktag);
-              if (fw == 0) *reinterpret_cast<float2*>(p.part + (((size_t)e * D2_G + cta) * D2_NB + fb) * 2) = make_float2(m, sx);
             }
           }
         }
+        // second pass, off the chain: softmax partials (max, sum exp) of my vocabulary rows for the log-probability
+        // post-pass, optional logit trace
+        auto second_pass = [&]() {
+#pragma unroll
+        for (int zs = 0; zs < D2_MAXS; ++zs) {
+          if (zs < NS) {
+            const bool vz = bvalid && c.active[fb] != 0 && c.t[fb] + zs < c.len[fb];
+            const int e = c.n_eval[fb] + zs;
+            float m = -INFINITY, sx = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < rptB && lv[zs][i] > m) m = lv[zs][i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < rptB) sx += expf(lv[zs][i] - m);
+            if (p.trace && vz && e < p.trace_cap) {
+              float* tr = p.trace + ((size_t)fb * p.trace_cap + e) * V + vB0 + fw * rptB;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i < rptB) tr[i] = lv[zs][i];
+            }
+#pragma unroll
+            for (int o = 1; o < 4; o <<= 1) {
+              const float m2 = __shfl_down_sync(0xffffffffu, m, o), s2 = __shfl_down_sync(0xffffffffu, sx, o);
+              if ((fw & (2 * o - 1)) == 0) {
+                if (m2 > m) { sx = sx * expf(m - m2) + s2; m = m2; }
+                else sx += s2 * expf(m2 - m);
+              }
+            }
+            if (vz && e < p.max_steps && fw == 0)
+              *reinterpret_cast<float2*>(p.part + (((size_t)e * D2_G + cta) * D2_NB + fb) * 2) = make_float2(m, sx);
+          }
+        }
+        };
+        if (!(p.tune & 2)) second_pass();
         // Arg-max exchange in two hops: every CTA hands its keys to the cluster leader through DSMEM (st.async, 117 ns), the
         // leader folds the four and publishes ONE tagged entry per (frame, utterance pair); every CTA then reads the 32-cluster
         // table of all look-ahead frames in a single pass (8 chunks per thread at two frames).
@@ -478,6 +515,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
 #pragma unroll
               for (int i = 0; i < 4; ++i) r[zs][i] = ld_relaxed_v4(src + ((size_t)zs * D2_NCL + 8 * i) * D2_NB);
             }
+          if (p.tune & 2) second_pass();   // while the table loads are in flight
           for (;;) {
             uint32_t bad = 0;
 #pragma unroll
@@ -516,8 +554,29 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
       // ---------------- R: greedy rule (models.py:408-437), identical in every CTA ----------------
       // consumes the look-ahead evaluations in order: a blank moves on to the next frame (whose evaluation is already there),
       // the first non-blank ends the step for the utterance (its predictor state changes)
+      int tok_pre = -1;
       {
-        if (step > 0) mbar_wait(ctlack, (step - 1) & 1);
+        // every thread replays the rule for ITS utterance on the reduced keys (read-only) to learn the token it will emit, and
+        // requests that token's table row now: the L2 round trip overlaps warp 0's rule and the barrier behind it
+        if (p.tune & 4) {
+          int tokc = -1;
+          if (bvalid && c.active[fb] != 0) {
+            int tl = c.t[fb];
+            const int ln = c.len[fb];
+#pragma unroll
+            for (int zs = 0; zs < D2_MAXS; ++zs) {
+              if (zs < NS && tokc < 0 && tl < ln) {
+                unsigned long long key = 0ull;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) key = c.kred[zs][g][fb] > key ? c.kred[zs][g][fb] : key;
+                const int am2 = (int)(0x7FFFFFFFu - (unsigned)((key & 0xFFFFFFFFull) >> 1));
+                if (am2 == w.blank) ++tl; else tokc = am2;
+              }
+            }
+          }
+          if (tokc >= 0) load_table0(tokc, vpre);
+          tok_pre = tokc;
+        }
         if (et < B) {
           const int bb = et;
           unsigned char emit = 0;
@@ -555,16 +614,23 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
           const unsigned ae = __ballot_sync(0xffffffffu, et < B && c.emit[et] != 0);
           const unsigned aa = __ballot_sync(0xffffffffu, et < B && c.active[et] != 0);
           if (lane == 0) {
+            // The six GEMM-side warps have read the previous flags.  ONLY this thread waits on ctlack: it is also the one whose
+            // ctlbar arrive lets the next ctlack phase begin, so it cannot be lapped.  (All 128 epilogue threads used to wait here;
+            // a warp that reached the wait late -- after this thread had already published the step and the six acks had come in --
+            // saw the parity of the NEXT completed phase and spun forever: a hang about once in 100 full-size calls once other
+            // work was placed in front of the wait.  Phase-lapping rule)
+            if (step > 0) mbar_wait(ctlack, (step - 1) & 1);
             c.flags[0] = ae != 0u; c.flags[1] = aa != 0u;
             mbar_arrive(ctlbar);
           }
+          __syncwarp();
         }
         named_bar_sync(1, 128);
       }
       const bool any_emit = c.flags[0] != 0, any_active = c.flags[1] != 0;
       stamp(3);
       if (any_emit) {
-        phase_c0();
+        phase_c0(tok_pre);
         stamp(4);
         phase_c1();
         stamp(5);

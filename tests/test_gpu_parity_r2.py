@@ -229,3 +229,26 @@ def test_forward_lattice_and_rnnt_loss():
         Tn, Un = int(xl2[n]), int(yl2[n]) + 1
         assert float((r["lattice"][n, :Tn, :Un].cpu() - lat2[n, :Tn, :Un]).abs().max()) < 3e-4
     np.testing.assert_allclose(r["loss"].cpu().numpy(), RL.rnnt_loss(lat2, y2.numpy(), xl2.numpy(), yl2.numpy()), atol=2e-2, rtol=1e-4)
+
+
+@pytest.mark.timeout(180, method="thread")
+def test_soak_full_size_batches_do_not_stall_and_stay_deterministic():
+    """Regression test for a phase-lapping hang of decode_tc2_kernel (all 128 epilogue threads used to wait on the `ctlack`
+    mbarrier whose next phase one of them could start: a late warp spun forever about once in 100 full-size calls).
+    300 back-to-back calls on the bench workload (32 x 10 s, 8 rotated batches); every repeat of a batch must reproduce
+    its tokens."""
+    from libreasr_b200 import synth
+
+    cfg, sd, m, orc = model_for("cfg2")
+    eng = m.engine()
+    n = 160000
+    base = weights.make_audio(32, n, seed=synth.BENCH_AUDIO_SEED)
+    batches = [torch.from_numpy(np.roll(base, 997 * r, axis=1).copy()).cuda() for r in range(8)]
+    first = {}
+    for i in range(300):
+        r = eng.transcribe(batches[i % 8], max_iters=3)
+        got = (r["ntok"].tolist(), r["tokens"][:, :8].tolist())
+        if i % 8 in first:
+            assert got == first[i % 8], f"call {i}"
+        first[i % 8] = got
+    assert sum(sum(f[0]) for f in first.values()) > 0
