@@ -241,6 +241,22 @@ int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, c
                                   int32_t* tokens_out_host, int32_t U_cap, int32_t* ntok_out_host,
                                   double* neg_logp_out_host, void* stream);
 
+/* Two-deep pipeline over the same path, for throughput (the analogue of the reference's request thread pool,
+ * api-server.py:138-139, which keeps several Transcribe calls in flight).  submit() queues one batch: `audio` / `lens` are
+ * host buffers (pinned for full speed) when on_host != 0, device buffers otherwise, complete in `stream` order.  Its
+ * host->device copy and front end run on an internal low-priority stream under the recurrent kernels of the batch
+ * submitted before it (which occupy 128 of the 148 SMs); encoder and decode follow in submission order on an internal
+ * high-priority stream and the results are copied to the HOST buffers given here.  collect() blocks until they are there.
+ * slot is 0 or 1; a slot must be collected before it is submitted again, and the plain transcribe / stream_push calls
+ * refuse to run while a slot is in flight (shared workspaces).  Results are identical to rnnt_b200_transcribe_host. */
+int32_t rnnt_b200_pipeline_submit(rnnt_b200_handle h, const float* audio, int32_t on_host, const int32_t* lens,
+                                  int32_t B, int64_t n, int32_t max_iters, int32_t slot,
+                                  int32_t* tokens_host, int32_t U_cap, int32_t* ntok_host,
+                                  double* neg_logp_host, void* stream);
+int32_t rnnt_b200_pipeline_collect(rnnt_b200_handle h, int32_t slot);
+/* Non-blocking probe: *front_done / *back_done become 1 when that half of the slot's batch has finished on the device. */
+int32_t rnnt_b200_pipeline_query(rnnt_b200_handle h, int32_t slot, int32_t* front_done, int32_t* back_done);
+
 /* ---- streaming sessions: a14 + the serving loop around it ------------------------------------- */
 
 /* B concurrent streams, one chunk per (active) stream per push, each in its own phase: the reference's serving

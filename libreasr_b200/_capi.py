@@ -57,6 +57,9 @@ SIGNATURES = {
     "rnnt_b200_decode_greedy": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "rnnt_b200_transcribe": (_i32, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "rnnt_b200_transcribe_host": (_i32, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "rnnt_b200_pipeline_submit": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "rnnt_b200_pipeline_collect": (_i32, [_vp, _i32]),
+    "rnnt_b200_pipeline_query": (_i32, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "rnnt_b200_stream_open": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
     "rnnt_b200_stream_push": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _vp, C.POINTER(_i32), _vp]),
     "rnnt_b200_decode_beam": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),

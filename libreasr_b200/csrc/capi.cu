@@ -108,6 +108,15 @@ struct rnnt_b200_handle_s {
   // transcribe_host: copy engine stream + events so that the H2D of utterance block i+1 overlaps the front end of block i
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // two-deep pipeline over the whole path (rnnt_b200_pipeline_submit / _collect): the front half of batch i+1 (host->device
+  // copy, front end) runs on a low-priority stream under the persistent recurrent kernels of batch i, which leave 20 SMs idle
+  struct PipeSlot {
+    DevBuf audio, feats, lens, tokens, ntok, nlp;
+    cudaEvent_t in_ready = nullptr, front_done = nullptr, back_done = nullptr;
+    bool busy = false;
+  };
+  PipeSlot pipe[2];
+  cudaStream_t pipe_front = nullptr, pipe_back = nullptr;
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t*> evsets;  // one set of events per profiled transcribe() call: 6 stage marks + 2 per encoder layer
@@ -322,6 +331,13 @@ int32_t rnnt_b200_destroy(rnnt_b200_handle h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (cudaEvent_t e : h->copy_ev)
     if (e) cudaEventDestroy(e);
+  for (auto& ps : h->pipe) {
+    for (DevBuf* b : {&ps.audio, &ps.feats, &ps.lens, &ps.tokens, &ps.ntok, &ps.nlp}) b->release();
+    for (cudaEvent_t e : {ps.in_ready, ps.front_done, ps.back_done})
+      if (e) cudaEventDestroy(e);
+  }
+  if (h->pipe_front) cudaStreamDestroy(h->pipe_front);
+  if (h->pipe_back) cudaStreamDestroy(h->pipe_back);
   for (cudaEvent_t* set : h->evsets) {
     for (int i = 0; i < kEvPerSet; ++i) cudaEventDestroy(set[i]);
     delete[] set;
@@ -1473,6 +1489,8 @@ static int32_t transcribe_impl(rnnt_b200_handle h, const float* audio, const flo
                                int32_t max_iters, int32_t* tokens_out, int32_t U_cap, int32_t* ntok_out, double* neg_logp_out,
                                uint8_t* iters_out, void* stream) {
   if (int r = check_ready(h)) return r;
+  if (h->pipe[0].busy || h->pipe[1].busy)
+    return fail(h, RNNT_B200_ERR_STATE, "transcribe: a pipelined batch is in flight on this handle (shared workspaces); collect it first");
   const rnnt_b200_config& c = h->cfg;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t T = num_steps(c, n);
@@ -1553,6 +1571,105 @@ int32_t rnnt_b200_transcribe_host(rnnt_b200_handle h, const float* audio_host, c
   CK(cudaMemcpyAsync(ntok_host, h->t_ntok.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   if (neg_logp_host) CK(cudaMemcpyAsync(neg_logp_host, h->t_nlp.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return RNNT_B200_OK;
+}
+
+// ---------------- two-deep pipeline over the whole path ----------------
+// The persistent recurrent kernels (4 LSTM layers + the decode loop: ~90 % of a batch) occupy 128 of the 148 SMs with one CTA
+// each and all of their shared memory; the copy engines and the other 20 SMs idle meanwhile.  submit() therefore queues the
+// front half of a batch (host->device copy, STFT / mel / stack) on a low-priority stream, where it runs under the recurrent
+// kernels of the batch submitted before it, and the back half (encoder, decode, results to the host) on a high-priority
+// stream in submission order.  The serving analogue in the reference is its request thread pool (api-server.py:138-139).
+int32_t rnnt_b200_pipeline_submit(rnnt_b200_handle h, const float* audio, int32_t on_host, const int32_t* lens, int32_t B, int64_t n,
+                                  int32_t max_iters, int32_t slot, int32_t* tokens_host, int32_t U_cap, int32_t* ntok_host,
+                                  double* neg_logp_host, void* stream) {
+  if (int r = check_ready(h)) return r;
+  if (!audio || !tokens_host || !ntok_host || B < 1 || n < 1 || U_cap < 1 || slot < 0 || slot > 1)
+    return fail(h, RNNT_B200_ERR_INVALID, "pipeline_submit: bad arguments");
+  rnnt_b200_handle_s::PipeSlot& s = h->pipe[slot];
+  if (s.busy) return fail(h, RNNT_B200_ERR_STATE, "pipeline_submit: slot still in flight; collect it first");
+  const rnnt_b200_config& c = h->cfg;
+  const int64_t T = num_steps(c, n);
+  if (T < 1) return fail(h, RNNT_B200_ERR_INVALID, "pipeline_submit: input shorter than one stacked row");
+  // RNNT_PIPE_PRIO=0: both internal streams at the same priority and cooperative launches kept (the front-end blocks then
+  // compete with the GEMM blocks of the batch ahead); RNNT_PIPE_SAME=1: no overlap at all (front half on the back stream)
+  static const int prio = [] { const char* e = getenv("RNNT_PIPE_PRIO"); return e ? atoi(e) : 1; }();
+  static const int same = [] { const char* e = getenv("RNNT_PIPE_SAME"); return e ? atoi(e) : 0; }();
+  if (!h->pipe_front) {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least urgent (numerically greatest), hi = most urgent
+    CK(cudaStreamCreateWithPriority(&h->pipe_front, cudaStreamNonBlocking, lo));
+    CK(cudaStreamCreateWithPriority(&h->pipe_back, cudaStreamNonBlocking, prio ? hi : lo));
+    for (auto& ps : h->pipe)
+      for (cudaEvent_t* e : {&ps.in_ready, &ps.front_done, &ps.back_done}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  const size_t X = (size_t)c.n_mels * c.n_stack;
+  if (on_host) CK(s.audio.ensure((size_t)B * n * 4));
+  CK(s.feats.ensure((size_t)B * T * X * 4));
+  CK(s.lens.ensure((size_t)B * 4 * 2));
+  CK(s.tokens.ensure((size_t)B * U_cap * 4));
+  CK(s.ntok.ensure((size_t)B * 4));
+  CK(s.nlp.ensure((size_t)B * 8));
+  CK(h->t_enc.ensure((size_t)B * T * c.hidden_sz * 4));
+  cudaStream_t st = (cudaStream_t)stream, fs = same ? h->pipe_back : h->pipe_front, bs = h->pipe_back;
+  CK(cudaEventRecord(s.in_ready, st));   // the caller's inputs are complete in `stream` order
+  CK(cudaStreamWaitEvent(fs, s.in_ready, 0));
+  const float* a_dev = audio;
+  const int32_t* lens_dev = lens;
+  if (on_host) {
+    CK(cudaMemcpyAsync(s.audio.p, audio, (size_t)B * n * 4, cudaMemcpyHostToDevice, fs));
+    a_dev = s.audio.as<float>();
+    if (lens) {
+      CK(cudaMemcpyAsync(s.lens.p, lens, (size_t)B * 4, cudaMemcpyHostToDevice, fs));
+      lens_dev = s.lens.as<int32_t>();
+    }
+  }
+  if (int r = rnnt_b200_features(h, a_dev, lens_dev, B, n, s.feats.as<float>(), fs)) return r;
+  const int32_t* lens_T = nullptr;
+  if (lens) {
+    int32_t* lt = s.lens.as<int32_t>() + B;
+    LAUNCH(1, launch_lens_to_steps(lens_dev, lt, B, c.hop_length, c.n_stack, c.downsample, (int)T, fs));
+    lens_T = lt;
+  }
+  CK(cudaEventRecord(s.front_done, fs));
+  CK(cudaStreamWaitEvent(bs, s.front_done, 0));
+  h->ev = nullptr;   // no stage events on the pipelined path (stages of consecutive batches overlap)
+  struct CoopOff {   // plain launches for the persistent kernels while the front end of the next batch may be resident (kernels.h)
+    bool prev, act;
+    explicit CoopOff(bool a) : prev(coop_launch_enabled()), act(a) { if (act) set_coop_launch(false); }
+    ~CoopOff() { if (act) set_coop_launch(prev); }
+  } coop_off(prio != 0 && !same);
+  if (int r = rnnt_b200_encode(h, s.feats.as<float>(), lens_T, B, (int)T, nullptr, nullptr, 0, h->t_enc.as<float>(), bs)) return r;
+  if (int r = rnnt_b200_decode_greedy(h, h->t_enc.as<float>(), lens_T, B, (int)T, max_iters, nullptr, nullptr, 0, s.tokens.as<int32_t>(), U_cap,
+                                      s.ntok.as<int32_t>(), s.nlp.as<double>(), nullptr, nullptr, 0, bs))
+    return r;
+  CK(cudaMemcpyAsync(tokens_host, s.tokens.p, (size_t)B * U_cap * 4, cudaMemcpyDeviceToHost, bs));
+  CK(cudaMemcpyAsync(ntok_host, s.ntok.p, (size_t)B * 4, cudaMemcpyDeviceToHost, bs));
+  if (neg_logp_host) CK(cudaMemcpyAsync(neg_logp_host, s.nlp.p, (size_t)B * 8, cudaMemcpyDeviceToHost, bs));
+  CK(cudaEventRecord(s.back_done, bs));
+  s.busy = true;
+  return RNNT_B200_OK;
+}
+
+/* Non-blocking progress probe of a slot: *front_done / *back_done = 1 when that half has finished on the device. */
+int32_t rnnt_b200_pipeline_query(rnnt_b200_handle h, int32_t slot, int32_t* front_done, int32_t* back_done) {
+  if (!h || slot < 0 || slot > 1 || !front_done || !back_done) return fail(h, RNNT_B200_ERR_INVALID, "pipeline_query: bad arguments");
+  rnnt_b200_handle_s::PipeSlot& s = h->pipe[slot];
+  *front_done = *back_done = 0;
+  if (!s.front_done) return RNNT_B200_OK;
+  *front_done = cudaEventQuery(s.front_done) == cudaSuccess;
+  *back_done = cudaEventQuery(s.back_done) == cudaSuccess;
+  cudaGetLastError();
+  return RNNT_B200_OK;
+}
+
+int32_t rnnt_b200_pipeline_collect(rnnt_b200_handle h, int32_t slot) {
+  if (!h || slot < 0 || slot > 1) return fail(h, RNNT_B200_ERR_INVALID, "pipeline_collect: bad arguments");
+  rnnt_b200_handle_s::PipeSlot& s = h->pipe[slot];
+  if (!s.busy) return fail(h, RNNT_B200_ERR_STATE, "pipeline_collect: nothing was submitted on this slot");
+  CK(cudaSetDevice(h->cfg.device));
+  s.busy = false;
+  CK(cudaEventSynchronize(s.back_done));
   return RNNT_B200_OK;
 }
 
@@ -1865,6 +1982,8 @@ int32_t rnnt_b200_stream_push(rnnt_b200_stream s, const float* chunks, int32_t o
   rnnt_b200_handle h = s->h;
   const rnnt_b200_config& c = h->cfg;
   if (!chunks || !advanced) return fail(h, RNNT_B200_ERR_INVALID, "stream_push: null argument");
+  if (h->pipe[0].busy || h->pipe[1].busy)
+    return fail(h, RNNT_B200_ERR_STATE, "stream_push: a pipelined batch is in flight on this handle (shared workspaces); collect it first");
   *advanced = 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int B = s->B, ck = s->chunk;

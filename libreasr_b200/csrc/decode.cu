@@ -587,8 +587,7 @@ cudaError_t configure_decode(int device, int* max_coop_blocks) {
 cudaError_t launch_decode(const DecodeArgs& a, int grid_blocks, cudaStream_t st) {
   DecodeArgs args = a;
   void* kargs[] = {&args};
-  return cudaLaunchCooperativeKernel((void*)decode_greedy_kernel, dim3(grid_blocks), dim3(TG_THREADS), kargs,
-                                     decode_smem_bytes(), st);
+  return launch_persistent((const void*)decode_greedy_kernel, dim3(grid_blocks), dim3(TG_THREADS), kargs, decode_smem_bytes(), st);
 }
 
 cudaError_t launch_gru_layer(const PredictArgs& a, cudaStream_t st) {

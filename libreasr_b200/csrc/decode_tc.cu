@@ -1170,7 +1170,7 @@ cudaError_t launch_decode_tc(const DecodeTcArgs& a, const DecodeTcPlan& pl, cuda
   args.rec_col0 = pl.rec_col0; args.rec_cols = pl.rec_cols;
   args.Ul = pl.Ul; args.NC_L = pl.NC_L; args.G_l = pl.G_l; args.lm_col0 = pl.lm_col0; args.lm_offset = pl.lm_offset;
   void* kargs[] = {&args};
-  cudaError_t e = cudaLaunchCooperativeKernel(a.lm.L > 0 ? (void*)decode_tc_kernel<true> : (void*)decode_tc_kernel<false>, dim3(pl.G), dim3(DT_THREADS), kargs, pl.smem_bytes, st);
+  cudaError_t e = launch_persistent(a.lm.L > 0 ? (const void*)decode_tc_kernel<true> : (const void*)decode_tc_kernel<false>, dim3(pl.G), dim3(DT_THREADS), kargs, pl.smem_bytes, st);
   if (e != cudaSuccess) return e;
   const int nB = (int)ceil_div(a.w.V, pl.NC_B);
   decode_finish_kernel<<<a.B, 1024, 0, st>>>(a.part, a.n_eval, nB, pl.Bq, a.max_steps, a.neg_logp, a.trace ? a.trace_lse : nullptr, a.trace_cap);

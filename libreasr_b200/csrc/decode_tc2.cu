@@ -903,10 +903,9 @@ cudaError_t launch_decode_tc2(const DecodeTc2Args& a, cudaStream_t st) {
   at[1].id = cudaLaunchAttributeCooperative;
   at[1].val.cooperative = 1;
   cfg.attrs = at;
-  // profilers cannot replay a cooperative cluster launch: RNNT_NO_COOP=1 drops the co-residency check of the launch
-  // (the plan has verified with cudaOccupancyMaxActiveClusters that all clusters fit; only use on an otherwise idle GPU)
-  static const bool no_coop = [] { const char* e = getenv("RNNT_NO_COOP"); return e && e[0] == '1'; }();
-  cfg.numAttrs = no_coop ? 1 : 2;
+  // cooperative unless switched off (kernels.h: coop_launch_enabled; the plan has verified with
+  // cudaOccupancyMaxActiveClusters that all clusters fit)
+  cfg.numAttrs = coop_launch_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, decode_tc2_kernel, a);
   if (e != cudaSuccess) return e;
   return launch_decode_finish(a.part, a.n_eval, a.B, D2_G, D2_NB, a.max_steps, a.neg_logp, a.trace, a.trace_lse, a.trace_cap, a.w.V, st);

@@ -4,6 +4,16 @@
 
 namespace rnnt {
 
+// The persistent kernels need their whole grid co-resident (they synchronise across CTAs).  The plans verify that against
+// the occupancy of an empty GPU; the launches normally also carry the cooperative attribute.  The two-deep pipeline
+// (capi.cu: rnnt_b200_pipeline_submit) launches them WITHOUT it: a cooperative launch from a high-priority stream next
+// to a running lower-priority kernel (the front end of the next batch) was measured 4x slower per batch, while a plain
+// launch just fills the SMs as the front-end blocks -- which never wait on anything -- retire.
+// Thread-local: set by the calling thread around its launches.
+bool coop_launch_enabled();
+void set_coop_launch(bool on);
+cudaError_t launch_persistent(const void* fn, dim3 grid, dim3 block, void** kargs, size_t smem, cudaStream_t st);
+
 constexpr int kDecodeMaxBatchWords = 8;   // 256 streams / 32
 
 // ---------------- frontend.cu ----------------

@@ -441,7 +441,7 @@ cudaError_t launch_lstm_layer_tc(const LstmTcArgs& a, const LstmTcPlan& pl, cuda
   args.kps = pl.kps; args.mma_m = pl.mma_m; args.fused = pl.fused; args.pre_offset = pl.pre_offset;
   void* kargs[] = {&args};
   void* fn = pl.fused ? (void*)lstm_layer_tc_kernel<true> : (void*)lstm_layer_tc_kernel<false>;
-  return cudaLaunchCooperativeKernel(fn, dim3(pl.grid), dim3(LT_THREADS), kargs, pl.smem_bytes, st);
+  return launch_persistent(fn, dim3(pl.grid), dim3(LT_THREADS), kargs, pl.smem_bytes, st);
 }
 
 }  // namespace rnnt

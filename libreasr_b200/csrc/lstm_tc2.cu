@@ -362,10 +362,9 @@ cudaError_t launch_lstm_layer_tc2(const LstmTc2Args& a, const LstmTc2Plan& pl, c
   at[1].id = cudaLaunchAttributeCooperative;
   at[1].val.cooperative = 1;
   cfg.attrs = at;
-  // profilers cannot replay a cooperative cluster launch: RNNT_NO_COOP=1 drops the co-residency check of the launch
-  // (the plan has verified with cudaOccupancyMaxActiveClusters that all clusters fit; only use on an otherwise idle GPU)
-  static const bool no_coop = [] { const char* e = getenv("RNNT_NO_COOP"); return e && e[0] == '1'; }();
-  cfg.numAttrs = no_coop ? 1 : 2;
+  // cooperative unless switched off (kernels.h: coop_launch_enabled; the plan has verified with
+  // cudaOccupancyMaxActiveClusters that all clusters fit)
+  cfg.numAttrs = coop_launch_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, lstm_layer_tc2_kernel, args);
 }
 

@@ -416,6 +416,50 @@ class Engine:
                 C.c_void_p(out["neg_logp"].data_ptr()), self._stream()))
         return out
 
+    # ---- two-deep pipeline (throughput): front end of batch i+1 under the recurrent kernels of batch i ----
+    def pipeline_submit(self, audio, slot, lens=None, max_iters=3, out=None):
+        """Queue one batch on pipeline slot 0/1 (rnnt_b200_pipeline_submit).  ``audio`` [B, n] fp32: a CUDA tensor, or a
+        host tensor (pin it) that is copied inside the pipeline.  ``lens`` lives where ``audio`` lives.  Returns the host
+        output dict, valid after ``pipeline_collect(slot)``."""
+        assert audio.dtype == torch.float32 and audio.is_contiguous() and audio.dim() == 2
+        on_host = not audio.is_cuda
+        if lens is not None:
+            assert lens.dtype == torch.int32 and lens.is_cuda == audio.is_cuda
+        B, n = audio.shape
+        U = max_iters * max(self.num_steps(n), 1)
+        if out is None:
+            out = self.alloc_host_outputs(B, U)
+        lens_p = C.c_void_p(lens.data_ptr()) if lens is not None else C.c_void_p(0)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rnnt_b200_pipeline_submit(
+                self._h, C.c_void_p(audio.data_ptr()), 1 if on_host else 0, lens_p, B, n, max_iters, slot,
+                C.c_void_p(out["tokens"].data_ptr()), out["tokens"].shape[1], C.c_void_p(out["ntok"].data_ptr()),
+                C.c_void_p(out["neg_logp"].data_ptr()), self._stream()))
+        return out
+
+    def pipeline_collect(self, slot):
+        self._ck(self.lib.rnnt_b200_pipeline_collect(self._h, slot))
+
+    def pipeline_query(self, slot):
+        """(front_done, back_done) of a slot's batch, without blocking."""
+        f, b = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.rnnt_b200_pipeline_query(self._h, slot, C.byref(f), C.byref(b)))
+        return bool(f.value), bool(b.value)
+
+    def transcribe_pipelined(self, batches, max_iters=3, lens=None):
+        """Run a sequence of [B, n] batches (host or device tensors) through the two-deep pipeline; yields one host
+        output dict per batch, in order."""
+        pending = None
+        for i, a in enumerate(batches):
+            out = self.pipeline_submit(a, i & 1, lens=None if lens is None else lens[i], max_iters=max_iters)
+            if pending is not None:
+                self.pipeline_collect(pending[0])
+                yield pending[1]
+            pending = (i & 1, out, a)   # the input stays referenced until its batch has been collected (asynchronous copy)
+        if pending is not None:
+            self.pipeline_collect(pending[0])
+            yield pending[1]
+
     @staticmethod
     def alloc_host_outputs(B, U, pin=True):
         mk = (lambda *s, dtype: torch.zeros(*s, dtype=dtype).pin_memory()) if pin else (lambda *s, dtype: torch.zeros(*s, dtype=dtype))

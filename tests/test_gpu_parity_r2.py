@@ -252,3 +252,48 @@ def test_soak_full_size_batches_do_not_stall_and_stay_deterministic():
             assert got == first[i % 8], f"call {i}"
         first[i % 8] = got
     assert sum(sum(f[0]) for f in first.values()) > 0
+
+
+@pytest.mark.timeout(240, method="thread")
+@pytest.mark.parametrize("name,B,n", [("tiny", 5, 24000), ("cfg2", 6, 48000), ("cfg2", 32, 160000)])
+def test_two_deep_pipeline_equals_plain_calls(name, B, n):
+    """rnnt_b200_pipeline_submit / _collect (host->device copy and front end of batch i+1 on a side stream under the
+    recurrent kernels of batch i): tokens, counts and scores of every batch equal the plain end-to-end call on the same
+    batch, for host and device inputs and ragged lengths (incl. the bench size, 24 batches back to back); the plain calls
+    refuse to run while a slot is in flight."""
+    cfg, sd, m, orc = model_for(name)
+    eng = m.engine()
+    nb = 5
+    batches = [weights.make_audio(B, n, seed=300 + i) for i in range(nb)]
+    lens = [None, torch.tensor([n - 800 * (b % 7) for b in range(B)], dtype=torch.int32), None, None,
+            torch.tensor([n - 1600 * (b % 3) for b in range(B)], dtype=torch.int32)]
+    want = []
+    for a, l in zip(batches, lens):
+        r = eng.transcribe_host(torch.from_numpy(a).pin_memory(), lens_host=l, max_iters=3)
+        want.append({k: v.clone() for k, v in r.items()})
+    reps = 5 if B == 32 else 1     # the bench size: 25 batches back to back
+    host = [torch.from_numpy(a).pin_memory() for a in batches]
+    got = list(eng.transcribe_pipelined(host * reps, max_iters=3, lens=lens * reps))
+    dev = [h.cuda() for h in host]
+    dlens = [None if l is None else l.cuda() for l in lens]
+    got_dev = list(eng.transcribe_pipelined(dev * reps, max_iters=3, lens=dlens * reps))
+    for j in range(nb * reps):
+        i = j % nb
+        for g in (got[j], got_dev[j]):
+            assert g["ntok"].tolist() == want[i]["ntok"].tolist(), f"batch {j}"
+            for b in range(B):
+                k = int(want[i]["ntok"][b])
+                assert g["tokens"][b, :k].tolist() == want[i]["tokens"][b, :k].tolist(), f"batch {j} utterance {b}"
+            assert torch.equal(g["neg_logp"], want[i]["neg_logp"]), f"batch {j}"
+    assert sum(int(w["ntok"].sum()) for w in want) > 0
+    # a slot in flight blocks the plain path and a second submit on the same slot
+    out = eng.pipeline_submit(host[0], 0)
+    with pytest.raises(RuntimeError):
+        eng.transcribe_host(host[1])
+    with pytest.raises(RuntimeError):
+        eng.pipeline_submit(host[1], 0)
+    eng.pipeline_collect(0)
+    assert out["ntok"].tolist() == want[0]["ntok"].tolist()
+    with pytest.raises(RuntimeError):
+        eng.pipeline_collect(0)
+    eng.transcribe_host(host[1])

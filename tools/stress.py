@@ -4,6 +4,7 @@ stall happened, and a determinism check across repeats of the same input.  STRES
   STRESS_MODE=lm       the same batches with the 4x768 LM fused (round-1 decode kernel with LM)
   STRESS_MODE=b64      64 x 10 s stateless (32-row sub-batches) and RNNT_SUB32=0 style wide launches are chosen by the env
   STRESS_MODE=cfg4     128 x 15 s on the 6x1536 shape (round-1 kernels, CTAs sitting phases out)
+  STRESS_MODE=pipe     the offline workload through rnnt_b200_pipeline_submit / _collect (STRESS_HOST=1: pinned host inputs)
   STRESS_MODE=stream   STRESS_STREAMS (64: round-1 kernels, 32: cluster kernels) concurrent streams through rnnt_b200_stream_push"""
 import os, sys, threading, time
 import numpy as np, torch
@@ -65,6 +66,36 @@ if mode in ("offline", "lm", "b64"):
         assert r not in want or nt == want[r], f"call {i} batch {r}: token counts changed"
         want[r] = nt
     print(f"OK mode={mode} {calls} calls, {(time.time()-t0)*1e3/calls:.3f} ms/call, fp32 decode launches {eng.fp32_decode_launches()}", flush=True)
+elif mode == "pipe":
+    cfg = synth.CONFIGS["cfg2"]
+    eng = Engine(econf(cfg)).load_state_dict(synth.make_state_dict(cfg, 1234))
+    B, n, NR = 32, 160000, 8
+    eng.reserve(B, n)
+    base = synth.make_audio(B, n, seed=synth.BENCH_AUDIO_SEED)
+    host = [torch.from_numpy(np.roll(base, 997 * r, axis=1).copy()).pin_memory() for r in range(NR)]
+    inp = host if os.environ.get("STRESS_HOST", "0") == "1" else [h.cuda() for h in host]
+    want = [eng.transcribe_host(h)["ntok"].tolist() for h in host]
+    U = 3 * eng.num_steps(n)
+    outs = [Engine.alloc_host_outputs(B, U), Engine.alloc_host_outputs(B, U)]
+    torch.cuda.synchronize()
+    t0 = time.time()
+    prev = None
+    for i in range(calls):
+        progress[:] = [time.time(), f"submit {i}"]
+        eng.pipeline_submit(inp[i % NR], i & 1, out=outs[i & 1])
+        if prev is not None:
+            progress[:] = [time.time(), f"collect {prev[1]} (slot states {eng.pipeline_query(0)} {eng.pipeline_query(1)})"]
+            eng.pipeline_collect(prev[0])
+            assert outs[prev[0]]["ntok"].tolist() == want[prev[1] % NR], f"batch {prev[1]}: token counts differ from the plain call"
+        prev = (i & 1, i)
+    eng.pipeline_collect(prev[0])
+    dt = time.time() - t0
+    t0 = time.time()
+    for i in range(min(calls, 200)):
+        progress[:] = [time.time(), f"plain call {i}"]
+        eng.transcribe_host(host[i % NR], out=outs[0]) if inp is host else eng.transcribe(inp[i % NR])
+    torch.cuda.synchronize()
+    print(f"OK mode=pipe {calls} batches, {dt*1e3/calls:.3f} ms/batch pipelined vs {(time.time()-t0)*1e3/min(calls,200):.3f} plain, host inputs={inp is host}", flush=True)
 elif mode == "cfg4":
     cfg = synth.CONFIGS["cfg4"]
     eng = Engine(econf(cfg)).load_state_dict(synth.make_state_dict(cfg, 1234))
