@@ -1277,6 +1277,8 @@ static int32_t decode_greedy_impl(rnnt_b200_handle h, const float* enc, const in
     t.n_spec = std::max(1, std::min(n_spec, decode_tc2_max_spec()));
     static const int dec_tune = [] { const char* e = getenv("RNNT_DEC_TUNE"); return e ? atoi(e) : 6; }();
     t.tune = dec_tune;
+    static const int dec_trig = [] { const char* e = getenv("RNNT_DEC_TRIG"); return e ? atoi(e) : 6; }();
+    t.trig_lanes = std::max(1, std::min(dec_trig, 8));
     t.img_stride = one;
     t.keys = h->dkeys.as<unsigned long long>();
     t.n_eval = reinterpret_cast<int*>(h->dkeys.as<uint8_t>() + decode_tc2_keys_bytes());

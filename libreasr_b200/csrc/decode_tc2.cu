@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decode_tc2_kernel(DecodeTc2Args
       const uint32_t tag = (n >> 1) & 1u;
       const uint8_t* src = img_ptr(img, n) + slice_off + (size_t)lt * 16;
       uint4 r[16];
-      poll_issue<16>(src, 16, tag, r);
+      poll_issue<16>(src, 16, tag, r, p.trig_lanes);
 #pragma unroll
       for (int kb = 0; kb < D2_KS; ++kb, ++ga) {
         poll_validate_kb<16>(src, kb, tag, r);

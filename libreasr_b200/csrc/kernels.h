@@ -296,6 +296,7 @@ struct DecodeTc2Args {
   const uint8_t* r_img[2];
   uint8_t* img[8];                 // tagged activation images g, BN(h0'), h0', h1', z of look-ahead frame 0, 1, ..: 2 buffers of img_stride bytes each
   int n_spec;                      // joint evaluations per utterance and lock-step (1 = none speculative)
+  int trig_lanes;                  // producers (of 8) whose chunk must be visible before the bulk load of a K slice is issued (RNNT_DEC_TRIG, default 6: measured 6.52 ms per batch at 1, 6.36-6.39 at 5-7, 6.42 at 8)
   int tune;                        // bit 1: softmax partials behind the key-table loads; bit 2: table row of the emitted token requested ahead of the rule (RNNT_DEC_TUNE, default 6)
   size_t img_stride;
   unsigned long long* keys;        // [2][128 CTAs][32] packed (logit, index, tag) arg-max keys
