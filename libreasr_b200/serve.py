@@ -350,9 +350,14 @@ class ASRServicer:
             try:
                 for req in request_iterator:
                     data, sr = decode_audio(req)
+                    pcm = tensorize(data)[0]
                     if sr and sr != self.asr.engine.cfg.sample_rate:
-                        raise ValueError(f"streaming expects {self.asr.engine.cfg.sample_rate} Hz frames (got {sr}); resample at the client")
-                    sch.feed(slot, tensorize(data)[0])
+                        # per-frame Resample like the reference's stream pipeline (transforms.py:135-144 applied to every
+                        # frame on its own, testing.yaml:357): an 80 ms frame at any rate becomes one 80 ms chunk at the
+                        # model rate; the engine is shared with the scheduler thread, hence the lock
+                        with self.lock:
+                            pcm = self.asr.engine.resample(torch.as_tensor(pcm, dtype=torch.float32)[None].to(self.asr.engine.device), sr)[0].cpu().numpy()
+                    sch.feed(slot, pcm)
                 sch.close(slot)            # in order: after the last frame's tokens have been delivered
             except Exception as e:  # noqa: BLE001 -- reported to the client below
                 err.append(e)

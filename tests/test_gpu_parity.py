@@ -648,14 +648,28 @@ def test_grpc_streaming_end_to_end():
                     time.sleep(0.001 * (b + 1))
             out.extend(S.decode_transcript(r) for r in stream(gen(), timeout=60))
 
-        outs = [[] for _ in range(3)]
-        ths = [threading.Thread(target=client, args=(b, outs[b])) for b in range(3)]
+        # a fourth client streams 8 kHz frames (80 ms = 640 samples): every frame is resampled on its own, like the reference's
+        # stream pipeline applies Resample per frame (transforms.py:135-144, testing.yaml:357)
+        audio8 = weights.make_audio(1, n_chunks * (CHUNK // 2), seed=79)[0]
+        want16 = np.concatenate([O.resample(torch.from_numpy(audio8[None, j * (CHUNK // 2):(j + 1) * (CHUNK // 2)]), 8000, 16000)[0].numpy()
+                                 for j in range(n_chunks)])
+        assert want16.shape[0] == n_chunks * CHUNK
+
+        def client8(out):
+            def gen():
+                for j in range(n_chunks):
+                    yield S.encode_audio(audio8[j * (CHUNK // 2):(j + 1) * (CHUNK // 2)].astype("<f4").tobytes(), 8000)
+                    time.sleep(0.002)
+            out.extend(S.decode_transcript(r) for r in stream(gen(), timeout=60))
+
+        outs = [[] for _ in range(4)]
+        ths = [threading.Thread(target=client, args=(b, outs[b])) for b in range(3)] + [threading.Thread(target=client8, args=(outs[3],))]
         for t in ths:
             t.start()
         for t in ths:
             t.join(timeout=90)
-        for b in range(3):
-            steps = _oracle_stream_tokens(orc, cfg, audio[b], n_chunks)
+        for b in range(4):
+            steps = _oracle_stream_tokens(orc, cfg, audio[b] if b < 3 else want16, n_chunks)
             want, last, last_diff, y = [], "", "", []
             for new in steps:
                 y = y + new
@@ -668,6 +682,7 @@ def test_grpc_streaming_end_to_end():
                     last_diff = diff
                     want.append(diff)
             assert outs[b] == want, f"client {b}"
+        assert len(outs[3]) > 0
         unary = ch.unary_unary(f"/{S.SERVICE}/Transcribe", request_serializer=ident, response_deserializer=ident)
         x8 = weights.make_audio(1, 12000, seed=78)[0]
         got = S.decode_transcript(unary(S.encode_audio(x8.astype("<f4").tobytes(), 8000), timeout=30))
